@@ -1,0 +1,163 @@
+/*
+ * b200sq — B200-native batched statevector engine: public C ABI.
+ *
+ * This is the drop-in boundary for sQUlearn's statevector hot path.  The reference has no
+ * C/FFI interface of its own (it is 100 % Python); each entry point below states which
+ * reference call it replaces (paths relative to the sQUlearn v0.11.0 source tree).
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` pointer is a CUDA device pointer, every other pointer
+ *     is host memory; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - all device work is enqueued asynchronously on `stream`; nothing synchronises.
+ *   - return value: 0 on success, non-zero error code otherwise; b200sq_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - handles are not thread-safe; use one program handle per host thread.
+ *   - qubit order is little-endian (qubit 0 = least significant bit of the amplitude index),
+ *     i.e. Qiskit / Qulacs order.  A batch of states is `N x 2^n` complex128, one state per row,
+ *     (re, im) interleaved: exactly the (N, 2^n) array FidelityKernelStatevector consumes
+ *     (src/squlearn/kernel/lowlevel_kernel/fidelity_kernel_statevector.py:318-352), up to the
+ *     PennyLane bit reversal documented in INTEGRATION.md.
+ */
+#ifndef B200SQ_PUBLIC_API_H_
+#define B200SQ_PUBLIC_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200SQ_API __attribute__((visibility("default")))
+#else
+#define B200SQ_API
+#endif
+
+#define B200SQ_ABI_VERSION 1
+#define B200SQ_MAX_QUBITS 26
+
+/* Gate vocabulary = the reference's gate table
+ * (src/squlearn/util/pennylane/pennylane_gates.py:56-93; Qulacs subset
+ * src/squlearn/util/qulacs/qulacs_gates.py:105-122).  For controlled gates the first listed
+ * qubit(s) are the control(s) (pennylane_circuit.py:397-401). */
+enum b200sq_gate_kind {
+    B200SQ_ID = 0, B200SQ_H, B200SQ_X, B200SQ_Y, B200SQ_Z, B200SQ_S, B200SQ_SDG, B200SQ_T,
+    B200SQ_TDG, B200SQ_SX,
+    B200SQ_RX, B200SQ_RY, B200SQ_RZ, B200SQ_P, B200SQ_U,
+    B200SQ_CX, B200SQ_CY, B200SQ_CZ, B200SQ_CH, B200SQ_CS, B200SQ_CSX,
+    B200SQ_CP, B200SQ_CRX, B200SQ_CRY, B200SQ_CRZ,
+    B200SQ_SWAP, B200SQ_ISWAP, B200SQ_ECR,
+    B200SQ_RXX, B200SQ_RYY, B200SQ_RZZ, B200SQ_RZX,
+    B200SQ_CCX, B200SQ_CSWAP,
+    B200SQ_NUM_GATE_KINDS
+};
+
+/* How a gate angle depends on the data point.  theta_i = c0 + c1 * f(x[i][feat]).
+ * Replaces the sympy-lambdified angle functions the reference evaluates per gate on (N,)
+ * arrays (pennylane_circuit.py:361-378, :570-579).  The library circuits only use
+ * p, x, p*x, p*arccos(x), p*arctan(x); anything else goes through B200SQ_FN_TABLE. */
+enum b200sq_angle_fn {
+    B200SQ_FN_CONST = 0, /* theta = c0                                   */
+    B200SQ_FN_LINEAR,    /* theta = c0 + c1 * x[feat]                    */
+    B200SQ_FN_ARCCOS,    /* theta = c0 + c1 * arccos(x[feat])            */
+    B200SQ_FN_ARCTAN,    /* theta = c0 + c1 * arctan(x[feat])            */
+    B200SQ_FN_TABLE      /* theta = angle_table[slot * N + i] (device)   */
+};
+
+typedef struct b200sq_gate {
+    int32_t kind;    /* enum b200sq_gate_kind                                   */
+    int32_t q[3];    /* qubits, unused entries = -1                             */
+    int32_t fn;      /* enum b200sq_angle_fn                                    */
+    int32_t feat;    /* feature column for LINEAR / ARCCOS / ARCTAN             */
+    int32_t slot;    /* angle-table row for FN_TABLE                            */
+    int32_t reserved;
+    double c0, c1;   /* angle coefficients (functions of the circuit parameters) */
+    double c2, c3;   /* phi, lambda of the U gate (constants)                   */
+} b200sq_gate;
+
+typedef struct b200sq_program b200sq_program;
+
+/* Gram flags */
+#define B200SQ_GRAM_SYMMETRIC 1u   /* psi_x == psi_y: compute lower-triangle tiles, mirror      */
+#define B200SQ_GRAM_DIAG_ONE 2u    /* symmetric: force K[i][i] = 1.0 (reference default)        */
+#define B200SQ_GRAM_DIAG_ZERO 4u   /* symmetric: leave K[i][i] = 0.0 (reference quirk, "all")   */
+#define B200SQ_GRAM_3M 8u          /* 3-multiplication complex product (fewer flops)            */
+
+B200SQ_API const char* b200sq_last_error(void);
+B200SQ_API int b200sq_abi_version(void);
+
+/* Number of CUDA devices visible; 0 when none (no CPU fallback exists: every compute entry
+ * point then fails with an error). */
+B200SQ_API int b200sq_device_count(void);
+
+/* Compile a gate list (the IR PennyLaneCircuit.build_circuit_instructions produces,
+ * pennylane_circuit.py:249-415) into a pass/round/micro-op plan for the tile kernel.
+ * tile_bits = 0 picks the default (12, or n if smaller). Host-only: needs no GPU. */
+B200SQ_API int b200sq_program_create(int n_qubits, int n_gates, const b200sq_gate* gates, int tile_bits,
+                          b200sq_program** out);
+B200SQ_API void b200sq_program_destroy(b200sq_program* prog);
+
+/* Update the angle coefficients (new circuit parameters) without re-planning.
+ * c0, c1: arrays of n_gates doubles. */
+B200SQ_API int b200sq_program_set_coeffs(b200sq_program* prog, const double* c0, const double* c1);
+
+/* Introspection (host-only; used by tests): number of passes over the state the plan makes,
+ * and a dump of the plan as int32 words (see csrc/plan.hpp for the layout). */
+B200SQ_API int b200sq_program_num_passes(const b200sq_program* prog);
+B200SQ_API int b200sq_program_dump(const b200sq_program* prog, int32_t* buf, int capacity, int* n_written);
+
+/* Apply the program to N data points: psi[v][i][:] = U(x_i; shift_v)|0...0>.
+ * Replaces Executor.pennylane_execute(circuit returning qml.state(), ...) /
+ * qulacs_evaluate_statevector (src/squlearn/util/executor.py:908-939,
+ * src/squlearn/util/qulacs/qulacs_execution.py:45-63).
+ *   x_dev            [N][d] float64 features (row-major), may be NULL when d == 0
+ *   angle_table_dev  [n_slots][N] float64 or NULL
+ *   n_variants       >= 1; variant v adds var_shift[v] to the angle of gate var_gate[v]
+ *                    (var_gate[v] < 0: unshifted).  var_* are HOST arrays (NULL => one
+ *                    unshifted variant).
+ *   psi_dev          [n_variants][N][2^n] complex128 output                                  */
+B200SQ_API int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                    const double* angle_table_dev, int n_variants, const int32_t* var_gate,
+                    const double* var_shift, void* psi_dev, void* stream);
+
+/* Simulate and reduce to Pauli expectation values without keeping the states when the state
+ * fits one tile (n <= tile_bits); otherwise states go through `workspace_dev`.
+ * Replaces the qml.expval stack of PennyLaneCircuit (pennylane_circuit.py:636-658) /
+ * qulacs_evaluate (qulacs_execution.py:11-42) and, with variants, the shifted-circuit batch
+ * of src/squlearn/util/optree/optree_derivative.py:130-158.
+ *   x_mask / z_mask  HOST arrays, one Pauli string per term: bit q of x_mask set for X or Y on
+ *                    qubit q, bit q of z_mask set for Z or Y on qubit q
+ *   out_dev          [n_variants][N][n_terms] float64                                         */
+B200SQ_API int b200sq_simulate_expvals(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                            const double* angle_table_dev, int n_variants,
+                            const int32_t* var_gate, const double* var_shift, int n_terms,
+                            const uint32_t* x_mask, const uint32_t* z_mask, double* out_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Pauli expectation values of states already in device memory: out[i][t] = <psi_i|P_t|psi_i>. */
+B200SQ_API int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int n_terms,
+                   const uint32_t* x_mask, const uint32_t* z_mask, double* out_dev, void* stream);
+
+/* Fidelity Gram matrix K[i][j] = |<psi_x[i] | psi_y[j]>|^2 (FP64 tensor-core contraction with the
+ * modulus-square fused into the epilogue).  Replaces the O(N^2) Python pair loop of
+ * FidelityKernelStatevector.evaluate_kernel_sv (fidelity_kernel_statevector.py:303-310,358-383).
+ *   psi_x_dev [Nx][dim], psi_y_dev [Ny][dim] complex128;  K_dev [Nx][ldk] float64              */
+B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
+                double* K_dev, int64_t ldk, uint32_t flags, void* stream);
+
+/* Gaussian outer kernel of the projected quantum kernel: K[i][j] = exp(-gamma |F_x[i]-F_y[j]|^2)
+ * (src/squlearn/kernel/lowlevel_kernel/projected_quantum_kernel.py:945-973).
+ *   fx_dev [Nx][nf], fy_dev [Ny][nf] float64; K_dev [Nx][ldk] float64                          */
+B200SQ_API int b200sq_rbf(const double* fx_dev, int64_t Nx, const double* fy_dev, int64_t Ny, int nf,
+               double gamma, double* K_dev, int64_t ldk, void* stream);
+
+/* Launch counter: number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches`), and the duration bookkeeping of the last Gram / gate-pass launches is left to
+ * the caller's CUDA events. */
+B200SQ_API int64_t b200sq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SQ_PUBLIC_API_H_ */

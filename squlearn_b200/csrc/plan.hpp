@@ -1,0 +1,311 @@
+// Gate-list -> pass / round / micro-op plan for the tile kernel (host-only C++, no CUDA).
+//
+// A PASS sweeps every state once: each thread team stages a TILE of 2^T amplitudes (the
+// amplitudes that differ only in the T "tile qubits") in shared memory, applies every gate the
+// tile can absorb, and writes the tile back.  Inside a pass, gates are grouped into ROUNDS: in a
+// round every thread holds the 2^nb (nb <= 3) amplitudes spanned by the round's register bits
+// and applies the round's MICRO-OPS to them in registers; rounds are separated by one team
+// barrier.  A gate can be absorbed by a pass when all qubits it acts on NON-diagonally are tile
+// qubits (controls and diagonal gates only read index bits, so they may sit anywhere).
+//
+// Index spaces:  "local" = position inside the tile (0..T-1, tile qubits in ascending order);
+// "ext" = local bits followed by the remaining ("outer") qubits in ascending order, so
+// ext = local | outer_index << T.  All masks / bit positions in micro-ops are ext positions.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sq.h"
+
+namespace b200sq {
+
+enum UopKind : int32_t { UOP_U1 = 0, UOP_U2 = 1, UOP_DIAG = 2 };
+
+struct Uop {         // 32 bytes, copied to the device verbatim
+    int32_t kind;    // UopKind
+    int32_t gate;    // index into the gate table (kind, angle coefficients)
+    int32_t r0, r1;  // U1: r0 = register bit. U2: r0 > r1 register bits (r0 = matrix MSB).
+                     // DIAG: ext positions of the first / second qubit (r1 = -1 for 1-qubit)
+    uint32_t ctrl;   // U1/U2: control mask (ext positions). DIAG: skip mask (bit j: phase j == 1)
+    int32_t mat;     // offset of this op's matrix in the team's matrix area (double2 units)
+    int32_t swap;    // U2: 1 when the gate's first qubit sits on r1 (matrix must be permuted)
+    int32_t pad;
+};
+
+struct Round {       // 24 bytes
+    int32_t nb;      // number of register bits (0..3)
+    int32_t rb[3];   // their tile-local positions, ascending
+    int32_t u0, u1;  // micro-op range
+};
+
+constexpr int kMaxRuns = 8;
+
+struct Pass {
+    int32_t T;               // tile bits
+    int32_t first;           // 1: tile starts as |0..0> (no load)
+    int32_t r0, r1;          // round range
+    int32_t u0, u1;          // micro-op range
+    int32_t mat_elems;       // double2 elements of matrix storage per team
+    int32_t n_lruns, n_oruns;
+    uint32_t lmask[kMaxRuns];  // local-index bit runs -> global amplitude index
+    int32_t lshift[kMaxRuns];
+    uint32_t omask[kMaxRuns];  // outer-index bit runs -> global amplitude index
+    int32_t oshift[kMaxRuns];
+    int32_t tile_qubits[32];   // the T tile qubits (ascending), for introspection / tests
+};
+
+struct GateInfo {
+    int nq;          // number of qubits
+    int nctrl;       // leading control qubits
+    bool diag;       // acts diagonally on all its qubits
+    bool has_angle;
+};
+
+inline GateInfo gate_info(int kind) {
+    switch (kind) {
+        case B200SQ_ID: return {1, 0, true, false};
+        case B200SQ_H: case B200SQ_X: case B200SQ_Y: case B200SQ_SX: return {1, 0, false, false};
+        case B200SQ_Z: case B200SQ_S: case B200SQ_SDG: case B200SQ_T: case B200SQ_TDG:
+            return {1, 0, true, false};
+        case B200SQ_RX: case B200SQ_RY: case B200SQ_U: return {1, 0, false, true};
+        case B200SQ_RZ: case B200SQ_P: return {1, 0, true, true};
+        case B200SQ_CX: case B200SQ_CY: case B200SQ_CH: case B200SQ_CSX: return {2, 1, false, false};
+        case B200SQ_CZ: case B200SQ_CS: return {2, 1, true, false};
+        case B200SQ_CP: case B200SQ_CRZ: return {2, 1, true, true};
+        case B200SQ_CRX: case B200SQ_CRY: return {2, 1, false, true};
+        case B200SQ_SWAP: case B200SQ_ISWAP: case B200SQ_ECR: return {2, 0, false, false};
+        case B200SQ_RXX: case B200SQ_RYY: case B200SQ_RZX: return {2, 0, false, true};
+        case B200SQ_RZZ: return {2, 0, true, true};
+        case B200SQ_CCX: return {3, 2, false, false};
+        case B200SQ_CSWAP: return {3, 1, false, false};
+        default: throw std::invalid_argument("unknown gate kind " + std::to_string(kind));
+    }
+}
+
+struct Plan {
+    int n = 0;
+    int T = 0;
+    std::vector<b200sq_gate> gates;
+    std::vector<Pass> passes;
+    std::vector<Round> rounds;
+    std::vector<Uop> uops;
+};
+
+namespace detail {
+
+struct GMask {
+    uint32_t all = 0;  // every qubit of the gate
+    uint32_t tgt = 0;  // qubits acted on non-diagonally
+};
+
+inline GMask gate_masks(const b200sq_gate& g, int n) {
+    GateInfo gi = gate_info(g.kind);
+    GMask m;
+    for (int k = 0; k < gi.nq; ++k) {
+        int q = g.q[k];
+        if (q < 0 || q >= n) throw std::invalid_argument("gate qubit out of range");
+        if (m.all & (1u << q)) throw std::invalid_argument("gate uses a qubit twice");
+        m.all |= 1u << q;
+        if (!gi.diag && k >= gi.nctrl) m.tgt |= 1u << q;
+    }
+    return m;
+}
+
+inline int popc(uint32_t v) { return __builtin_popcount(v); }
+
+// Build the bit-run tables that scatter a compact index over the set bits of `qmask`.
+inline int make_runs(uint32_t qmask, uint32_t* masks, int32_t* shifts) {
+    int nruns = 0, compact = 0, q = 0;
+    while (q < 32) {
+        if (!(qmask >> q & 1u)) { ++q; continue; }
+        int start = q, len = 0;
+        while (q < 32 && (qmask >> q & 1u)) { ++q; ++len; }
+        if (nruns == kMaxRuns) throw std::runtime_error("tile qubit set has too many runs");
+        masks[nruns] = ((len >= 32 ? 0u : (1u << len)) - 1u) << compact;
+        shifts[nruns] = start - compact;
+        ++nruns;
+        compact += len;
+    }
+    return nruns;
+}
+
+}  // namespace detail
+
+// low_bits: number of lowest qubits every tile must contain (keeps global accesses in
+// contiguous runs of 2^low_bits * 16 bytes).
+inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_bits,
+                      int low_bits = 4) {
+    using namespace detail;
+    if (n < 1 || n > B200SQ_MAX_QUBITS) throw std::invalid_argument("n_qubits out of range");
+    Plan plan;
+    plan.n = n;
+    int T = tile_bits <= 0 ? 12 : tile_bits;
+    if (T > 13) throw std::invalid_argument("tile_bits must be <= 13");
+    T = std::min(T, n);
+    plan.T = T;
+    plan.gates = gates_in;
+    const int G = (int)gates_in.size();
+    std::vector<GMask> gm(G);
+    for (int i = 0; i < G; ++i) gm[i] = gate_masks(gates_in[i], n);
+    // leave room for two freely chosen target qubits; with T == n the tile is the whole state
+    low_bits = (T == n) ? T : std::max(0, std::min(low_bits, T - 2));
+    const uint32_t mandatory = (low_bits >= 32 ? ~0u : (1u << low_bits) - 1u);
+
+    std::vector<int> pending;
+    for (int i = 0; i < G; ++i)
+        if (gates_in[i].kind != B200SQ_ID) pending.push_back(i);
+
+    bool first = true;
+    // A circuit without gates still needs one pass to write |0..0>.
+    while (!pending.empty() || first) {
+        // ---- choose the tile qubit set by first demand
+        uint32_t L = mandatory;
+        {
+            uint32_t blockedT = 0, blockedD = 0;
+            for (int gi : pending) {
+                const GMask& m = gm[gi];
+                bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
+                if (free_ && popc(L | m.tgt) <= T) {
+                    L |= m.tgt;
+                } else {
+                    blockedT |= m.all;
+                    blockedD |= m.tgt;
+                }
+            }
+            for (int q = 0; q < n && popc(L) < T; ++q) L |= 1u << q;
+        }
+        // ---- absorb gates
+        std::vector<int> absorbed, rest;
+        {
+            uint32_t blockedT = 0, blockedD = 0;
+            for (int gi : pending) {
+                const GMask& m = gm[gi];
+                bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
+                if (free_ && (m.tgt & ~L) == 0) {
+                    absorbed.push_back(gi);
+                } else {
+                    rest.push_back(gi);
+                    blockedT |= m.all;
+                    blockedD |= m.tgt;
+                }
+            }
+        }
+        if (absorbed.empty() && !pending.empty())
+            throw std::runtime_error("planner made no progress (gate needs more target qubits than a tile)");
+
+        // ---- ext positions
+        int pos[32];
+        {
+            int c = 0;
+            for (int q = 0; q < n; ++q) if (L >> q & 1u) pos[q] = c++;
+            for (int q = 0; q < n; ++q) if (!(L >> q & 1u)) pos[q] = c++;
+        }
+        Pass ps;
+        std::memset(&ps, 0, sizeof(ps));
+        ps.T = T;
+        ps.first = first ? 1 : 0;
+        ps.n_lruns = make_runs(L, ps.lmask, ps.lshift);
+        uint32_t full = (n >= 32 ? ~0u : (1u << n) - 1u);
+        ps.n_oruns = make_runs(full & ~L, ps.omask, ps.oshift);
+        {
+            int c = 0;
+            for (int q = 0; q < n; ++q) if (L >> q & 1u) ps.tile_qubits[c++] = q;
+        }
+        ps.r0 = (int)plan.rounds.size();
+        ps.u0 = (int)plan.uops.size();
+
+        // ---- pack absorbed gates into rounds (list scheduling with the same hop-over rule)
+        std::vector<char> done(absorbed.size(), 0);
+        size_t n_done = 0;
+        int mat_off = 0;
+        while (n_done < absorbed.size()) {
+            Round rd;
+            std::memset(&rd, 0, sizeof(rd));
+            rd.u0 = (int)plan.uops.size();
+            uint32_t bits = 0;  // local positions of this round's register bits
+            uint32_t blockedT = 0, blockedD = 0;
+            std::vector<int> members;
+            for (size_t a = 0; a < absorbed.size(); ++a) {
+                if (done[a]) continue;
+                const GMask& m = gm[absorbed[a]];
+                uint32_t tl = 0;
+                for (int q = 0; q < n; ++q) if (m.tgt >> q & 1u) tl |= 1u << pos[q];
+                bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
+                if (free_ && popc(bits | tl) <= 3) {
+                    bits |= tl;
+                    members.push_back((int)a);
+                    done[a] = 1;
+                    ++n_done;
+                } else {
+                    blockedT |= m.all;
+                    blockedD |= m.tgt;
+                }
+            }
+            // give rounds without non-diagonal work (pure phase rounds) three low bits so that
+            // each thread still handles eight amplitudes
+            for (int b = 0; b < T && popc(bits) < std::min(3, T); ++b) bits |= 1u << b;
+            rd.nb = popc(bits);
+            {
+                int c = 0;
+                for (int b = 0; b < T; ++b) if (bits >> b & 1u) rd.rb[c++] = b;
+            }
+            auto regbit = [&](int q) {
+                for (int c = 0; c < rd.nb; ++c) if (rd.rb[c] == pos[q]) return c;
+                throw std::logic_error("target qubit is not a register bit");
+            };
+            for (int a : members) {
+                int gi = absorbed[a];
+                const b200sq_gate& g = gates_in[gi];
+                GateInfo info = gate_info(g.kind);
+                Uop u;
+                std::memset(&u, 0, sizeof(u));
+                u.gate = gi;
+                u.mat = mat_off;
+                if (info.diag) {
+                    u.kind = UOP_DIAG;
+                    u.r0 = pos[g.q[0]];
+                    u.r1 = info.nq > 1 ? pos[g.q[1]] : -1;
+                    // phases that are exactly 1: index = bit(q0) | bit(q1) << 1
+                    switch (g.kind) {
+                        case B200SQ_Z: case B200SQ_S: case B200SQ_SDG: case B200SQ_T:
+                        case B200SQ_TDG: case B200SQ_P: u.ctrl = 0x5; break;        // bit(q0)=0
+                        case B200SQ_CZ: case B200SQ_CS: case B200SQ_CP: u.ctrl = 0x7; break;
+                        case B200SQ_CRZ: u.ctrl = 0x5; break;                       // control = 0
+                        default: u.ctrl = 0; break;
+                    }
+                    mat_off += 4;
+                } else if (info.nq - info.nctrl == 1) {
+                    u.kind = UOP_U1;
+                    u.r0 = regbit(g.q[info.nctrl]);
+                    for (int k = 0; k < info.nctrl; ++k) u.ctrl |= 1u << pos[g.q[k]];
+                    mat_off += 4;
+                } else {
+                    u.kind = UOP_U2;
+                    int ra = regbit(g.q[info.nctrl]), rb = regbit(g.q[info.nctrl + 1]);
+                    u.r0 = std::max(ra, rb);
+                    u.r1 = std::min(ra, rb);
+                    u.swap = ra < rb ? 1 : 0;
+                    for (int k = 0; k < info.nctrl; ++k) u.ctrl |= 1u << pos[g.q[k]];
+                    mat_off += 16;
+                }
+                plan.uops.push_back(u);
+            }
+            rd.u1 = (int)plan.uops.size();
+            plan.rounds.push_back(rd);
+        }
+        ps.r1 = (int)plan.rounds.size();
+        ps.u1 = (int)plan.uops.size();
+        ps.mat_elems = mat_off;
+        plan.passes.push_back(ps);
+        pending.swap(rest);
+        first = false;
+    }
+    return plan;
+}
+
+}  // namespace b200sq

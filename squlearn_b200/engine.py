@@ -1,0 +1,234 @@
+"""Device-side engine: thin Python wrapper over the C ABI, with PyTorch used only for device
+memory, streams and host<->device copies.
+
+All arithmetic happens in libb200sq.so's CUDA kernels.  There is no CPU path: constructing an
+:class:`Engine` without a CUDA device (or without the built library) raises.
+"""
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .observables import pauli_masks
+from .program import Program, as_uint32_array
+
+_DIAG_FLAGS = {"one": _lib.GRAM_DIAG_ONE, "zero": _lib.GRAM_DIAG_ZERO, "computed": 0}
+
+
+class CompiledProgram:
+    """A planned gate list living behind a b200sq_program handle."""
+
+    def __init__(self, program: Program, params: Optional[np.ndarray], tile_bits: int = 0):
+        self._lib = _lib.load()
+        self.program = program
+        self._handle = ctypes.c_void_p()
+        gates = program.c_gates(params)
+        _lib.check(self._lib.b200sq_program_create(program.num_qubits, len(program), gates,
+                                                   int(tile_bits), ctypes.byref(self._handle)))
+        self.params = None if params is None else np.array(params, dtype=np.float64)
+
+    @property
+    def handle(self):
+        return self._handle
+
+    @property
+    def num_passes(self) -> int:
+        return self._lib.b200sq_program_num_passes(self._handle)
+
+    def set_params(self, params: Optional[np.ndarray]):
+        """New circuit parameters: only the angle coefficients change, the plan is kept."""
+        c0, c1 = self.program.coefficient_arrays(params)
+        n = max(len(c0), 1)
+        a0 = (ctypes.c_double * n)(*c0)
+        a1 = (ctypes.c_double * n)(*c1)
+        _lib.check(self._lib.b200sq_program_set_coeffs(self._handle, a0, a1))
+        self.params = None if params is None else np.array(params, dtype=np.float64)
+
+    def dump(self) -> np.ndarray:
+        n = ctypes.c_int(0)
+        _lib.check(self._lib.b200sq_program_dump(self._handle, None, 0, ctypes.byref(n)))
+        buf = (ctypes.c_int32 * n.value)()
+        _lib.check(self._lib.b200sq_program_dump(self._handle, buf, n.value, ctypes.byref(n)))
+        return np.frombuffer(buf, dtype=np.int32).copy()
+
+    def __del__(self):
+        try:
+            if self._handle:
+                self._lib.b200sq_program_destroy(self._handle)
+                self._handle = ctypes.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class Engine:
+    """One engine per process / GPU (``device`` = CUDA device index, default: current)."""
+
+    #: cap of the scratch buffer for expectation values of states that do not fit one tile
+    workspace_bytes = 2 << 30
+
+    def __init__(self, device: Optional[int] = None):
+        import torch
+
+        self._torch = torch
+        self._lib = _lib.load()
+        if not torch.cuda.is_available() or self._lib.b200sq_device_count() < 1:
+            raise RuntimeError(
+                "squlearn_b200 needs a CUDA device (built for sm_100a / B200); there is no CPU "
+                "fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", int(device))
+        self._workspace = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, arr, dtype=None):
+        torch = self._torch
+        if isinstance(arr, torch.Tensor):
+            t = arr.to(self.device, dtype=dtype or arr.dtype, non_blocking=True)
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype).to(self.device,
+                                                                           non_blocking=True)
+        return t.contiguous()
+
+    def _features(self, program: Program, x):
+        torch = self._torch
+        xd = self.to_device(x, torch.float64)
+        if xd.dim() == 1:
+            xd = xd.reshape(-1, max(program.num_features, 1))
+        if xd.dim() != 2 or (program.num_features and xd.shape[1] != program.num_features):
+            raise ValueError(
+                f"features must have shape (N, {program.num_features}), got {tuple(xd.shape)}")
+        return xd
+
+    def _table(self, cprog: CompiledProgram, x):
+        prog = cprog.program
+        if not prog.table_gates:
+            return None
+        xh = x.detach().cpu().numpy() if isinstance(x, self._torch.Tensor) else np.asarray(x)
+        return self.to_device(prog.angle_table(np.asarray(xh, dtype=np.float64), cprog.params),
+                              self._torch.float64)
+
+    @staticmethod
+    def _variants(variants):
+        if variants is None:
+            return 1, None, None, None
+        gate_idx, shift = variants
+        gate_idx = np.ascontiguousarray(gate_idx, dtype=np.int32)
+        shift = np.ascontiguousarray(shift, dtype=np.float64)
+        keep = (gate_idx, shift)
+        return (len(gate_idx), gate_idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                shift.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), keep)
+
+    @staticmethod
+    def _masks(terms, n_qubits):
+        xs, zs = [], []
+        for t in terms:
+            if isinstance(t, str):
+                if len(t) != n_qubits:
+                    raise ValueError("Pauli string length does not match the number of qubits")
+                xm, zm = pauli_masks(t)
+            else:
+                xm, zm = t
+            xs.append(xm)
+            zs.append(zm)
+        return as_uint32_array(xs), as_uint32_array(zs)
+
+    # ------------------------------------------------------------------ entry points
+    def compile(self, program: Program, params=None, tile_bits: int = 0) -> CompiledProgram:
+        return CompiledProgram(program, params, tile_bits)
+
+    def simulate(self, cprog: CompiledProgram, x, variants=None):
+        """States of every data point: complex128 tensor (N, 2^n), or (V, N, 2^n) with variants."""
+        torch = self._torch
+        prog = cprog.program
+        xd = self._features(prog, x)
+        n_samples = xd.shape[0]
+        nv, vg, vs, keep = self._variants(variants)
+        table = self._table(cprog, x)
+        with torch.cuda.device(self.device):
+            psi = torch.empty((nv, n_samples, 1 << prog.num_qubits), dtype=torch.complex128,
+                              device=self.device)
+            _lib.check(self._lib.b200sq_simulate(
+                cprog.handle, n_samples, xd.shape[1], xd.data_ptr(),
+                table.data_ptr() if table is not None else None, nv, vg, vs, psi.data_ptr(),
+                self._stream()))
+        return psi if variants is not None else psi[0]
+
+    def simulate_expvals(self, cprog: CompiledProgram, x, terms: Sequence, variants=None):
+        """Pauli expectation values <P_t> of every data point: float64 (N, n_terms) or (V, N, n_terms)."""
+        torch = self._torch
+        prog = cprog.program
+        xd = self._features(prog, x)
+        n_samples = xd.shape[0]
+        nv, vg, vs, keep = self._variants(variants)
+        xm, zm = self._masks(terms, prog.num_qubits)
+        table = self._table(cprog, x)
+        with torch.cuda.device(self.device):
+            out = torch.empty((nv, n_samples, len(terms)), dtype=torch.float64, device=self.device)
+            ws_ptr, ws_bytes = None, 0
+            if cprog.num_passes > 1 or prog.num_qubits > 13:
+                state_bytes = 16 << prog.num_qubits
+                want = min(max(self.workspace_bytes // state_bytes, 1), n_samples) * state_bytes
+                if self._workspace is None or self._workspace.numel() < want:
+                    self._workspace = None
+                    self._workspace = torch.empty(want, dtype=torch.uint8, device=self.device)
+                ws_ptr, ws_bytes = self._workspace.data_ptr(), self._workspace.numel()
+            _lib.check(self._lib.b200sq_simulate_expvals(
+                cprog.handle, n_samples, xd.shape[1], xd.data_ptr(),
+                table.data_ptr() if table is not None else None, nv, vg, vs, len(terms), xm, zm,
+                out.data_ptr(), ws_ptr, ws_bytes, self._stream()))
+        return out if variants is not None else out[0]
+
+    def expvals(self, psi, n_qubits: int, terms: Sequence):
+        torch = self._torch
+        psi = psi.contiguous()
+        if psi.dtype != torch.complex128 or psi.shape[-1] != (1 << n_qubits):
+            raise ValueError("psi must be complex128 with 2^n amplitudes per state")
+        n_states = psi.numel() >> n_qubits
+        xm, zm = self._masks(terms, n_qubits)
+        with torch.cuda.device(self.device):
+            out = torch.empty((n_states, len(terms)), dtype=torch.float64, device=self.device)
+            _lib.check(self._lib.b200sq_expvals(psi.data_ptr(), n_states, n_qubits, len(terms), xm,
+                                                zm, out.data_ptr(), self._stream()))
+        return out.reshape(tuple(psi.shape[:-1]) + (len(terms),))
+
+    def gram(self, psi_x, psi_y=None, diagonal: str = "one", out=None, three_m: bool = False):
+        """K[i, j] = |<psi_x[i]|psi_y[j]>|^2.  ``psi_y=None`` means the symmetric Gram of psi_x;
+        ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy."""
+        torch = self._torch
+        psi_x = psi_x.contiguous()
+        sym = psi_y is None
+        psi_y = psi_x if sym else psi_y.contiguous()
+        if psi_x.dtype != torch.complex128 or psi_y.dtype != torch.complex128:
+            raise ValueError("states must be complex128")
+        if psi_x.dim() != 2 or psi_y.dim() != 2 or psi_x.shape[1] != psi_y.shape[1]:
+            raise ValueError("states must be (N, 2^n) arrays with equal 2^n")
+        nx, ny, dim = psi_x.shape[0], psi_y.shape[0], psi_x.shape[1]
+        flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[diagonal]) if sym else 0
+        if three_m:
+            flags |= _lib.GRAM_3M
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
+            _lib.check(self._lib.b200sq_gram(psi_x.data_ptr(), nx, psi_y.data_ptr(), ny, dim,
+                                             out.data_ptr(), out.stride(0), flags, self._stream()))
+        return out
+
+    def rbf(self, fx, fy, gamma: float):
+        torch = self._torch
+        fx = self.to_device(fx, torch.float64)
+        fy = self.to_device(fy, torch.float64)
+        with torch.cuda.device(self.device):
+            out = torch.empty((fx.shape[0], fy.shape[0]), dtype=torch.float64, device=self.device)
+            _lib.check(self._lib.b200sq_rbf(fx.data_ptr(), fx.shape[0], fy.data_ptr(), fy.shape[0],
+                                            fx.shape[1], float(gamma), out.data_ptr(),
+                                            out.stride(0), self._stream()))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.b200sq_launch_count())

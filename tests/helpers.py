@@ -1,0 +1,77 @@
+"""Shared test helpers: random circuits expressed both as a product Program and as an oracle gate list."""
+
+import numpy as np
+
+import oracle
+from oracle.statevector import Gate
+from squlearn_b200.program import Angle, GateOp, Program
+
+FIXED_1Q = ["h", "x", "y", "z", "s", "sdg", "t", "tdg", "sx", "id"]
+ROT_1Q = ["rx", "ry", "rz", "p"]
+FIXED_2Q = ["cx", "cy", "cz", "ch", "cs", "csx", "swap", "iswap", "ecr"]
+ROT_2Q = ["cp", "crx", "cry", "crz", "rxx", "ryy", "rzz", "rzx"]
+FIXED_3Q = ["ccx", "cswap"]
+
+
+def _oracle_angle(a: Angle):
+    fn = {None: None, "linear": (lambda v: v), "arccos": np.arccos, "arctan": np.arctan}[a.fn]
+
+    def f(x, p, a=a, fn=fn):
+        val = a.scale
+        if a.param is not None:
+            val = val * p[a.param]
+        if a.feature is not None:
+            val = val * fn(x[:, a.feature])
+        return a.offset + val
+
+    return f
+
+
+def random_circuit(n, n_gates, num_params, num_features, rng, kinds=None):
+    """Random circuit over the whole gate vocabulary. Returns (Program, oracle gate list)."""
+    ops, ogates = [], []
+    pool = kinds or (FIXED_1Q + ROT_1Q + ["u"] + (FIXED_2Q + ROT_2Q if n >= 2 else [])
+                     + (FIXED_3Q if n >= 3 else []))
+    for _ in range(n_gates):
+        name = pool[rng.integers(len(pool))]
+        nq = 1 if name in FIXED_1Q + ROT_1Q + ["u"] else (3 if name in FIXED_3Q else 2)
+        qs = tuple(int(q) for q in rng.choice(n, size=nq, replace=False))
+        angle, extra = None, (0.0, 0.0)
+        if name in ROT_1Q + ROT_2Q + ["u"]:
+            mode = rng.integers(4)
+            scale = float(rng.uniform(0.5, 1.5))
+            offset = float(rng.uniform(-0.3, 0.3)) if rng.integers(2) else 0.0
+            if mode == 0:
+                angle = Angle(param=int(rng.integers(num_params)), scale=scale, offset=offset)
+            elif mode == 1:
+                angle = Angle(feature=int(rng.integers(num_features)), fn="linear", scale=scale,
+                              offset=offset)
+            elif mode == 2:
+                angle = Angle(param=int(rng.integers(num_params)),
+                              feature=int(rng.integers(num_features)),
+                              fn=["arccos", "arctan", "linear"][rng.integers(3)], scale=scale)
+            else:
+                angle = Angle(scale=scale, offset=offset)  # constant
+            if name == "u":
+                extra = (float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)))
+        ops.append(GateOp(name, qs, angle, extra))
+        if name == "u":
+            ogates.append(Gate("u", qs, (_oracle_angle(angle), extra[0], extra[1])))
+        elif angle is not None:
+            ogates.append(Gate(name, qs, (_oracle_angle(angle),)))
+        else:
+            ogates.append(Gate(name, qs, ()))
+    return Program(n, ops, num_params, num_features), ogates
+
+
+def program_to_oracle(program: Program):
+    """Oracle gate list of a product Program (used where the oracle has no builder of its own)."""
+    out = []
+    for g in program.gates:
+        if g.name == "u":
+            out.append(Gate("u", g.qubits, (_oracle_angle(g.angle), g.extra[0], g.extra[1])))
+        elif g.angle is not None:
+            out.append(Gate(g.name, g.qubits, (_oracle_angle(g.angle),)))
+        else:
+            out.append(Gate(g.name, g.qubits, ()))
+    return out
