@@ -230,5 +230,13 @@ class Engine:
                                             out.stride(0), self._stream()))
         return out
 
+    def to_host(self, t) -> np.ndarray:
+        """Device -> host through pinned memory (full PCIe rate); the NumPy array owns the buffer."""
+        torch = self._torch
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
     def launch_count(self) -> int:
         return int(self._lib.b200sq_launch_count())

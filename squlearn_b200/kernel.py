@@ -173,7 +173,7 @@ class FidelityKernel(KernelMatrixBase):
     def evaluate(self, x, y=None) -> np.ndarray:
         x = convert_to_float64(x)
         y_in = x if y is None else convert_to_float64(y)
-        kernel_matrix = self.evaluate_device(x, y_in).cpu().numpy()
+        kernel_matrix = self._executor.engine.to_host(self.evaluate_device(x, y_in))
         if self._evaluate_duplicates == "none":
             # identical statevectors are short-circuited to exactly 1.0 by the reference
             # (:365-369,375-378); identical states <=> identical feature rows

@@ -1,0 +1,102 @@
+"""world_size-2 (and 3) gloo tests of the multi-GPU sharding logic on the CPU.
+
+The sharding code is engine-agnostic; here a stand-in engine backed by the ORACLE supplies states
+and Gram blocks (tests may use the oracle; the product never does), so what is tested is the row
+partition, the symmetric half-ring block schedule, the mirror exchange and the final gather."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from squlearn_b200.distributed import (ShardedFidelityKernel, row_partition, sharded_parameter_shift,
+                                       symmetric_block_schedule)
+
+
+def test_row_partition_and_schedule():
+    assert row_partition(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert row_partition(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    for parts in range(1, 10):
+        sched = symmetric_block_schedule(parts)
+        pairs = set()
+        for r, cols in enumerate(sched):
+            for c in cols:
+                key = (min(r, c), max(r, c))
+                assert key not in pairs          # every unordered pair exactly once
+                pairs.add(key)
+        assert len(pairs) == parts * (parts + 1) // 2
+        loads = [len(c) for c in sched]
+        assert max(loads) - min(loads) <= 1      # balanced
+
+
+class _OracleEngine:
+    device = "cpu"
+
+    def gram(self, a, b=None, diagonal="one"):
+        an = a.numpy()
+        if b is None:
+            k = oracle.fidelity_gram_zgemm(an, an, True, "off_diagonal" if diagonal == "one" else "all")
+            if diagonal == "computed":
+                k = np.abs(an.conj() @ an.T) ** 2
+            return torch.from_numpy(k)
+        return torch.from_numpy(np.abs(an.conj() @ b.numpy().T) ** 2)
+
+
+class _OracleExecutor:
+    engine = _OracleEngine()
+
+
+class _OracleKernel:
+    def __init__(self, n, layers, d):
+        self.n, self.d = n, d
+        self.gates = oracle.chebyshev_pqc(n, layers, d)
+        self.p = oracle.chebyshev_pqc_initial_parameters(n, layers, d, seed=0)
+        self._executor = _OracleExecutor()
+
+    def states(self, x):
+        if len(x) == 0:
+            return torch.zeros((0, 2 ** self.n), dtype=torch.complex128)
+        return torch.from_numpy(oracle.simulate(self.gates, self.n, x, self.p))
+
+
+def _worker(rank, world, port, n_points, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        X = rng.uniform(-0.95, 0.95, (n_points, 2))
+        kern = _OracleKernel(4, 2, 2)
+        full = ShardedFidelityKernel(kern).evaluate(X)
+        if rank == 0:
+            np.save(os.path.join(out_dir, f"k_{world}_{n_points}.npy"), full)
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (2, 1)])
+def test_sharded_gram_gloo(tmp_path, world, n_points):
+    mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / f"k_{world}_{n_points}.npy")
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.95, 0.95, (n_points, 2))
+    want = oracle.fidelity_kernel(oracle.chebyshev_pqc(4, 2, 2), 4, X, None,
+                                  oracle.chebyshev_pqc_initial_parameters(4, 2, 2, seed=0))
+    assert got.shape == (n_points, n_points)
+    assert np.max(np.abs(got - want)) < 1e-13
+    assert np.array_equal(got, got.T)
