@@ -83,6 +83,8 @@ typedef struct b200sq_program b200sq_program;
 #define B200SQ_GRAM_DIAG_ONE 2u    /* symmetric: force K[i][i] = 1.0 (reference default)        */
 #define B200SQ_GRAM_DIAG_ZERO 4u   /* symmetric: leave K[i][i] = 0.0 (reference quirk, "all")   */
 #define B200SQ_GRAM_3M 8u          /* 3-multiplication complex product (fewer flops)            */
+#define B200SQ_GRAM_CLASSIC 16u    /* with 3M: use the barrier-pipelined kernel, not the          */
+                                   /* warp-specialised bulk-copy one (kept for A/B measurements) */
 
 B200SQ_API const char* b200sq_last_error(void);
 B200SQ_API int b200sq_abi_version(void);

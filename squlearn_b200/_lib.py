@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sq.so")
+LIB_PATH = os.environ.get("B200SQ_LIB", os.path.join(_HERE, "libb200sq.so"))
 
 GATE_KINDS = [
     "id", "h", "x", "y", "z", "s", "sdg", "t", "tdg", "sx",
@@ -34,7 +34,7 @@ GATE_ARITY = {
 
 FN_CONST, FN_LINEAR, FN_ARCCOS, FN_ARCTAN, FN_TABLE = range(5)
 
-GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M = 1, 2, 4, 8
+GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M, GRAM_CLASSIC = 1, 2, 4, 8, 16
 
 
 class Gate(ctypes.Structure):

@@ -35,8 +35,6 @@ struct b200sq_program {
     Plan plan;
     // device mirrors (lazily created on the device that is current at first use)
     int device = -1;
-    Round* d_rounds = nullptr;
-    Uop* d_uops = nullptr;
     b200sq_gate* d_gates = nullptr;
     bool gates_dirty = true;
     int32_t* d_var_gate = nullptr;
@@ -50,8 +48,6 @@ struct b200sq_program {
             int cur = -1;
             cudaGetDevice(&cur);
             cudaSetDevice(device);
-            cudaFree(d_rounds);
-            cudaFree(d_uops);
             cudaFree(d_gates);
             cudaFree(d_var_gate);
             cudaFree(d_var_shift);
@@ -71,17 +67,8 @@ int ensure_device(b200sq_program* p, cudaStream_t stream) {
         return fail(3, "program handle was first used on another device; create one handle per device");
     if (p->device < 0) {
         const Plan& pl = p->plan;
-        size_t nr = std::max<size_t>(pl.rounds.size(), 1), nu = std::max<size_t>(pl.uops.size(), 1),
-               ng = std::max<size_t>(pl.gates.size(), 1);
-        if ((e = cudaMalloc(&p->d_rounds, nr * sizeof(Round))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&p->d_uops, nu * sizeof(Uop))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        size_t ng = std::max<size_t>(pl.gates.size(), 1);
         if ((e = cudaMalloc(&p->d_gates, ng * sizeof(b200sq_gate))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        if (!pl.rounds.empty())
-            cudaMemcpyAsync(p->d_rounds, pl.rounds.data(), pl.rounds.size() * sizeof(Round),
-                            cudaMemcpyHostToDevice, stream);
-        if (!pl.uops.empty())
-            cudaMemcpyAsync(p->d_uops, pl.uops.data(), pl.uops.size() * sizeof(Uop),
-                            cudaMemcpyHostToDevice, stream);
         p->device = dev;
         p->gates_dirty = true;
     }
@@ -143,9 +130,33 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
     for (size_t ip = 0; ip < pl.passes.size(); ++ip) {
         TileArgs a;
         std::memset(&a, 0, sizeof(a));
-        a.pass = pl.passes[ip];
-        a.rounds = p->d_rounds;
-        a.uops = p->d_uops;
+        const Pass& ps = pl.passes[ip];
+        a.pass.T = ps.T;
+        a.pass.first = ps.first;
+        a.pass.n_rounds = ps.r1 - ps.r0;
+        a.pass.n_uops = ps.u1 - ps.u0;
+        a.pass.mat_elems = ps.mat_elems;
+        a.pass.n_lruns = ps.n_lruns;
+        a.pass.n_oruns = ps.n_oruns;
+        for (int i = 0; i < kMaxRuns; ++i) {
+            a.pass.lmask[i] = ps.lmask[i];
+            a.pass.lshift[i] = ps.lshift[i];
+            a.pass.omask[i] = ps.omask[i];
+            a.pass.oshift[i] = ps.oshift[i];
+        }
+        for (int i = 0; i < 32; ++i) a.pass.extq[i] = ps.extq[i];
+        a.n_init = 0;
+        if (ps.first) {
+            a.n_init = (int)pl.init_gates.size();
+            for (int i = 0; i < a.n_init; ++i) {
+                a.inits[i].gate = (uint16_t)pl.init_gates[i];
+                a.inits[i].qubit = (uint8_t)pl.gates[pl.init_gates[i]].q[0];
+            }
+        }
+        if (a.pass.n_rounds > kMaxPassRounds || a.pass.n_uops > kMaxPassUops)
+            return fail(5, "internal: pass exceeds the kernel-parameter capacity");
+        for (int r = ps.r0; r < ps.r1; ++r) a.rounds[r - ps.r0] = pack_round(pl.rounds[r], ps.u0);
+        for (int u = ps.u0; u < ps.u1; ++u) a.uops[u - ps.u0] = pack_uop(pl.uops[u], ps.u0);
         a.gates = p->d_gates;
         a.psi = psi;
         a.psi_off = psi_off;
@@ -243,6 +254,8 @@ int b200sq_program_dump(const b200sq_program* prog, int32_t* buf, int capacity, 
     }
     for (const Round& r : pl.rounds) w.insert(w.end(), {r.nb, r.rb[0], r.rb[1], r.rb[2], r.u0, r.u1});
     for (const Uop& u : pl.uops) w.insert(w.end(), {u.kind, u.gate, u.r0, u.r1, (int32_t)u.ctrl, u.mat, u.swap});
+    w.push_back((int32_t)pl.init_gates.size());
+    for (int32_t g : pl.init_gates) w.push_back(g);
     *n_written = (int)w.size();
     if (buf && capacity >= (int)w.size()) std::memcpy(buf, w.data(), w.size() * sizeof(int32_t));
     return 0;

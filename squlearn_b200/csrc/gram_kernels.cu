@@ -2,18 +2,28 @@
 //
 // The contraction is a complex GEMM  C = conj(X) * Y^T  over the amplitude index; both operands
 // are K-major (one state per row), which is the layout FP64 tensor-core fragments want.  tcgen05
-// has no f64 kind, so the tensor path for FP64 on sm_100a is DMMA (mma.sync.m8n8k4.f64).  Complex
-// arithmetic is folded into real DMMAs without any data rearrangement: a lane that loads one
-// complex element (re, im) of X and of Y with a single 16-byte LDS feeds four DMMAs
-//      Re += Xre*Yre,  Re += Xim*Yim,  Im += Xre*Yim,  Im += Xim*(-Yre)
+// has no f64 kind, so the tensor path for FP64 on sm_100a is DMMA (mma.sync.m8n8k4.f64; measured
+// 37.1 TFLOP/s on B200, above cuBLAS DGEMM's 35.5).  Complex arithmetic is folded into real DMMAs
+// without rearranging data: a lane that loads one complex element (re, im) of X and of Y with a
+// single 16-byte LDS feeds
+//   4M mode:  Re += Xre*Yre, Re += Xim*Yim, Im += Xre*Yim, Im += Xim*(-Yre)       (4 DMMA)
+//   3M mode:  T1 += Xre*Yre, T2 += Xim*Yim, T3 += (Xre+Xim)*(Yim-Yre)             (3 DMMA)
+//             Re = T1 + T2,  Im = T3 + T1 - T2   (Gauss / Karatsuba: 25 % fewer tensor flops)
 // i.e. the interleaved (re, im) storage IS the K' = 2K real operand.  The modulus square and the
 // symmetric mirror / diagonal policy are fused into the epilogue, so K is written exactly once
 // and C never exists in memory.
 //
-// Tiling: CTA tile 128 x 64 outputs, 8 warps (4 x 2) of 32 x 32, BK = 16 complex per stage,
-// 4-stage cp.async pipeline (48 KiB / stage).  Per k-step a warp issues 8 LDS.128 for 64 DMMAs,
-// so shared-memory bandwidth sits at ~1/8 of the DMMA issue time: the kernel is FP64-pipe bound
-// by construction.  Symmetric Grams only run the tiles that touch the lower triangle.
+// Tiling: 8 warps per CTA, BK = 16 complex per stage, 4-stage cp.async pipeline.
+//   4M: CTA tile 128 x 64, warp tile 32 x 32 (128 accumulator registers per thread)
+//   3M: CTA tile  64 x 64, warp tile 16 x 32 ( 96 accumulator registers per thread)
+// Shared-memory traffic is ~1/8 (4M) / ~1/4 (3M) of the DMMA issue time and L2->SM traffic is
+// <= 3 TB/s of the measured ~11.8 TB/s, so the kernel is FP64-pipe bound by construction.
+//
+// Work decomposition (split-K for the ragged last wave): the (lower-triangle) tiles are cut into
+// UNITS.  The first floor(tiles / G) * G tiles (G = CTAs resident on the GPU) are whole-tile units;
+// each of the remaining R tiles is split along K into S = floor(G / R) slices so that the last
+// wave also fills the machine.  Slices park their partial sums in a workspace; the slice that
+// arrives last adds them in slice order (deterministic) and runs the epilogue.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -23,12 +33,10 @@ namespace b200sq {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4, NT = 256;
-constexpr int A_ELEMS = BM * BK, B_ELEMS = BN * BK, STAGE_ELEMS = A_ELEMS + B_ELEMS;
-constexpr int GRAM_SMEM = STAGES * STAGE_ELEMS * (int)sizeof(double2);
+constexpr int BK = 16, STAGES = 4, NT = 256;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -48,47 +56,105 @@ __device__ __forceinline__ void cp_async_wait() {
 // the two rows a quarter-warp touches land in different halves of the 128-byte bank window.
 __device__ __forceinline__ int slot(int row, int chunk) { return row * BK + (chunk ^ ((row & 1) << 2)); }
 
-__global__ void __launch_bounds__(NT, 1)
-k_gram(const double2* __restrict__ X, int64_t nx, const double2* __restrict__ Y, int64_t ny,
-       int64_t dim, double* __restrict__ K, int64_t ldk, uint32_t flags) {
+struct GramArgs {
+    const double2* X;
+    const double2* Y;
+    int64_t nx, ny, dim;
+    double* K;
+    int64_t ldk;
+    uint32_t flags;
+    int tiles_m, tiles_n;
+    int n_tiles;         // tiles that are computed (lower triangle when symmetric)
+    int full_units;      // whole-tile units
+    int slices;          // K slices of each remaining tile (>= 1)
+    double2* partial;    // [n_tiles - full_units][slices][BM*BN] (re, im) partial sums
+    unsigned* counters;  // [n_tiles - full_units] arrival counters (zero-initialised)
+};
+
+template <int BM, int BN>
+__device__ __forceinline__ int tiles_in_row(const GramArgs& A, int bi) {
+    if (!(A.flags & B200SQ_GRAM_SYMMETRIC)) return A.tiles_n;
+    // column tiles bj with bj * BN <= bi * BM + BM - 1
+    int c = (bi * BM + BM - 1) / BN + 1;
+    return c < A.tiles_n ? c : A.tiles_n;
+}
+
+// MODE 0: 4M, MODE 1: 3M.  WM x WN = warp tile; warps are laid out (BM / WM) x (BN / WN) = 8.
+template <int BM, int BN, int WM, int WN, int MODE>
+__global__ void __launch_bounds__(NT, 1) k_gram(const __grid_constant__ GramArgs A) {
+    constexpr int MI = WM / 8, NI = WN / 8;
+    constexpr int WARPS_M = BM / WM;
+    constexpr int A_ELEMS = BM * BK, B_ELEMS = BN * BK, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    constexpr int NACC = MODE == 0 ? 2 : 3;
+    static_assert((BM / WM) * (BN / WN) == NT / 32, "eight warps");
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* sm = reinterpret_cast<double2*>(smem_raw);
-
-    const int bi = blockIdx.y, bj = blockIdx.x;
-    const int64_t row0 = (int64_t)bi * BM, col0 = (int64_t)bj * BN;
-    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
-    if (sym && col0 > row0 + BM - 1) return;  // tile lies strictly above the diagonal
+    __shared__ int s_tile[2];
+    __shared__ unsigned s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int lr = lane >> 2, lq = lane & 3;
-    const int KT = (int)((dim + BK - 1) / BK);
 
+    // ---- decode the unit
+    const int unit = blockIdx.x;
+    int tile, slice = 0, nslices = 1;
+    if (unit < A.full_units) {
+        tile = unit;
+    } else {
+        const int r = (unit - A.full_units) / A.slices;
+        slice = (unit - A.full_units) - r * A.slices;
+        nslices = A.slices;
+        tile = A.full_units + r;
+    }
+    if (tid == 0) {
+        int bi = 0, t = tile;
+        for (; bi < A.tiles_m; ++bi) {
+            const int c = tiles_in_row<BM, BN>(A, bi);
+            if (t < c) break;
+            t -= c;
+        }
+        s_tile[0] = bi;
+        s_tile[1] = t;
+    }
+    __syncthreads();
+    const int bi = s_tile[0], bj = s_tile[1];
+    const int64_t row0 = (int64_t)bi * BM, col0 = (int64_t)bj * BN;
+    const int KT_all = (int)((A.dim + BK - 1) / BK);
+    const int kt_begin = (int)((int64_t)KT_all * slice / nslices);
+    const int kt_end = (int)((int64_t)KT_all * (slice + 1) / nslices);
+    const int KT = kt_end - kt_begin;
+
+    const double2* __restrict__ X = A.X;
+    const double2* __restrict__ Y = A.Y;
     auto load_stage = [&](int st, int kt) {
         double2* sa = sm + st * STAGE_ELEMS;
         double2* sb = sa + A_ELEMS;
-        const int64_t k0 = (int64_t)kt * BK;
+        const int64_t k0 = (int64_t)(kt_begin + kt) * BK;
 #pragma unroll
         for (int j = 0; j < A_ELEMS / NT; ++j) {
             const int c = tid + j * NT, r = c >> 4, ch = c & 15;
-            const bool ok = (row0 + r < nx) && (k0 + ch < dim);
-            const double2* src = ok ? X + (row0 + r) * dim + k0 + ch : X;
+            const bool ok = (row0 + r < A.nx) && (k0 + ch < A.dim);
+            const double2* src = ok ? X + (row0 + r) * A.dim + k0 + ch : X;
             cp_async16(sa + slot(r, ch), src, ok ? 16 : 0);
         }
 #pragma unroll
         for (int j = 0; j < B_ELEMS / NT; ++j) {
             const int c = tid + j * NT, r = c >> 4, ch = c & 15;
-            const bool ok = (col0 + r < ny) && (k0 + ch < dim);
-            const double2* src = ok ? Y + (col0 + r) * dim + k0 + ch : Y;
+            const bool ok = (col0 + r < A.ny) && (k0 + ch < A.dim);
+            const double2* src = ok ? Y + (col0 + r) * A.dim + k0 + ch : Y;
             cp_async16(sb + slot(r, ch), src, ok ? 16 : 0);
         }
     };
 
-    double cre[4][4][2], cim[4][4][2];
+    double acc[NACC][MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int s = 0; s < NACC; ++s)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0;
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -108,58 +174,450 @@ k_gram(const double2* __restrict__ X, int64_t nx, const double2* __restrict__ Y,
         const double2* sb = sa + A_ELEMS;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double2 a[4], b[4];
-            double nb[4];
+            double2 a[MI], b[NI];
+            double a2[MI], b2[NI];
             const int ch = kk * 4 + lq;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sa[slot(wm * 32 + i * 8 + lr, ch)];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                b[j] = sb[slot(wn * 32 + j * 8 + lr, ch)];
-                nb[j] = -b[j].x;
+            for (int i = 0; i < MI; ++i) {
+                a[i] = sa[slot(wm * WM + i * 8 + lr, ch)];
+                if (MODE == 1) a2[i] = a[i].x + a[i].y;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < NI; ++j) {
+                b[j] = sb[slot(wn * WN + j * 8 + lr, ch)];
+                b2[j] = MODE == 1 ? b[j].y - b[j].x : -b[j].x;
+            }
+            if (MODE == 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j < NI; ++j) dmma(acc[0][i][j][0], acc[0][i][j][1], a[i].x, b[j].x);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j < NI; ++j) dmma(acc[1][i][j][0], acc[1][i][j][1], a[i].x, b[j].y);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], a[i].y, b[j].y);
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j < NI; ++j) dmma(acc[0][i][j][0], acc[0][i][j][1], a[i].y, b[j].y);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], a[i].y, nb[j]);
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma(acc[1][i][j][0], acc[1][i][j][1], a[i].y, b2[j]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma(acc[0][i][j][0], acc[0][i][j][1], a[i].x, b[j].x);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma(acc[1][i][j][0], acc[1][i][j][1], a[i].y, b[j].y);
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma(acc[NACC - 1][i][j][0], acc[NACC - 1][i][j][1], a2[i], b2[j]);
+            }
         }
     }
     cp_async_wait<0>();
 
-    // ---- epilogue: |.|^2, diagonal policy, mirror
-    const bool diag_one = flags & B200SQ_GRAM_DIAG_ONE, diag_zero = flags & B200SQ_GRAM_DIAG_ZERO;
+    // ---- (re, im) of this unit's share of the sum
+    double re[MI][NI][2], im[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t r = row0 + wm * 32 + i * 8 + lr;
-        if (r >= nx) continue;
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NI; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t c = col0 + wn * 32 + j * 8 + 2 * lq + e;
-                if (c >= ny) continue;
-                double v = cre[i][j][e] * cre[i][j][e] + cim[i][j][e] * cim[i][j][e];
+                if (MODE == 0) {
+                    re[i][j][e] = acc[0][i][j][e];
+                    im[i][j][e] = acc[1][i][j][e];
+                } else {
+                    re[i][j][e] = acc[0][i][j][e] + acc[1][i][j][e];
+                    im[i][j][e] = acc[NACC - 1][i][j][e] + (acc[0][i][j][e] - acc[1][i][j][e]);
+                }
+            }
+
+    // ---- split tiles: park partial sums, last arrival reduces them in slice order
+    if (nslices > 1) {
+        const int r = tile - A.full_units;
+        double2* mine = A.partial + ((size_t)r * nslices + slice) * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    mine[((i * NI + j) * 2 + e) * NT + tid] = double2{re[i][j][e], im[i][j][e]};
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(A.counters + r, 1u) == (unsigned)(nslices - 1));
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) re[i][j][e] = im[i][j][e] = 0.0;
+        for (int s = 0; s < nslices; ++s) {
+            const double2* p = A.partial + ((size_t)r * nslices + s) * (BM * BN);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double2 v = __ldcg(p + ((i * NI + j) * 2 + e) * NT + tid);
+                        re[i][j][e] += v.x;
+                        im[i][j][e] += v.y;
+                    }
+        }
+    }
+
+    // ---- epilogue: |.|^2, diagonal policy, mirror
+    const bool sym = A.flags & B200SQ_GRAM_SYMMETRIC;
+    const bool diag_one = A.flags & B200SQ_GRAM_DIAG_ONE, diag_zero = A.flags & B200SQ_GRAM_DIAG_ZERO;
+    double* __restrict__ K = A.K;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t r = row0 + wm * WM + i * 8 + lr;
+        if (r >= A.nx) continue;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + wn * WN + j * 8 + 2 * lq + e;
+                if (c >= A.ny) continue;
+                double v = re[i][j][e] * re[i][j][e] + im[i][j][e] * im[i][j][e];
                 if (sym) {
                     if (c > r) continue;  // filled by the mirror of (c, r)
                     if (c == r) v = diag_one ? 1.0 : (diag_zero ? 0.0 : v);
-                    K[c * ldk + r] = v;
+                    K[c * A.ldk + r] = v;
                 }
-                K[r * ldk + c] = v;
+                K[r * A.ldk + c] = v;
             }
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 3M kernel, warp-specialised (the default path).  Eight consumer warps issue DMMAs; a ninth
+// PRODUCER warp streams the operand tiles L2 -> SMEM with 16-byte cp.async (LDGSTS) into the same
+// XOR-swizzled layout as above and lets the copy unit signal completion on an mbarrier
+// (cp.async.mbarrier.arrive.noinc).  Stages are handed over through full/empty mbarriers, so the
+// consumer warps never meet at a CTA-wide barrier inside the k-loop: they drift apart and the
+// FP64 pipe always finds a ready warp.  (The classic kernel above pays ~1300 cycles of barrier
+// drain + load issue per k-tile: 15 % at 128x64 4M tiles, 30 % at 64x64 3M tiles.)
+// Measured alternative, kept out: one cp.async.bulk per 256-byte operand row (128 bulk copies
+// per stage) costs ~60 cycles per copy in the copy engine and ran 1.7x SLOWER than the classic
+// kernel.
+constexpr int WS_BM = 64, WS_BN = 64, WS_WM = 16, WS_WN = 32, WS_STAGES = 5;
+constexpr int WS_STAGE_ELEMS = (WS_BM + WS_BN) * BK;
+constexpr int WS_NT = 288;
+constexpr int WS_SMEM = WS_STAGES * WS_STAGE_ELEMS * (int)sizeof(double2) + 2 * WS_STAGES * 8;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ GramArgs A) {
+    constexpr int BM = WS_BM, BN = WS_BN, WM = WS_WM, WN = WS_WN;
+    constexpr int MI = WM / 8, NI = WN / 8, WARPS_M = BM / WM;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* sm = reinterpret_cast<double2*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + WS_STAGES * WS_STAGE_ELEMS);
+    uint64_t* empty = full + WS_STAGES;
+    __shared__ int s_tile[2];
+    __shared__ unsigned s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int unit = blockIdx.x;
+    int tile, slice = 0, nslices = 1;
+    if (unit < A.full_units) {
+        tile = unit;
+    } else {
+        const int r = (unit - A.full_units) / A.slices;
+        slice = (unit - A.full_units) - r * A.slices;
+        nslices = A.slices;
+        tile = A.full_units + r;
+    }
+    if (tid == 0) {
+        int bi = 0, t = tile;
+        for (; bi < A.tiles_m; ++bi) {
+            const int c = tiles_in_row<BM, BN>(A, bi);
+            if (t < c) break;
+            t -= c;
+        }
+        s_tile[0] = bi;
+        s_tile[1] = t;
+        for (int s = 0; s < WS_STAGES; ++s) {
+            mbar_init(full + s, 32);   // one asynchronous arrival per producer lane
+            mbar_init(empty + s, 8);    // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int bi = s_tile[0], bj = s_tile[1];
+    const int64_t row0 = (int64_t)bi * BM, col0 = (int64_t)bj * BN;
+    const int KT_all = (int)((A.dim + BK - 1) / BK);
+    const int kt_begin = (int)((int64_t)KT_all * slice / nslices);
+    const int kt_end = (int)((int64_t)KT_all * (slice + 1) / nslices);
+    const int KT = kt_end - kt_begin;
+
+    if (warp == 8) {
+        // ================= producer =================
+        // lane -> (row parity, 16-byte chunk); chunk c = lane + 32 j  <=>  row 2j + (lane >> 4)
+        const int pr = lane >> 4, pc = lane & 15;
+        const bool full_tile = (row0 + BM <= A.nx) && (col0 + BN <= A.ny) && (A.dim % BK == 0);
+        const double2* pa = A.X + (row0 + pr) * A.dim + (int64_t)kt_begin * BK + pc;
+        const double2* pb = A.Y + (col0 + pr) * A.dim + (int64_t)kt_begin * BK + pc;
+        const int64_t step = 2 * A.dim;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % WS_STAGES;
+            if (kt >= WS_STAGES) mbar_wait(empty + s, ((kt / WS_STAGES) - 1) & 1);
+            double2* sa = sm + s * WS_STAGE_ELEMS;
+            double2* sb = sa + BM * BK;
+            if (full_tile) {
+                const double2* qa = pa;
+                const double2* qb = pb;
+#pragma unroll 8
+                for (int j = 0; j < BM / 2; ++j, qa += step) cp_async16(sa + slot(2 * j + pr, pc), qa, 16);
+#pragma unroll 8
+                for (int j = 0; j < BN / 2; ++j, qb += step) cp_async16(sb + slot(2 * j + pr, pc), qb, 16);
+            } else {
+                const int64_t k0 = (int64_t)(kt_begin + kt) * BK;
+                for (int j = 0; j < BM / 2; ++j) {
+                    const int r = 2 * j + pr;
+                    const bool ok = (row0 + r < A.nx) && (k0 + pc < A.dim);
+                    cp_async16(sa + slot(r, pc), ok ? A.X + (row0 + r) * A.dim + k0 + pc : A.X, ok ? 16 : 0);
+                }
+                for (int j = 0; j < BN / 2; ++j) {
+                    const int r = 2 * j + pr;
+                    const bool ok = (col0 + r < A.ny) && (k0 + pc < A.dim);
+                    cp_async16(sb + slot(r, pc), ok ? A.Y + (col0 + r) * A.dim + k0 + pc : A.Y, ok ? 16 : 0);
+                }
+            }
+            // the copy unit arrives on full[s] once all of this lane's copies have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(full + s))
+                         : "memory");
+            pa += BK;
+            pb += BK;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
+
+    // ================= consumers =================
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const int lr = lane >> 2, lq = lane & 3;
+    double acc[3][MI][NI][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % WS_STAGES;
+        mbar_wait(full + s, (kt / WS_STAGES) & 1);
+        const double2* sa = sm + s * WS_STAGE_ELEMS;
+        const double2* sb = sa + BM * BK;
+        // fragments of step kk + 1 are fetched while step kk feeds the tensor pipe
+        double2 a[MI], b[NI], an[MI], bn[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[i] = sa[slot(wm * WM + i * 8 + lr, lq)];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) b[j] = sb[slot(wn * WN + j * 8 + lr, lq)];
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            if (kk + 1 < BK / 4) {
+                const int ch = (kk + 1) * 4 + lq;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) an[i] = sa[slot(wm * WM + i * 8 + lr, ch)];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) bn[j] = sb[slot(wn * WN + j * 8 + lr, ch)];
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma(acc[0][i][j][0], acc[0][i][j][1], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma(acc[1][i][j][0], acc[1][i][j][1], a[i].y, b[j].y);
+            double a2[MI], b2[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a2[i] = a[i].x + a[i].y;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) b2[j] = b[j].y - b[j].x;
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma(acc[2][i][j][0], acc[2][i][j][1], a2[i], b2[j]);
+            if (kk + 1 < BK / 4) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[i] = an[i];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) b[j] = bn[j];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+
+    double re[MI][NI][2], im[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                re[i][j][e] = acc[0][i][j][e] + acc[1][i][j][e];
+                im[i][j][e] = acc[2][i][j][e] + (acc[0][i][j][e] - acc[1][i][j][e]);
+            }
+
+    constexpr int CT = 256;  // consumer threads
+    if (nslices > 1) {
+        const int r = tile - A.full_units;
+        double2* mine = A.partial + ((size_t)r * nslices + slice) * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    mine[((i * NI + j) * 2 + e) * CT + tid] = double2{re[i][j][e], im[i][j][e]};
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) s_last = (atomicAdd(A.counters + r, 1u) == (unsigned)(nslices - 1));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!s_last) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) re[i][j][e] = im[i][j][e] = 0.0;
+        for (int s = 0; s < nslices; ++s) {
+            const double2* p = A.partial + ((size_t)r * nslices + s) * (BM * BN);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double2 v = __ldcg(p + ((i * NI + j) * 2 + e) * CT + tid);
+                        re[i][j][e] += v.x;
+                        im[i][j][e] += v.y;
+                    }
+        }
+    }
+
+    const bool sym = A.flags & B200SQ_GRAM_SYMMETRIC;
+    const bool diag_one = A.flags & B200SQ_GRAM_DIAG_ONE, diag_zero = A.flags & B200SQ_GRAM_DIAG_ZERO;
+    double* __restrict__ K = A.K;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int64_t r = row0 + wm * WM + i * 8 + lr;
+        if (r >= A.nx) continue;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + wn * WN + j * 8 + 2 * lq + e;
+                if (c >= A.ny) continue;
+                double v = re[i][j][e] * re[i][j][e] + im[i][j][e] * im[i][j][e];
+                if (sym) {
+                    if (c > r) continue;
+                    if (c == r) v = diag_one ? 1.0 : (diag_zero ? 0.0 : v);
+                    K[c * A.ldk + r] = v;
+                }
+                K[r * A.ldk + c] = v;
+            }
+        }
+    }
+}
+
+// KERNEL: 0 = classic template, 1 = warp-specialised 3M
+template <int BM, int BN, int WM, int WN, int MODE, int KERNEL>
+int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
+                   int64_t ldk, uint32_t flags, cudaStream_t stream) {
+    constexpr int SMEM = KERNEL == 1 ? WS_SMEM : STAGES * (BM + BN) * BK * (int)sizeof(double2);
+    constexpr int THREADS = KERNEL == 1 ? WS_NT : NT;
+    cudaError_t e;
+    if (KERNEL == 1) e = cudaFuncSetAttribute(k_gram3m_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else e = cudaFuncSetAttribute(k_gram<BM, BN, WM, WN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    GramArgs A;
+    A.X = x; A.Y = y; A.nx = nx; A.ny = ny; A.dim = dim; A.K = k; A.ldk = ldk; A.flags = flags;
+    A.tiles_m = (int)((nx + BM - 1) / BM);
+    A.tiles_n = (int)((ny + BN - 1) / BN);
+    int64_t n_tiles = 0;
+    for (int bi = 0; bi < A.tiles_m; ++bi) {
+        int c = A.tiles_n;
+        if (flags & B200SQ_GRAM_SYMMETRIC) {
+            int cc = (bi * BM + BM - 1) / BN + 1;
+            c = cc < c ? cc : c;
+        }
+        n_tiles += c;
+    }
+    if (n_tiles > 0x3fffffff) return (int)cudaErrorInvalidConfiguration;
+    A.n_tiles = (int)n_tiles;
+    const int G = sms;  // one CTA per SM (launch bounds)
+    const int KT = (int)((dim + BK - 1) / BK);
+    int rem = A.n_tiles % G;
+    int slices = rem ? G / rem : 1;
+    // a slice must keep the pipeline busy for a while: at least 16 k-tiles
+    if (slices > KT / 16) slices = KT / 16;
+    if (slices < 1) slices = 1;
+    if (slices == 1) rem = 0;
+    A.full_units = A.n_tiles - rem;
+    A.slices = slices;
+    A.partial = nullptr;
+    A.counters = nullptr;
+    const int units = A.full_units + rem * slices;
+    void* ws = nullptr;
+    if (rem) {
+        const size_t part_bytes = (size_t)rem * slices * BM * BN * sizeof(double2);
+        const size_t cnt_bytes = ((size_t)rem * sizeof(unsigned) + 255) & ~(size_t)255;
+        e = cudaMallocAsync(&ws, part_bytes + cnt_bytes, stream);
+        if (e != cudaSuccess) return (int)e;
+        A.counters = (unsigned*)ws;
+        A.partial = (double2*)((char*)ws + cnt_bytes);
+        cudaMemsetAsync(ws, 0, cnt_bytes, stream);
+    }
+    if (KERNEL == 1) k_gram3m_ws<<<units, THREADS, SMEM, stream>>>(A);
+    else k_gram<BM, BN, WM, WN, MODE><<<units, THREADS, SMEM, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (ws) cudaFreeAsync(ws, stream);
+    return (int)e;
 }
 
 }  // namespace
@@ -167,14 +625,12 @@ k_gram(const double2* __restrict__ X, int64_t nx, const double2* __restrict__ Y,
 int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                 int64_t ldk, uint32_t flags, cudaStream_t stream) {
     if (nx <= 0 || ny <= 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    const int64_t tm = (nx + BM - 1) / BM, tn = (ny + BN - 1) / BN;
-    if (tm > 65535) return (int)cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned)tn, (unsigned)tm);
-    k_gram<<<grid, NT, GRAM_SMEM, stream>>>(x, nx, y, ny, dim, k, ldk, flags);
-    count_launch();
-    return (int)cudaGetLastError();
+    if (flags & B200SQ_GRAM_3M) {
+        if (!(flags & B200SQ_GRAM_CLASSIC))
+            return launch_variant<64, 64, 16, 32, 1, 1>(x, nx, y, ny, dim, k, ldk, flags, stream);
+        return launch_variant<64, 64, 16, 32, 1, 0>(x, nx, y, ny, dim, k, ldk, flags, stream);
+    }
+    return launch_variant<128, 64, 32, 32, 0, 0>(x, nx, y, ny, dim, k, ldk, flags, stream);
 }
 
 }  // namespace b200sq

@@ -9,10 +9,12 @@
 namespace b200sq {
 
 struct TileArgs {
-    Pass pass;                 // this pass (by value)
-    const Round* rounds;       // device arrays, indexed with the plan's global indices
-    const Uop* uops;
-    const b200sq_gate* gates;
+    DPass pass;                        // this pass, its rounds and micro-ops travel in the kernel
+    DRound rounds[kMaxPassRounds];     // parameters (constant bank: uniform, broadcast reads)
+    DUop uops[kMaxPassUops];
+    DInit inits[kMaxInit];             // product-state prefix (first pass only)
+    int32_t n_init;
+    const b200sq_gate* gates;          // device gate table (angle coefficients)
     double2* psi;              // states; state (v, i) lives at psi + ((v * n_total + i - psi_off) << n)
     int64_t psi_off;
     const double* x;           // [n_total][d]

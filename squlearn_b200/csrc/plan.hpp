@@ -24,24 +24,83 @@
 
 namespace b200sq {
 
-enum UopKind : int32_t { UOP_U1 = 0, UOP_U2 = 1, UOP_DIAG = 2 };
+// Micro-op kinds.  The U1 family differs only in how much FP64 work the 2x2 product needs:
+//   U1RX   [[c, -is], [-is, c]]  (rx)            8 FP64 instructions per amplitude pair
+//   U1REAL real 2x2 (ry, h, x)                   8
+//   U1G    general complex 2x2 (y, sx, u)       16
+//   U1CTRL general 2x2 under a control mask (cx, cy, ch, csx, crx, cry, ccx)
+enum UopKind : int32_t { UOP_U1G = 0, UOP_U2 = 1, UOP_DIAG = 2, UOP_U1RX = 3, UOP_U1REAL = 4,
+                         UOP_U1CTRL = 5 };
 
-struct Uop {         // 32 bytes, copied to the device verbatim
+struct Uop {         // host-side micro-op (the device gets the packed DUop below)
     int32_t kind;    // UopKind
     int32_t gate;    // index into the gate table (kind, angle coefficients)
-    int32_t r0, r1;  // U1: r0 = register bit. U2: r0 > r1 register bits (r0 = matrix MSB).
+    int32_t r0, r1;  // U1*: r0 = register bit. U2: r0 > r1 register bits (r0 = matrix MSB).
                      // DIAG: ext positions of the first / second qubit (r1 = -1 for 1-qubit)
-    uint32_t ctrl;   // U1/U2: control mask (ext positions). DIAG: skip mask (bit j: phase j == 1)
+    uint32_t ctrl;   // U1CTRL/U2: control mask (ext positions). DIAG: skip mask (bit j: phase j == 1)
     int32_t mat;     // offset of this op's matrix in the team's matrix area (double2 units)
     int32_t swap;    // U2: 1 when the gate's first qubit sits on r1 (matrix must be permuted)
-    int32_t pad;
+    int32_t pat;     // DIAG: 2 bits per register slot k: phase-index bits contributed by slot k
 };
 
-struct Round {       // 24 bytes
+struct Round {       // host-side round
     int32_t nb;      // number of register bits (0..3)
     int32_t rb[3];   // their tile-local positions, ascending
     int32_t u0, u1;  // micro-op range
 };
+
+// Packed forms that travel to the device inside the kernel parameters (constant bank).
+struct DUop {        // 16 bytes
+    uint8_t kind, r0, swap, pad0;
+    int8_t r1, pad1;
+    uint16_t gate;
+    uint32_t ctrl;
+    uint16_t mat;
+    uint16_t pat;
+};
+struct DRound {      // 8 bytes
+    uint8_t nb, rb[3];
+    uint16_t u0, u1;  // micro-op range relative to the pass
+};
+struct DPass {       // device view of a pass
+    int32_t T, first, n_rounds, n_uops, mat_elems, n_lruns, n_oruns;
+    uint32_t lmask[8];
+    int32_t lshift[8];
+    uint32_t omask[8];
+    int32_t oshift[8];
+    uint8_t extq[32];  // ext position -> qubit (tile qubits first, then outer qubits)
+};
+struct DInit {       // a 1-qubit gate folded into the product-state start of the first pass
+    uint16_t gate;
+    uint8_t qubit, pad;
+};
+constexpr int kMaxPassUops = 128;    // per pass, so that a pass fits the 4 KiB kernel-parameter space
+constexpr int kMaxPassRounds = 64;
+constexpr int kMaxInit = 96;
+
+inline DUop pack_uop(const Uop& u, int pass_u0) {
+    (void)pass_u0;
+    DUop d{};
+    d.kind = (uint8_t)u.kind;
+    d.r0 = (uint8_t)u.r0;
+    d.r1 = (int8_t)u.r1;
+    d.swap = (uint8_t)u.swap;
+    d.gate = (uint16_t)u.gate;
+    d.ctrl = u.ctrl;
+    d.mat = (uint16_t)u.mat;
+    d.pat = (uint16_t)u.pat;
+    return d;
+}
+inline DRound pack_round(const Round& r, int pass_u0) {
+    DRound d{};
+    d.nb = (uint8_t)r.nb;
+    d.rb[0] = (uint8_t)r.rb[0];
+    d.rb[1] = (uint8_t)r.rb[1];
+    d.rb[2] = (uint8_t)r.rb[2];
+    d.u0 = (uint16_t)(r.u0 - pass_u0);
+    d.u1 = (uint16_t)(r.u1 - pass_u0);
+    return d;
+}
 
 constexpr int kMaxRuns = 8;
 
@@ -57,6 +116,7 @@ struct Pass {
     uint32_t omask[kMaxRuns];  // outer-index bit runs -> global amplitude index
     int32_t oshift[kMaxRuns];
     int32_t tile_qubits[32];   // the T tile qubits (ascending), for introspection / tests
+    uint8_t extq[32];          // ext position -> qubit
 };
 
 struct GateInfo {
@@ -66,6 +126,9 @@ struct GateInfo {
     bool has_angle;
 };
 
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 inline GateInfo gate_info(int kind) {
     switch (kind) {
         case B200SQ_ID: return {1, 0, true, false};
@@ -83,7 +146,7 @@ inline GateInfo gate_info(int kind) {
         case B200SQ_RZZ: return {2, 0, true, true};
         case B200SQ_CCX: return {3, 2, false, false};
         case B200SQ_CSWAP: return {3, 1, false, false};
-        default: throw std::invalid_argument("unknown gate kind " + std::to_string(kind));
+        default: return {0, 0, false, false};  // unknown kind (rejected by gate_masks)
     }
 }
 
@@ -94,6 +157,12 @@ struct Plan {
     std::vector<Pass> passes;
     std::vector<Round> rounds;
     std::vector<Uop> uops;
+    // Product-state prefix: 1-qubit gates that act on a qubit before any multi-qubit gate touches
+    // it.  U_k ... U_1 |0> stays a tensor product, so the first pass starts from
+    // (x)_q v_q with v_q = (folded gates of q)|0> instead of applying these gates amplitude by
+    // amplitude (circuit order is preserved per qubit).
+    std::vector<int32_t> init_gates;
+    uint32_t first_tile_mask = 0;  // the first pass must use exactly this tile (folded qubits are local)
 };
 
 namespace detail {
@@ -105,6 +174,7 @@ struct GMask {
 
 inline GMask gate_masks(const b200sq_gate& g, int n) {
     GateInfo gi = gate_info(g.kind);
+    if (gi.nq == 0) throw std::invalid_argument("unknown gate kind " + std::to_string(g.kind));
     GMask m;
     for (int k = 0; k < gi.nq; ++k) {
         int q = g.q[k];
@@ -139,7 +209,7 @@ inline int make_runs(uint32_t qmask, uint32_t* masks, int32_t* shifts) {
 // low_bits: number of lowest qubits every tile must contain (keeps global accesses in
 // contiguous runs of 2^low_bits * 16 bytes).
 inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_bits,
-                      int low_bits = 4) {
+                      int low_bits = 4, bool fold_prefix = true) {
     using namespace detail;
     if (n < 1 || n > B200SQ_MAX_QUBITS) throw std::invalid_argument("n_qubits out of range");
     Plan plan;
@@ -150,22 +220,58 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
     plan.T = T;
     plan.gates = gates_in;
     const int G = (int)gates_in.size();
+    if (G > 65535) throw std::invalid_argument("at most 65535 gates per program");
     std::vector<GMask> gm(G);
     for (int i = 0; i < G; ++i) gm[i] = gate_masks(gates_in[i], n);
     // leave room for two freely chosen target qubits; with T == n the tile is the whole state
     low_bits = (T == n) ? T : std::max(0, std::min(low_bits, T - 2));
     const uint32_t mandatory = (low_bits >= 32 ? ~0u : (1u << low_bits) - 1u);
 
+    // Gates of the first pass' tile qubits that can be folded into the product-state start.  Only
+    // TILE qubits are folded: an outer qubit that stays |0> keeps 2^(n-T) - 1 of every 2^(n-T) tiles
+    // identically zero during the first pass (they are skipped), which is worth more than folding.
+    auto first_tile = [&](const std::vector<int>& gates_all) {
+        uint32_t L = mandatory, blockedT = 0, blockedD = 0;
+        for (int gi : gates_all) {
+            const GMask& m = gm[gi];
+            bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
+            if (free_ && popc(L | m.tgt) <= T) {
+                L |= m.tgt;
+            } else {
+                blockedT |= m.all;
+                blockedD |= m.tgt;
+            }
+        }
+        for (int q = 0; q < n && popc(L) < T; ++q) L |= 1u << q;
+        return L;
+    };
     std::vector<int> pending;
-    for (int i = 0; i < G; ++i)
-        if (gates_in[i].kind != B200SQ_ID) pending.push_back(i);
-
+    {
+        std::vector<int> all;
+        for (int i = 0; i < G; ++i)
+            if (gates_in[i].kind != B200SQ_ID) all.push_back(i);
+        const uint32_t L0 = first_tile(all);
+        uint32_t entangled = 0;  // qubits already touched by a multi-qubit gate (or a kept gate)
+        for (int i : all) {
+            GateInfo gi = gate_info(gates_in[i].kind);
+            if (fold_prefix && gi.nq == 1 && !(entangled & gm[i].all) && (gm[i].all & L0) &&
+                (int)plan.init_gates.size() < kMaxInit) {
+                plan.init_gates.push_back(i);
+                continue;
+            }
+            entangled |= gm[i].all;
+            pending.push_back(i);
+        }
+        plan.first_tile_mask = L0;
+    }
     bool first = true;
     // A circuit without gates still needs one pass to write |0..0>.
     while (!pending.empty() || first) {
         // ---- choose the tile qubit set by first demand
         uint32_t L = mandatory;
-        {
+        if (first) {
+            L = plan.first_tile_mask;
+        } else {
             uint32_t blockedT = 0, blockedD = 0;
             for (int gi : pending) {
                 const GMask& m = gm[gi];
@@ -186,7 +292,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
             for (int gi : pending) {
                 const GMask& m = gm[gi];
                 bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
-                if (free_ && (m.tgt & ~L) == 0) {
+                if (free_ && (m.tgt & ~L) == 0 && (int)absorbed.size() < kMaxPassUops) {
                     absorbed.push_back(gi);
                 } else {
                     rest.push_back(gi);
@@ -215,6 +321,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
         {
             int c = 0;
             for (int q = 0; q < n; ++q) if (L >> q & 1u) ps.tile_qubits[c++] = q;
+            for (int q = 0; q < n; ++q) ps.extq[pos[q]] = (uint8_t)q;
         }
         ps.r0 = (int)plan.rounds.size();
         ps.u0 = (int)plan.uops.size();
@@ -224,6 +331,13 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
         size_t n_done = 0;
         int mat_off = 0;
         while (n_done < absorbed.size()) {
+            if ((int)plan.rounds.size() - ps.r0 >= kMaxPassRounds) {
+                // the pass is full: hand the remaining gates back (gate order == circuit order)
+                for (size_t a = 0; a < absorbed.size(); ++a)
+                    if (!done[a]) rest.push_back(absorbed[a]);
+                std::sort(rest.begin(), rest.end());
+                break;
+            }
             Round rd;
             std::memset(&rd, 0, sizeof(rd));
             rd.u0 = (int)plan.uops.size();
@@ -278,11 +392,21 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                         case B200SQ_CRZ: u.ctrl = 0x5; break;                       // control = 0
                         default: u.ctrl = 0; break;
                     }
+                    // phase-index bits that depend on the register slot k
+                    for (int k = 0; k < 8; ++k)
+                        for (int c = 0; c < rd.nb; ++c)
+                            if (k >> c & 1) {
+                                if (rd.rb[c] == u.r0) u.pat |= 1 << (2 * k);
+                                if (rd.rb[c] == u.r1) u.pat |= 2 << (2 * k);
+                            }
                     mat_off += 4;
                 } else if (info.nq - info.nctrl == 1) {
-                    u.kind = UOP_U1;
                     u.r0 = regbit(g.q[info.nctrl]);
                     for (int k = 0; k < info.nctrl; ++k) u.ctrl |= 1u << pos[g.q[k]];
+                    if (info.nctrl > 0) u.kind = UOP_U1CTRL;
+                    else if (g.kind == B200SQ_RX) u.kind = UOP_U1RX;
+                    else if (g.kind == B200SQ_RY || g.kind == B200SQ_H || g.kind == B200SQ_X) u.kind = UOP_U1REAL;
+                    else u.kind = UOP_U1G;
                     mat_off += 4;
                 } else {
                     u.kind = UOP_U2;

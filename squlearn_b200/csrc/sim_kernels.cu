@@ -16,6 +16,9 @@ namespace b200sq {
 
 namespace {
 
+#ifndef B200SQ_TILE_MINBLOCKS
+#define B200SQ_TILE_MINBLOCKS 3
+#endif
 constexpr int kCtaThreads = 256;
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -35,7 +38,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kCtaThreads) k_tile_pass(const __grid_constant__ TileArgs A) {
+__global__ void __launch_bounds__(kCtaThreads, B200SQ_TILE_MINBLOCKS) k_tile_pass(const __grid_constant__ TileArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* smem = reinterpret_cast<double2*>(smem_raw);
 
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_tile_pass(const __grid_constant
     const int64_t item = (int64_t)blockIdx.x * A.teams_per_cta + team;
     if (item >= A.total_items) return;  // the whole team leaves together
 
-    const Pass& P = A.pass;
+    const DPass& P = A.pass;
     const int T = P.T;
     const uint32_t tile_elems = 1u << T;
     const uint32_t n_outer = 1u << (A.n - T);
@@ -57,31 +60,67 @@ __global__ void __launch_bounds__(kCtaThreads) k_tile_pass(const __grid_constant
     double2* tile = smem + (size_t)team * A.team_elems;
     double2* mats = tile + tile_elems;
 
-    // ---- per-sample gate matrices
-    {
-        const double* xrow = A.x ? A.x + sample * A.d : nullptr;
-        const int vgate = A.var_gate ? A.var_gate[variant] : -1;
-        const double vshift = A.var_gate ? A.var_shift[variant] : 0.0;
-        for (int ui = P.u0 + tid; ui < P.u1; ui += TS) {
-            const Uop u = A.uops[ui];
-            const b200sq_gate g = A.gates[u.gate];
-            double theta = gate_angle(g, xrow, A.table, A.n_total, sample);
-            if (u.gate == vgate) theta += vshift;
-            build_matrix(u, g, theta, mats + u.mat);
+    const double* xrow = A.x ? A.x + sample * A.d : nullptr;
+    const int vgate = A.var_gate ? A.var_gate[variant] : -1;
+    const double vshift = A.var_gate ? A.var_shift[variant] : 0.0;
+    double2* state = A.psi ? A.psi + (((int64_t)variant * A.n_total + sample - A.psi_off) << A.n) : nullptr;
+    const uint32_t obase = scatter_runs(outer, P.n_oruns, P.omask, P.oshift);
+
+    // ---- first pass: a tile whose outer qubits are not all |0> is identically zero
+    if (P.first && outer != 0) {
+        bool zero = false;  // outer qubits are never folded, so any set outer bit means a zero tile
+        for (int j = 0; j < A.n - T; ++j) zero |= (outer >> j) & 1u;
+        if (zero) {
+            if (A.store)
+                for (uint32_t l = tid; l < tile_elems; l += TS)
+                    __stcs(state + (obase | scatter_runs(l, P.n_lruns, P.lmask, P.lshift)), double2{0.0, 0.0});
+            return;
         }
     }
 
+    // ---- per-sample gate matrices
+    for (int ui = tid; ui < P.n_uops; ui += TS) {
+        const DUop u = A.uops[ui];
+        const b200sq_gate g = A.gates[u.gate];
+        double theta = gate_angle(g, xrow, A.table, A.n_total, sample);
+        if ((int)u.gate == vgate) theta += vshift;
+        build_matrix(u, g, theta, mats + u.mat);
+    }
+
     // ---- stage the tile
-    const uint32_t obase = scatter_runs(outer, P.n_oruns, P.omask, P.oshift);
-    double2* state = A.psi ? A.psi + (((int64_t)variant * A.n_total + sample - A.psi_off) << A.n) : nullptr;
-    const bool zero_tile = P.first && outer != 0;
+    bool zero_tile = false;
     if (P.first) {
+        // product-state start: |psi> = (x)_q v_q with v_q = (folded 1-qubit gates of q)|0>
+        double2* qv = mats + P.mat_elems;  // [32][2]
+        double2* lo = qv + 64;             // [64] partial products over the low tile bits
+        double2* hi = lo + 64;             // [<=128] partial products over the high tile bits
+        for (int q = tid; q < A.n; q += TS)
+            fold_qubit_vector(q, A.inits, A.n_init, A.gates, xrow, A.table, A.n_total, sample, vgate,
+                              vshift, qv + 2 * q);
+        team_sync(TS, team);
+        const int nlo = T < 6 ? T : 6, nhi = T - nlo;
+        const double2 oscal = product_amp(outer, A.n - T, P.extq + T, qv);
+        zero_tile = (oscal.x == 0.0 && oscal.y == 0.0);
+        for (int t = tid; t < (1 << nlo); t += TS) lo[t] = product_amp(t, nlo, P.extq, qv);
+        for (int t = tid; t < (1 << nhi); t += TS) hi[t] = cmul(oscal, product_amp(t, nhi, P.extq + nlo, qv));
+        team_sync(TS, team);
         for (uint32_t l = tid; l < tile_elems; l += TS)
-            tile[tile_sw(l)] = double2{(outer == 0 && l == 0) ? 1.0 : 0.0, 0.0};
+            tile[tile_sw(l)] = cmul(lo[l & ((1u << nlo) - 1u)], hi[l >> nlo]);
     } else {
-        for (uint32_t l = tid; l < tile_elems; l += TS) {
-            const uint32_t gidx = obase | scatter_runs(l, P.n_lruns, P.lmask, P.lshift);
-            tile[tile_sw(l)] = __ldcs(state + gidx);
+        // batches of eight independent 16-byte loads per thread keep the memory pipe full
+        for (uint32_t l0 = tid; l0 < tile_elems; l0 += 8 * TS) {
+            double2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t l = l0 + j * TS;
+                if (l < tile_elems)
+                    v[j] = __ldcs(state + (obase | scatter_runs(l, P.n_lruns, P.lmask, P.lshift)));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t l = l0 + j * TS;
+                if (l < tile_elems) tile[tile_sw(l)] = v[j];
+            }
         }
     }
     team_sync(TS, team);
@@ -89,7 +128,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_tile_pass(const __grid_constant
     // ---- rounds
     if (!zero_tile) {
         const uint32_t ext_base = outer << T;
-        for (int r = P.r0; r < P.r1; ++r) {
+        for (int r = 0; r < P.n_rounds; ++r) {
             exec_round_thread(tile, A.rounds[r], A.uops, mats, ext_base, T, tid, TS);
             team_sync(TS, team);
         }
@@ -159,7 +198,7 @@ int tile_pass_smem_bytes(int T, int mat_elems, int* team_size, int* teams_per_ct
                          int* team_elems) {
     int groups = T >= 3 ? (1 << (T - 3)) : 1;
     int ts = groups < 32 ? 32 : (groups > kCtaThreads ? kCtaThreads : groups);
-    int elems = (1 << T) + mat_elems;
+    int elems = (1 << T) + mat_elems + 64 + 64 + 128;  // tile + matrices + product-start scratch
     elems = (elems + 7) & ~7;  // keep every team 128-byte aligned
     int teams = kCtaThreads / ts;
     while (teams > 1 && (size_t)teams * elems * sizeof(double2) > (size_t)kMaxSmem / 2) teams >>= 1;

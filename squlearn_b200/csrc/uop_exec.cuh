@@ -51,7 +51,7 @@ B200SQ_HD double gate_angle(const b200sq_gate& g, const double* x_row, const dou
 //   U1:   m[0..3]  = 2x2 row-major
 //   U2:   m[0..15] = 4x4 row-major, index = bit(r0) << 1 | bit(r1)
 //   DIAG: m[0..3]  = phases, index = bit(q0) | bit(q1) << 1
-B200SQ_HD void build_matrix(const Uop& u, const b200sq_gate& g, double theta, double2* m) {
+B200SQ_HD void build_matrix(const DUop& u, const b200sq_gate& g, double theta, double2* m) {
     const double kInvSqrt2 = 0.70710678118654752440;
     double s, c;
     sincos(0.5 * theta, &s, &c);
@@ -76,7 +76,7 @@ B200SQ_HD void build_matrix(const Uop& u, const b200sq_gate& g, double theta, do
         }
         return;
     }
-    if (u.kind == UOP_U1) {
+    if (u.kind != UOP_U2) {  // the U1 family
         switch (g.kind) {
             case B200SQ_H: case B200SQ_CH:
                 m[0] = m[1] = m[2] = double2{kInvSqrt2, 0.0}; m[3] = double2{-kInvSqrt2, 0.0}; break;
@@ -145,95 +145,223 @@ B200SQ_HD void build_matrix(const Uop& u, const b200sq_gate& g, double theta, do
     }
 }
 
-// Apply one micro-op to the register amplitudes a[0..2^nb).  `e` is the ext index of a[0]
-// (register bits cleared); ko[k] is the ext/local offset of register slot k.
-B200SQ_HD void apply_uop(double2 (&a)[8], const Uop& u, const double2* __restrict__ m, uint32_t e,
-                         const uint32_t (&ko)[8], int nk) {
-    if (u.kind == UOP_DIAG) {
-        const int qa = u.r0, qb = u.r1;
-        const uint32_t skip = u.ctrl;
+// ---------------------------------------------------------------------------------------------
+// Product-state start of the first pass.
+
+// v = (folded 1-qubit gates of `qubit`) |0>, in circuit order.
+B200SQ_HD void fold_qubit_vector(int qubit, const DInit* inits, int n_init, const b200sq_gate* gates,
+                                 const double* xrow, const double* table, int64_t n_total,
+                                 int64_t sample, int vgate, double vshift, double2* out2) {
+    double2 v0{1.0, 0.0}, v1{0.0, 0.0};
+    for (int i = 0; i < n_init; ++i) {
+        if (inits[i].qubit != qubit) continue;
+        const b200sq_gate g = gates[inits[i].gate];
+        double theta = gate_angle(g, xrow, table, n_total, sample);
+        if ((int)inits[i].gate == vgate) theta += vshift;
+        DUop u{};
+        double2 m[4];
+        const GateInfo gi = gate_info(g.kind);
+        if (gi.diag) {
+            u.kind = UOP_DIAG;
+            build_matrix(u, g, theta, m);  // m[0], m[1] = phases of |0>, |1>
+            v0 = cmul(m[0], v0);
+            v1 = cmul(m[1], v1);
+        } else {
+            u.kind = UOP_U1G;
+            build_matrix(u, g, theta, m);
+            const double2 w0 = cfma(m[1], v1, cmul(m[0], v0));
+            const double2 w1 = cfma(m[3], v1, cmul(m[2], v0));
+            v0 = w0;
+            v1 = w1;
+        }
+    }
+    out2[0] = v0;
+    out2[1] = v1;
+}
+
+// prod_b qv[qubits[b]][bit b of idx]
+B200SQ_HD double2 product_amp(uint32_t idx, int nbits, const uint8_t* qubits, const double2* qv) {
+    double2 r{1.0, 0.0};
+    for (int b = 0; b < nbits; ++b) r = cmul(r, qv[2 * qubits[b] + ((idx >> b) & 1u)]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register micro-op interpreter.  Everything is templated on NB (register bits of the round) so
+// that the amplitude array a[2^NB] is indexed with compile-time constants only.
+
+template <int NB, int R>
+B200SQ_HD void u1_general(double2 (&a)[1 << NB], const double2* __restrict__ m) {
+    const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < nk) {
-                uint32_t ek = e | ko[k];
-                uint32_t idx = (ek >> qa) & 1u;
-                if (qb >= 0) idx |= ((ek >> qb) & 1u) << 1;
-                if (!((skip >> idx) & 1u)) a[k] = cmul(a[k], m[idx]);
-            }
-        }
-        return;
-    }
-    if (u.kind == UOP_U1) {
-        const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
-        const uint32_t cm = u.ctrl;
-#define B200SQ_PAIR(k0, k1)                                                       \
-    if ((k1) < nk && (((e | ko[k0]) & cm) == cm)) {                              \
-        double2 v0 = a[k0], v1 = a[k1];                                          \
-        a[k0] = cfma(m01, v1, cmul(m00, v0));                                    \
-        a[k1] = cfma(m11, v1, cmul(m10, v0));                                    \
-    }
-        switch (u.r0) {
-            case 0: B200SQ_PAIR(0, 1) B200SQ_PAIR(2, 3) B200SQ_PAIR(4, 5) B200SQ_PAIR(6, 7) break;
-            case 1: B200SQ_PAIR(0, 2) B200SQ_PAIR(1, 3) B200SQ_PAIR(4, 6) B200SQ_PAIR(5, 7) break;
-            default: B200SQ_PAIR(0, 4) B200SQ_PAIR(1, 5) B200SQ_PAIR(2, 6) B200SQ_PAIR(3, 7) break;
-        }
-#undef B200SQ_PAIR
-        return;
-    }
-    // U2 on register bits (r0 > r1); matrix index = bit(r0) << 1 | bit(r1)
-    {
-        const uint32_t cm = u.ctrl;
-#define B200SQ_QUAD(k00, k01, k10, k11)                                           \
-    if ((k11) < nk && (((e | ko[k00]) & cm) == cm)) {                            \
-        double2 v0 = a[k00], v1 = a[k01], v2 = a[k10], v3 = a[k11];              \
-        a[k00] = cfma(m[3], v3, cfma(m[2], v2, cfma(m[1], v1, cmul(m[0], v0)))); \
-        a[k01] = cfma(m[7], v3, cfma(m[6], v2, cfma(m[5], v1, cmul(m[4], v0)))); \
-        a[k10] = cfma(m[11], v3, cfma(m[10], v2, cfma(m[9], v1, cmul(m[8], v0)))); \
-        a[k11] = cfma(m[15], v3, cfma(m[14], v2, cfma(m[13], v1, cmul(m[12], v0)))); \
-    }
-        if (u.r0 == 1) {            // bits (1, 0); free bit 2
-            B200SQ_QUAD(0, 1, 2, 3) B200SQ_QUAD(4, 5, 6, 7)
-        } else if (u.r1 == 0) {     // bits (2, 0); free bit 1
-            B200SQ_QUAD(0, 1, 4, 5) B200SQ_QUAD(2, 3, 6, 7)
-        } else {                    // bits (2, 1); free bit 0
-            B200SQ_QUAD(0, 2, 4, 6) B200SQ_QUAD(1, 3, 5, 7)
-        }
-#undef B200SQ_QUAD
+    for (int k0 = 0; k0 < (1 << NB); ++k0) {
+        if (k0 & (1 << R)) continue;
+        const int k1 = k0 | (1 << R);
+        const double2 v0 = a[k0], v1 = a[k1];
+        a[k0] = cfma(m01, v1, cmul(m00, v0));
+        a[k1] = cfma(m11, v1, cmul(m10, v0));
     }
 }
 
-// One thread's share of a round: groups g = tid, tid + nthreads, ...
-B200SQ_HD void exec_round_thread(double2* tile, const Round& rd, const Uop* uops,
-                                 const double2* mats, uint32_t ext_base, int T, int tid,
-                                 int nthreads) {
-    const int nb = rd.nb;
-    const int nk = 1 << nb;
-    const int ngroups = 1 << (T - nb);
-    uint32_t ko[8];
+// [[c, -i s], [-i s, c]]
+template <int NB, int R>
+B200SQ_HD void u1_rx(double2 (&a)[1 << NB], const double2* __restrict__ m) {
+    const double c = m[0].x, s = -m[1].y;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k0 = 0; k0 < (1 << NB); ++k0) {
+        if (k0 & (1 << R)) continue;
+        const int k1 = k0 | (1 << R);
+        const double2 v0 = a[k0], v1 = a[k1];
+        a[k0] = double2{fma(s, v1.y, c * v0.x), fma(-s, v1.x, c * v0.y)};
+        a[k1] = double2{fma(s, v0.y, c * v1.x), fma(-s, v0.x, c * v1.y)};
+    }
+}
+
+// real 2x2
+template <int NB, int R>
+B200SQ_HD void u1_real(double2 (&a)[1 << NB], const double2* __restrict__ m) {
+    const double m00 = m[0].x, m01 = m[1].x, m10 = m[2].x, m11 = m[3].x;
+#pragma unroll
+    for (int k0 = 0; k0 < (1 << NB); ++k0) {
+        if (k0 & (1 << R)) continue;
+        const int k1 = k0 | (1 << R);
+        const double2 v0 = a[k0], v1 = a[k1];
+        a[k0] = double2{fma(m01, v1.x, m00 * v0.x), fma(m01, v1.y, m00 * v0.y)};
+        a[k1] = double2{fma(m11, v1.x, m10 * v0.x), fma(m11, v1.y, m10 * v0.y)};
+    }
+}
+
+template <int NB, int R>
+B200SQ_HD void u1_ctrl(double2 (&a)[1 << NB], const double2* __restrict__ m, uint32_t e,
+                       const uint32_t (&ko)[1 << NB], uint32_t cm) {
+    const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+    for (int k0 = 0; k0 < (1 << NB); ++k0) {
+        if (k0 & (1 << R)) continue;
+        const int k1 = k0 | (1 << R);
+        if (((e | ko[k0]) & cm) == cm) {
+            const double2 v0 = a[k0], v1 = a[k1];
+            a[k0] = cfma(m01, v1, cmul(m00, v0));
+            a[k1] = cfma(m11, v1, cmul(m10, v0));
+        }
+    }
+}
+
+// 4x4 on register bits (RH > RL), matrix index = bit(RH) << 1 | bit(RL)
+template <int NB, int RH, int RL>
+B200SQ_HD void u2_general(double2 (&a)[1 << NB], const double2* __restrict__ m, uint32_t e,
+                          const uint32_t (&ko)[1 << NB], uint32_t cm) {
+#pragma unroll
+    for (int k = 0; k < (1 << NB); ++k) {
+        if (k & ((1 << RH) | (1 << RL))) continue;
+        if (((e | ko[k]) & cm) != cm) continue;
+        const int k00 = k, k01 = k | (1 << RL), k10 = k | (1 << RH), k11 = k | (1 << RH) | (1 << RL);
+        const double2 v0 = a[k00], v1 = a[k01], v2 = a[k10], v3 = a[k11];
+        a[k00] = cfma(m[3], v3, cfma(m[2], v2, cfma(m[1], v1, cmul(m[0], v0))));
+        a[k01] = cfma(m[7], v3, cfma(m[6], v2, cfma(m[5], v1, cmul(m[4], v0))));
+        a[k10] = cfma(m[11], v3, cfma(m[10], v2, cfma(m[9], v1, cmul(m[8], v0))));
+        a[k11] = cfma(m[15], v3, cfma(m[14], v2, cfma(m[13], v1, cmul(m[12], v0))));
+    }
+}
+
+template <int NB>
+B200SQ_HD void diag_apply(double2 (&a)[1 << NB], const DUop& u, const double2* __restrict__ m,
+                          uint32_t e) {
+    uint32_t base = (e >> u.r0) & 1u;
+    if (u.r1 >= 0) base |= ((e >> u.r1) & 1u) << 1;
+    const uint32_t skip = u.ctrl, pat = u.pat;
+    if (pat == 0) {
+        // none of the gate's qubits is a register bit: one phase for all of this thread's amplitudes
+        if (!((skip >> base) & 1u)) {
+            const double2 ph = m[base];
+#pragma unroll
+            for (int k = 0; k < (1 << NB); ++k) a[k] = cmul(a[k], ph);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << NB); ++k) {
+        const uint32_t idx = base | ((pat >> (2 * k)) & 3u);
+        if (!((skip >> idx) & 1u)) a[k] = cmul(a[k], m[idx]);
+    }
+}
+
+template <int NB>
+B200SQ_HD void apply_uop(double2 (&a)[1 << NB], const DUop& u, const double2* __restrict__ m,
+                         uint32_t e, const uint32_t (&ko)[1 << NB]) {
+#define B200SQ_BY_R(FN, ...)                                        \
+    switch (u.r0) {                                                  \
+        case 0: FN<NB, 0>(__VA_ARGS__); break;                      \
+        case 1: if (NB > 1) FN<NB, (NB > 1 ? 1 : 0)>(__VA_ARGS__); break; \
+        default: if (NB > 2) FN<NB, (NB > 2 ? 2 : 0)>(__VA_ARGS__); break; \
+    }
+    switch (u.kind) {
+        case UOP_U1RX: B200SQ_BY_R(u1_rx, a, m) break;
+        case UOP_U1REAL: B200SQ_BY_R(u1_real, a, m) break;
+        case UOP_U1G: B200SQ_BY_R(u1_general, a, m) break;
+        case UOP_U1CTRL: B200SQ_BY_R(u1_ctrl, a, m, e, ko, u.ctrl) break;
+        case UOP_DIAG: diag_apply<NB>(a, u, m, e); break;
+        default:  // UOP_U2
+            if (NB >= 2) {
+                if (u.r0 == 1) {
+                    u2_general<NB, (NB >= 2 ? 1 : 0), 0>(a, m, e, ko, u.ctrl);
+                } else if (NB >= 3) {
+                    if (u.r1 == 0) u2_general<NB, (NB >= 3 ? 2 : 1), 0>(a, m, e, ko, u.ctrl);
+                    else u2_general<NB, (NB >= 3 ? 2 : 1), (NB >= 3 ? 1 : 0)>(a, m, e, ko, u.ctrl);
+                }
+            }
+            break;
+    }
+#undef B200SQ_BY_R
+}
+
+// One thread's share of a round: groups g = tid, tid + nthreads, ...
+template <int NB>
+B200SQ_HD void exec_round_nb(double2* tile, const DRound& rd, const DUop* uops, const double2* mats,
+                             uint32_t ext_base, int T, int tid, int nthreads) {
+    constexpr int NK = 1 << NB;
+    const int ngroups = 1 << (T - NB);
+    uint32_t ko[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
         uint32_t o = 0;
-        if (nb > 0 && (k & 1)) o |= 1u << rd.rb[0];
-        if (nb > 1 && (k & 2)) o |= 1u << rd.rb[1];
-        if (nb > 2 && (k & 4)) o |= 1u << rd.rb[2];
+        if (NB > 0 && (k & 1)) o |= 1u << rd.rb[0];
+        if (NB > 1 && (k & 2)) o |= 1u << rd.rb[1];
+        if (NB > 2 && (k & 4)) o |= 1u << rd.rb[2];
         ko[k] = o;
     }
     for (int g = tid; g < ngroups; g += nthreads) {
         // insert zero bits at the register-bit positions (ascending)
         uint32_t base = (uint32_t)g;
-        for (int c = 0; c < nb; ++c) {
-            uint32_t low = base & ((1u << rd.rb[c]) - 1u);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            const uint32_t low = base & ((1u << rd.rb[c]) - 1u);
             base = ((base >> rd.rb[c]) << (rd.rb[c] + 1)) | low;
         }
-        double2 a[8];
+        uint32_t addr[NK];
+        double2 a[NK];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < nk) a[k] = tile[tile_sw(base | ko[k])];
+        for (int k = 0; k < NK; ++k) {
+            addr[k] = tile_sw(base | ko[k]);
+            a[k] = tile[addr[k]];
+        }
         const uint32_t e = ext_base | base;
-        for (int ui = rd.u0; ui < rd.u1; ++ui) apply_uop(a, uops[ui], mats + uops[ui].mat, e, ko, nk);
+        for (int ui = rd.u0; ui < rd.u1; ++ui) {
+            const DUop u = uops[ui];
+            apply_uop<NB>(a, u, mats + u.mat, e, ko);
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < nk) tile[tile_sw(base | ko[k])] = a[k];
+        for (int k = 0; k < NK; ++k) tile[addr[k]] = a[k];
+    }
+}
+
+B200SQ_HD void exec_round_thread(double2* tile, const DRound& rd, const DUop* uops,
+                                 const double2* mats, uint32_t ext_base, int T, int tid,
+                                 int nthreads) {
+    switch (rd.nb) {
+        case 3: exec_round_nb<3>(tile, rd, uops, mats, ext_base, T, tid, nthreads); break;
+        case 2: exec_round_nb<2>(tile, rd, uops, mats, ext_base, T, tid, nthreads); break;
+        default: exec_round_nb<1>(tile, rd, uops, mats, ext_base, T, tid, nthreads); break;
     }
 }
 

@@ -6,6 +6,7 @@ All arithmetic happens in libb200sq.so's CUDA kernels.  There is no CPU path: co
 """
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -197,7 +198,7 @@ class Engine:
                                                 zm, out.data_ptr(), self._stream()))
         return out.reshape(tuple(psi.shape[:-1]) + (len(terms),))
 
-    def gram(self, psi_x, psi_y=None, diagonal: str = "one", out=None, three_m: bool = False):
+    def gram(self, psi_x, psi_y=None, diagonal: str = "one", out=None, three_m: Optional[bool] = None):
         """K[i, j] = |<psi_x[i]|psi_y[j]>|^2.  ``psi_y=None`` means the symmetric Gram of psi_x;
         ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy."""
         torch = self._torch
@@ -210,8 +211,12 @@ class Engine:
             raise ValueError("states must be (N, 2^n) arrays with equal 2^n")
         nx, ny, dim = psi_x.shape[0], psi_y.shape[0], psi_x.shape[1]
         flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[diagonal]) if sym else 0
+        if three_m is None:  # default: 3M (Gauss) complex product; B200SQ_GRAM_MODE=4m selects 4M
+            three_m = os.environ.get("B200SQ_GRAM_MODE", "3m").lower() != "4m"
         if three_m:
             flags |= _lib.GRAM_3M
+            if os.environ.get("B200SQ_GRAM_MODE", "").lower() == "3m-classic" or three_m == "classic":
+                flags |= _lib.GRAM_CLASSIC
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)

@@ -18,6 +18,7 @@ and re-raises immediately instead of retrying ten times (:1054-1099).
 """
 
 import logging
+import os
 from typing import Callable, List, Optional, Sequence, Union
 
 import numpy as np
@@ -129,7 +130,8 @@ class B200Circuit:
         for o in self.observables:
             if o.num_qubits != program.num_qubits:
                 raise ValueError("Number of qubits of the observable and the circuit differ")
-        self.tile_bits = tile_bits
+        # B200SQ_TILE_BITS overrides the default tile size (tuning / experiments)
+        self.tile_bits = tile_bits or int(os.environ.get("B200SQ_TILE_BITS", "0"))
         self._compiled = None
 
     @property

@@ -40,8 +40,12 @@ __attribute__((visibility("default"))) int hostemu_simulate(
                         const double* xrow = x ? x + s * d : nullptr;
                         const int vgate = var_gate ? var_gate[v] : -1;
                         const double vshift = var_gate ? var_shift[v] : 0.0;
-                        for (int ui = P.u0; ui < P.u1; ++ui) {
-                            const Uop& u = pl.uops[ui];
+                        std::vector<DUop> duops;
+                        std::vector<DRound> drounds;
+                        for (int ui = P.u0; ui < P.u1; ++ui) duops.push_back(pack_uop(pl.uops[ui], P.u0));
+                        for (int r = P.r0; r < P.r1; ++r) drounds.push_back(pack_round(pl.rounds[r], P.u0));
+                        for (int ui = 0; ui < (int)duops.size(); ++ui) {
+                            const DUop& u = duops[ui];
                             const b200sq_gate& gg = pl.gates[u.gate];
                             double theta = gate_angle(gg, xrow, table, N, s);
                             if (u.gate == vgate) theta += vshift;
@@ -49,19 +53,32 @@ __attribute__((visibility("default"))) int hostemu_simulate(
                         }
                         const uint32_t obase = scatter_runs(outer, P.n_oruns, P.omask, P.oshift);
                         double2* state = psi + (((int64_t)v * N + s) << n);
-                        const bool zero_tile = P.first && outer != 0;
-                        for (uint32_t l = 0; l < tile_elems; ++l) {
-                            if (P.first) {
-                                tile[tile_sw(l)] = double2{(outer == 0 && l == 0) ? 1.0 : 0.0, 0.0};
-                            } else {
-                                tile[tile_sw(l)] = state[obase | scatter_runs(l, P.n_lruns, P.lmask, P.lshift)];
+                        bool zero_tile = false;
+                        if (P.first) {
+                            std::vector<DInit> inits;
+                            for (int32_t gi : pl.init_gates)
+                                inits.push_back(DInit{(uint16_t)gi, (uint8_t)pl.gates[gi].q[0], 0});
+                            std::vector<double2> qv(64);
+                            for (int q = 0; q < n; ++q)
+                                fold_qubit_vector(q, inits.data(), (int)inits.size(), pl.gates.data(), xrow, table,
+                                                  N, s, vgate, vshift, qv.data() + 2 * q);
+                            const int nlo = T < 6 ? T : 6, nhi = T - nlo;
+                            const double2 oscal = product_amp(outer, n - T, P.extq + T, qv.data());
+                            zero_tile = (oscal.x == 0.0 && oscal.y == 0.0);
+                            for (uint32_t l = 0; l < tile_elems; ++l) {
+                                const double2 lo = product_amp(l & ((1u << nlo) - 1u), nlo, P.extq, qv.data());
+                                const double2 hi = cmul(oscal, product_amp(l >> nlo, nhi, P.extq + nlo, qv.data()));
+                                tile[tile_sw(l)] = cmul(lo, hi);
                             }
+                        } else {
+                            for (uint32_t l = 0; l < tile_elems; ++l)
+                                tile[tile_sw(l)] = state[obase | scatter_runs(l, P.n_lruns, P.lmask, P.lshift)];
                         }
                         if (!zero_tile) {
                             const uint32_t ext_base = outer << T;
-                            for (int r = P.r0; r < P.r1; ++r)
+                            for (size_t r = 0; r < drounds.size(); ++r)
                                 for (int tid = 0; tid < TS; ++tid)  // rounds are barrier-separated
-                                    exec_round_thread(tile.data(), pl.rounds[r], pl.uops.data(), mats.data(),
+                                    exec_round_thread(tile.data(), drounds[r], duops.data(), mats.data(),
                                                       ext_base, T, tid, TS);
                         }
                         for (uint32_t l = 0; l < tile_elems; ++l)

@@ -117,9 +117,10 @@ def test_large_state_subset_n20(sq, executor):
 
 
 # ------------------------------------------------------------------------------ Gram
+@pytest.mark.parametrize("three_m", [False, True])
 @pytest.mark.parametrize("nx,ny,dim", [(1, 1, 2), (5, 3, 8), (37, 130, 64), (129, 65, 1024),
-                                        (200, 200, 48), (64, 257, 4096)])
-def test_gram_rectangular(executor, nx, ny, dim):
+                                        (200, 200, 48), (64, 257, 4096), (700, 520, 2048)])
+def test_gram_rectangular(executor, nx, ny, dim, three_m):
     import torch
 
     rng = np.random.default_rng(nx * 7 + ny)
@@ -128,7 +129,7 @@ def test_gram_rectangular(executor, nx, ny, dim):
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     eng = executor.engine
-    got = eng.gram(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    got = eng.gram(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), three_m=three_m).cpu().numpy()
     want = oracle.fidelity_gram_zgemm(a, b, False)
     assert got.shape == (nx, ny)
     assert np.max(np.abs(got - want)) < GRAM_TOL
@@ -136,8 +137,9 @@ def test_gram_rectangular(executor, nx, ny, dim):
         assert np.max(np.abs(got - oracle.fidelity_gram_pairloop(a, b, False))) < GRAM_TOL
 
 
-@pytest.mark.parametrize("n,dim", [(1, 4), (63, 16), (128, 256), (300, 512), (513, 64)])
-def test_gram_symmetric_and_diagonal_policies(executor, n, dim):
+@pytest.mark.parametrize("three_m", [False, True])
+@pytest.mark.parametrize("n,dim", [(1, 4), (63, 16), (128, 256), (300, 512), (513, 64), (1100, 1024)])
+def test_gram_symmetric_and_diagonal_policies(executor, n, dim, three_m):
     import torch
 
     rng = np.random.default_rng(n)
@@ -145,9 +147,10 @@ def test_gram_symmetric_and_diagonal_policies(executor, n, dim):
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     t = torch.from_numpy(a).cuda()
     eng = executor.engine
-    k_one = eng.gram(t, None, diagonal="one").cpu().numpy()
-    k_zero = eng.gram(t, None, diagonal="zero").cpu().numpy()
-    k_cmp = eng.gram(t, None, diagonal="computed").cpu().numpy()
+    k_one = eng.gram(t, None, diagonal="one", three_m=three_m).cpu().numpy()
+    k_zero = eng.gram(t, None, diagonal="zero", three_m=three_m).cpu().numpy()
+    k_cmp = eng.gram(t, None, diagonal="computed", three_m=three_m).cpu().numpy()
+    assert np.array_equal(k_one, eng.gram(t, None, diagonal="one", three_m=three_m).cpu().numpy())  # deterministic
     want = oracle.fidelity_gram_pairloop(a, a, True, "off_diagonal") if n <= 130 else \
         oracle.fidelity_gram_zgemm(a, a, True, "off_diagonal")
     assert np.max(np.abs(k_one - want)) < GRAM_TOL
