@@ -283,6 +283,7 @@ def run_gpu_arm(args):
         return kernel.evaluate(X)
 
     e2e_step()
+    e2e_step()  # two warm-ups: the pinned host buffers of the D2H path are allocated once
     sync_all()
     t0 = time.perf_counter()
     e_start, e_end = ev(), ev()
@@ -318,20 +319,26 @@ def run_gpu_arm(args):
             pass
         if not multi:
             fp64_peak = fp64_peak_probe(torch, dev)
-            tiles_m = (n_points + 127) // 128
-            # symmetric: only tiles touching the lower triangle run (128 x 64 tiles)
+            mode_4m = os.environ.get("B200SQ_GRAM_MODE", "3m").lower() == "4m"
+            bm = 128 if mode_4m else 64
+            tiles_m = (n_points + bm - 1) // bm
+            # symmetric: only tiles touching the lower triangle run
             tiles = sum(1 for bi in range(tiles_m) for bj in range((n_points + 63) // 64)
-                        if bj * 64 <= bi * 128 + 127)
-            entries_computed = tiles * 128 * 64
+                        if bj * 64 <= bi * bm + bm - 1)
+            entries_computed = tiles * bm * 64
             flops = 8.0 * dim * entries_computed
             g_ms = float(np.mean(gram_ms))
             achieved = flops / (g_ms * 1e-3) / 1e12
             line["roofline"] = {
-                "kernel": "k_gram (FP64 DMMA, fused |.|^2 epilogue)", "bound": "tensor",
+                "kernel": ("k_gram 4M" if mode_4m else "k_gram3m_ws (3M, warp-specialised)")
+                          + ", FP64 DMMA, fused |.|^2 epilogue", "bound": "tensor",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": None, "ms_per_launch": g_ms,
                 "algorithmic": f"8*2^n flop per entry x {entries_computed} entries computed "
-                               f"({tiles} lower-triangle 128x64 tiles of the symmetric Gram)",
+                               f"({tiles} lower-triangle {bm}x64 tiles of the symmetric Gram)",
+                "executed_tflops": achieved * (1.0 if mode_4m else 0.75),
+                "executed_note": "3M (Gauss) complex product issues 6*2^n tensor flops per entry; the DMMA "
+                                 "hardware ceiling measured with tools/dmma_probe.cu is 37.1 TFLOP/s",
                 "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3; "
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "share_of_step": g_ms / ms_per_step,

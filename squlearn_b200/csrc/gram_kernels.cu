@@ -21,8 +21,8 @@
 //
 // Work decomposition (split-K for the ragged last wave): the (lower-triangle) tiles are cut into
 // UNITS.  The first floor(tiles / G) * G tiles (G = CTAs resident on the GPU) are whole-tile units;
-// each of the remaining R tiles is split along K into S = floor(G / R) slices so that the last
-// wave also fills the machine.  Slices park their partial sums in a workspace; the slice that
+// each of the remaining R tiles is split along K into S slices, S chosen to minimise the tail
+// time ceil(R * S / G) / S, so that the last wave also fills the machine.  Slices park their partial sums in a workspace; the slice that
 // arrives last adds them in slice order (deterministic) and runs the epilogue.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -591,11 +591,22 @@ int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     A.n_tiles = (int)n_tiles;
     const int G = sms;  // one CTA per SM (launch bounds)
     const int KT = (int)((dim + BK - 1) / BK);
+    // Tail policy: the last rem = n_tiles mod G tiles are cut into `slices` K-slices each.  With s
+    // slices the tail takes ceil(rem * s / G) / s tile-times; pick the s (<= 16, and leaving every
+    // slice at least 16 k-tiles) that minimises it.
     int rem = A.n_tiles % G;
-    int slices = rem ? G / rem : 1;
-    // a slice must keep the pipeline busy for a while: at least 16 k-tiles
-    if (slices > KT / 16) slices = KT / 16;
-    if (slices < 1) slices = 1;
+    int slices = 1;
+    if (rem) {
+        const int s_max = KT / 16 < 16 ? KT / 16 : 16;
+        double best = 1.0;
+        for (int sl = 2; sl <= s_max; ++sl) {
+            const double t = (double)((rem * sl + G - 1) / G) / sl;
+            if (t < best - 1e-9) {
+                best = t;
+                slices = sl;
+            }
+        }
+    }
     if (slices == 1) rem = 0;
     A.full_units = A.n_tiles - rem;
     A.slices = slices;

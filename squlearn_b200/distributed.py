@@ -4,9 +4,11 @@ The reference has no multi-device path at all; this module is 
 extension the north star asks for, built on the same single-GPU entry points:
 
   1. rank r simulates its slice of the data points            (no communication)
-  2. the statevector blocks are exchanged (all-gather over NCCL / NVLink)
+  2. each rank receives the statevector blocks its share of the Gram needs (NCCL point-to-point
+     over NVLink: floor(P/2) of the P-1 remote blocks), overlapped with its diagonal block
   3. the P x P grid of Gram blocks is covered using Hermitian symmetry: rank r computes the
-     diagonal block (r, r) with the symmetric kernel and the rectangular blocks (r, (r+s) mod P),
+     diagonal block (r, r) with the symmetric kernel and, in one launch, the rectangular blocks
+     (r, (r+s) mod P),
      s = 1 .. floor(P/2)  (for even P the s = P/2 blocks are split between the two owners), i.e.
      P(P+1)/2 blocks in total, balanced to within one block
   4. every off-diagonal block is transposed and sent to the rank that owns the mirrored position,
@@ -44,6 +46,39 @@ def symmetric_block_schedule(parts: int) -> List[List[int]]:
     return sched
 
 
+def gram_jobs(parts: List[Tuple[int, int]]) -> List[List[dict]]:
+    """Per rank, the rectangular pieces of the symmetric Gram matrix it computes.
+
+    Every job is ``{"rows": (a, b), "cols": (a, b), "owner": rank owning the column states,
+    "diag": bool}`` in global indices; ``rows`` is a sub-range of the rank's own row block.
+    Regular half-ring blocks use the full row block; for even P the antipodal block (r, r + P/2)
+    is split between its two owners — the lower rank takes the first half of its rows against the
+    whole remote block, the upper rank takes its full row block against the second half of the
+    lower rank's states — so every rank carries exactly P/2 block units."""
+    world = len(parts)
+    sched = symmetric_block_schedule(world)
+    jobs: List[List[dict]] = [[] for _ in range(world)]
+    for r in range(world):
+        r0, r1 = parts[r]
+        if r1 > r0:
+            jobs[r].append({"rows": (r0, r1), "cols": (r0, r1), "owner": r, "diag": True})
+        for c in sched[r]:
+            if c == r:
+                continue
+            c0, c1 = parts[c]
+            if c1 == c0 or r1 == r0:
+                continue
+            antipodal = world % 2 == 0 and (c - r) % world == world // 2
+            if not antipodal:
+                jobs[r].append({"rows": (r0, r1), "cols": (c0, c1), "owner": c, "diag": False})
+            else:  # r is the lower rank of the pair (the schedule lists the pair only there)
+                mid = r0 + (r1 - r0 + 1) // 2
+                jobs[r].append({"rows": (r0, mid), "cols": (c0, c1), "owner": c, "diag": False})
+                if r1 > mid:
+                    jobs[c].append({"rows": (c0, c1), "cols": (mid, r1), "owner": r, "diag": False})
+    return jobs
+
+
 class ShardedFidelityKernel:
     """Fidelity Gram matrix of ``x`` across all ranks of a process group.
 
@@ -73,56 +108,80 @@ class ShardedFidelityKernel:
         parts = row_partition(n, self.world)
         r0, r1 = parts[self.rank]
         eng = self.kernel._executor.engine
-        psi_local = self.kernel.states(x[r0:r1])
+        psi_local = self.kernel.states(x[r0:r1]).contiguous()
         dim = psi_local.shape[1]
+        dev = psi_local.device
+        f64 = torch.float64
 
-        # ---- exchange of statevector blocks (uniform NVSwitch bandwidth: plain all-gather)
-        sizes = [b - a for a, b in parts]
-        rows_max = max(sizes)
-        if len(set(sizes)) == 1:
-            send = psi_local.contiguous()
-        else:  # pad to a common block height (at most one extra row)
-            send = torch.zeros((rows_max, dim), dtype=psi_local.dtype, device=psi_local.device)
-            send[: r1 - r0] = psi_local
-        psi_all = torch.empty((self.world, rows_max, dim), dtype=psi_local.dtype,
-                              device=psi_local.device)
-        dist.all_gather_into_tensor(psi_all.view(torch.float64).reshape(-1),
-                                    send.view(torch.float64).reshape(-1), group=self.group)
-        blocks = [psi_all[c, : sizes[c]] for c in range(self.world)]
+        jobs = gram_jobs(parts)
+        mine = [j for j in jobs[self.rank] if not j["diag"]]
 
-        # ---- my share of the block grid
-        sched = symmetric_block_schedule(self.world)
-        rows = torch.zeros((r1 - r0, n), dtype=torch.float64, device=psi_local.device)
-        computed = {}
-        for c in sched[self.rank]:
-            c0, c1 = parts[c]
-            if c1 == c0 or r1 == r0:
+        # ---- exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
+        # every peer is one NVSwitch hop away, so there is no ring-order penalty).  The receive
+        # buffer holds the column states of all my jobs back to back, so that jobs sharing a row
+        # range become ONE rectangular Gram launch.
+        mine.sort(key=lambda j: (j["rows"], j["owner"]))
+        total_cols = sum(j["cols"][1] - j["cols"][0] for j in mine)
+        recv = torch.empty((max(total_cols, 1), dim), dtype=psi_local.dtype, device=dev)
+        ops, off = [], 0
+        for q in range(self.world):          # sends: rows of mine that other ranks' jobs need
+            if q == self.rank:
                 continue
-            if c == self.rank:
-                rows[:, c0:c1] = eng.gram(psi_local, None, diagonal=self.diagonal)
-            else:
-                blk = eng.gram(psi_local, blocks[c])
-                rows[:, c0:c1] = blk
-                computed[c] = blk
+            for j in jobs[q]:
+                if j["owner"] == self.rank and not j["diag"]:
+                    a, b = j["cols"]
+                    ops.append(dist.P2POp(dist.isend, psi_local[a - r0:b - r0].view(f64),
+                                          self._global_rank(q), self.group))
+        for j in mine:
+            w = j["cols"][1] - j["cols"][0]
+            j["off"] = off
+            ops.append(dist.P2POp(dist.irecv, recv[off:off + w].view(f64),
+                                  self._global_rank(j["owner"]), self.group))
+            off += w
+        reqs = dist.batch_isend_irecv(ops) if ops else []
 
-        # ---- mirror: send K_rc^T to rank c, receive K_cr^T from the ranks that computed (c, r)
-        ops, recv_bufs = [], {}
-        for c, blk in computed.items():
-            ops.append(dist.P2POp(dist.isend, blk.t().contiguous(), self._global_rank(c), self.group))
-        for c in range(self.world):
-            if c != self.rank and self.rank in sched[c]:
-                c0, c1 = parts[c]
-                if c1 == c0 or r1 == r0:
-                    continue
-                buf = torch.empty((r1 - r0, c1 - c0), dtype=torch.float64, device=psi_local.device)
-                recv_bufs[c] = buf
-                ops.append(dist.P2POp(dist.irecv, buf, self._global_rank(c), self.group))
+        # ---- the diagonal block needs no remote data: it runs while the blocks are in flight
+        rows = torch.zeros((r1 - r0, n), dtype=f64, device=dev)
+        if r1 > r0:
+            rows[:, r0:r1] = eng.gram(psi_local, None, diagonal=self.diagonal)
+        for req in reqs:
+            req.wait()
+
+        # ---- one launch per distinct row range
+        i = 0
+        while i < len(mine):
+            k = i
+            while k < len(mine) and mine[k]["rows"] == mine[i]["rows"]:
+                k += 1
+            ra, rb = mine[i]["rows"]
+            c_lo, c_hi = mine[i]["off"], mine[k - 1]["off"] + (mine[k - 1]["cols"][1] - mine[k - 1]["cols"][0])
+            big = eng.gram(psi_local[ra - r0:rb - r0], recv[c_lo:c_hi])
+            for j in mine[i:k]:
+                w = j["cols"][1] - j["cols"][0]
+                blk = big[:, j["off"] - c_lo: j["off"] - c_lo + w]
+                rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
+                j["blk"] = blk
+            i = k
+
+        # ---- mirror: every off-diagonal piece, transposed, belongs to the owner of its columns
+        ops, placements = [], []
+        for j in mine:
+            ops.append(dist.P2POp(dist.isend, j["blk"].t().contiguous(), self._global_rank(j["owner"]),
+                                  self.group))
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            for j in jobs[q]:
+                if j["owner"] == self.rank and not j["diag"]:
+                    (a, b), (ra, rb) = j["cols"], j["rows"]
+                    buf = torch.empty((b - a, rb - ra), dtype=f64, device=dev)
+                    placements.append((a - r0, b - r0, ra, rb, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, self._global_rank(q), self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        for c, buf in recv_bufs.items():
-            c0, c1 = parts[c]
-            rows[:, c0:c1] = buf
+        for a, b, ra, rb, buf in placements:
+            rows[a:b, ra:rb] = buf
         return rows, (r0, r1)
 
     def _global_rank(self, group_rank: int) -> int:

@@ -14,8 +14,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle
-from squlearn_b200.distributed import (ShardedFidelityKernel, row_partition, sharded_parameter_shift,
-                                       symmetric_block_schedule)
+from squlearn_b200.distributed import (ShardedFidelityKernel, gram_jobs, row_partition,
+                                       sharded_parameter_shift, symmetric_block_schedule)
 
 
 def test_row_partition_and_schedule():
@@ -32,6 +32,32 @@ def test_row_partition_and_schedule():
         assert len(pairs) == parts * (parts + 1) // 2
         loads = [len(c) for c in sched]
         assert max(loads) - min(loads) <= 1      # balanced
+
+
+def test_gram_jobs_cover_every_pair_once_and_balance():
+    for world in range(1, 9):
+        for n in (world * 8, world * 8 + 3, 5):
+            parts = row_partition(n, world)
+            jobs = gram_jobs(parts)
+            cover = np.zeros((n, n), dtype=int)
+            loads = []
+            for r, js in enumerate(jobs):
+                load = 0.0
+                for j in js:
+                    (a, b), (c, d) = j["rows"], j["cols"]
+                    assert parts[r][0] <= a <= b <= parts[r][1]          # rows are local
+                    assert parts[j["owner"]][0] <= c <= d <= parts[j["owner"]][1]
+                    if j["diag"]:
+                        cover[a:b, c:d] += 1
+                        load += 0.5 * (b - a) * (d - c)
+                    else:
+                        cover[a:b, c:d] += 1
+                        cover[c:d, a:b] += 1
+                        load += (b - a) * (d - c)
+                loads.append(load)
+            assert np.all(cover == 1), (world, n)
+            if n % (2 * world) == 0:
+                assert max(loads) == min(loads)                          # perfectly balanced
 
 
 class _OracleEngine:
@@ -89,7 +115,7 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (2, 1)])
+@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (2, 1), (4, 13)])
 def test_sharded_gram_gloo(tmp_path, world, n_points):
     mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / f"k_{world}_{n_points}.npy")
