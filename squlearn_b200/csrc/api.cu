@@ -177,7 +177,7 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.xmask = p->d_masks;
         a.zmask = p->d_masks ? p->d_masks + n_terms : nullptr;
         a.out = out;
-        tile_pass_smem_bytes(a.pass.T, a.pass.mat_elems, &a.team_size, &a.teams_per_cta, &a.team_elems);
+        tile_pass_smem_bytes(a.pass.T, a.pass.mat_elems, a.pass.first, &a.team_size, &a.teams_per_cta, &a.team_elems);
         a.total_items = (int64_t)nv * ns * ((int64_t)1 << (pl.n - a.pass.T));
         int e = launch_tile_pass(a, stream);
         if (e) return cuda_fail(e, "tile pass launch");

@@ -26,6 +26,7 @@
 // arrives last adds them in slice order (deterministic) and runs the epilogue.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -315,9 +316,8 @@ __global__ void __launch_bounds__(NT, 1) k_gram(const __grid_constant__ GramArgs
 // Measured alternative, kept out: one cp.async.bulk per 256-byte operand row (128 bulk copies
 // per stage) costs ~60 cycles per copy in the copy engine and ran 1.7x SLOWER than the classic
 // kernel.
-constexpr int WS_BM = 64, WS_BN = 64, WS_WM = 16, WS_WN = 32, WS_STAGES = 5;
+constexpr int WS_BM = 64, WS_BN = 64, WS_STAGES = 5;
 constexpr int WS_STAGE_ELEMS = (WS_BM + WS_BN) * BK;
-constexpr int WS_NT = 288;
 constexpr int WS_SMEM = WS_STAGES * WS_STAGE_ELEMS * (int)sizeof(double2) + 2 * WS_STAGES * 8;
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -336,8 +336,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
 }
-__global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ GramArgs A) {
-    constexpr int BM = WS_BM, BN = WS_BN, WM = WS_WM, WN = WS_WN;
+// WM x WN = consumer warp tile; (64 / WM) * (64 / WN) consumer warps + one producer warp group
+// (registers are allotted per group of 4 warps, so the producer occupies a whole group).
+template <int WM, int WN>
+__global__ void __launch_bounds__((64 / WM) * (64 / WN) * 32 + 128, 1) k_gram3m_ws(const __grid_constant__ GramArgs A) {
+    constexpr int BM = WS_BM, BN = WS_BN;
+    constexpr int NCW = (BM / WM) * (BN / WN);      // consumer warps
+    constexpr int CT = NCW * 32;                     // consumer threads
+    constexpr int REG_CONS = NCW == 8 ? 208 : 112, REG_PROD = NCW == 8 ? 40 : 24;
     constexpr int MI = WM / 8, NI = WN / 8, WARPS_M = BM / WM;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
         s_tile[1] = t;
         for (int s = 0; s < WS_STAGES; ++s) {
             mbar_init(full + s, 32);   // one asynchronous arrival per producer lane
-            mbar_init(empty + s, 8);    // one arrival per consumer warp
+            mbar_init(empty + s, NCW);  // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -383,17 +389,21 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
     const int kt_end = (int)((int64_t)KT_all * (slice + 1) / nslices);
     const int KT = kt_end - kt_begin;
 
-    if (warp == 8) {
-        // ================= producer =================
+    if (warp >= NCW) {
+        // ================= producer warp group =================
+        // hand most of this group's registers to the consumers (setmaxnreg works per warp group)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_PROD));
+        if (warp != NCW) return;
         // lane -> (row parity, 16-byte chunk); chunk c = lane + 32 j  <=>  row 2j + (lane >> 4)
         const int pr = lane >> 4, pc = lane & 15;
         const bool full_tile = (row0 + BM <= A.nx) && (col0 + BN <= A.ny) && (A.dim % BK == 0);
         const double2* pa = A.X + (row0 + pr) * A.dim + (int64_t)kt_begin * BK + pc;
         const double2* pb = A.Y + (col0 + pr) * A.dim + (int64_t)kt_begin * BK + pc;
         const int64_t step = 2 * A.dim;
+        int s = 0;
+        unsigned eph = 1;  // parity of the empty-barrier phase to wait for (first ring pass: none)
         for (int kt = 0; kt < KT; ++kt) {
-            const int s = kt % WS_STAGES;
-            if (kt >= WS_STAGES) mbar_wait(empty + s, ((kt / WS_STAGES) - 1) & 1);
+            if (kt >= WS_STAGES) mbar_wait(empty + s, eph);
             double2* sa = sm + s * WS_STAGE_ELEMS;
             double2* sb = sa + BM * BK;
             if (full_tile) {
@@ -422,12 +432,17 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
                          : "memory");
             pa += BK;
             pb += BK;
+            if (++s == WS_STAGES) {
+                s = 0;
+                eph ^= 1u;
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         return;
     }
 
     // ================= consumers =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_CONS));
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int lr = lane >> 2, lq = lane & 3;
     double acc[3][MI][NI][2];
@@ -438,25 +453,57 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < NI; ++j) acc[s][i][j][0] = acc[s][i][j][1] = 0.0;
 
+    // Software pipeline over (k-tile, k-step): the fragments AND the 3M sums (Xr+Xi, Yi-Yr) of the
+    // next step are produced while the current step feeds the tensor pipe, also across k-tile
+    // boundaries, so neither LDS nor DADD latency nor the mbarrier wait sits in front of a DMMA.
+    const int a_row = wm * WM + lr, b_row = wn * WN + lr;
+    double2 a[MI], b[NI], an[MI], bn[NI];
+    double a2[MI], b2[NI];
+    if (KT > 0) {
+        mbar_wait(full + 0, 0);
+        const double2* sa = sm;
+        const double2* sb = sa + BM * BK;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            a[i] = sa[slot(a_row + i * 8, lq)];
+            a2[i] = a[i].x + a[i].y;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            b[j] = sb[slot(b_row + j * 8, lq)];
+            b2[j] = b[j].y - b[j].x;
+        }
+    }
+    int s = 0;
+    unsigned fph = 0;  // parity of the full-barrier phase of stage s
     for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % WS_STAGES;
-        mbar_wait(full + s, (kt / WS_STAGES) & 1);
         const double2* sa = sm + s * WS_STAGE_ELEMS;
         const double2* sb = sa + BM * BK;
-        // fragments of step kk + 1 are fetched while step kk feeds the tensor pipe
-        double2 a[MI], b[NI], an[MI], bn[NI];
-#pragma unroll
-        for (int i = 0; i < MI; ++i) a[i] = sa[slot(wm * WM + i * 8 + lr, lq)];
-#pragma unroll
-        for (int j = 0; j < NI; ++j) b[j] = sb[slot(wn * WN + j * 8 + lr, lq)];
+        int sn = s + 1;
+        unsigned nph = fph;
+        if (sn == WS_STAGES) {
+            sn = 0;
+            nph ^= 1u;
+        }
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
+            bool have_next = true;
             if (kk + 1 < BK / 4) {
                 const int ch = (kk + 1) * 4 + lq;
 #pragma unroll
-                for (int i = 0; i < MI; ++i) an[i] = sa[slot(wm * WM + i * 8 + lr, ch)];
+                for (int i = 0; i < MI; ++i) an[i] = sa[slot(a_row + i * 8, ch)];
 #pragma unroll
-                for (int j = 0; j < NI; ++j) bn[j] = sb[slot(wn * WN + j * 8 + lr, ch)];
+                for (int j = 0; j < NI; ++j) bn[j] = sb[slot(b_row + j * 8, ch)];
+            } else if (kt + 1 < KT) {
+                mbar_wait(full + sn, nph);
+                const double2* na = sm + sn * WS_STAGE_ELEMS;
+                const double2* nb = na + BM * BK;
+#pragma unroll
+                for (int i = 0; i < MI; ++i) an[i] = na[slot(a_row + i * 8, lq)];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) bn[j] = nb[slot(b_row + j * 8, lq)];
+            } else {
+                have_next = false;
             }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
@@ -466,24 +513,29 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma(acc[1][i][j][0], acc[1][i][j][1], a[i].y, b[j].y);
-            double a2[MI], b2[NI];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) a2[i] = a[i].x + a[i].y;
-#pragma unroll
-            for (int j = 0; j < NI; ++j) b2[j] = b[j].y - b[j].x;
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma(acc[2][i][j][0], acc[2][i][j][1], a2[i], b2[j]);
-            if (kk + 1 < BK / 4) {
+            if (kk + 1 == BK / 4) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
+            }
+            if (have_next) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i) a[i] = an[i];
+                for (int i = 0; i < MI; ++i) {
+                    a[i] = an[i];
+                    a2[i] = an[i].x + an[i].y;
+                }
 #pragma unroll
-                for (int j = 0; j < NI; ++j) b[j] = bn[j];
+                for (int j = 0; j < NI; ++j) {
+                    b[j] = bn[j];
+                    b2[j] = bn[j].y - bn[j].x;
+                }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
+        s = sn;
+        fph = nph;
     }
 
     double re[MI][NI][2], im[MI][NI][2];
@@ -497,7 +549,6 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
                 im[i][j][e] = acc[2][i][j][e] + (acc[0][i][j][e] - acc[1][i][j][e]);
             }
 
-    constexpr int CT = 256;  // consumer threads
     if (nslices > 1) {
         const int r = tile - A.full_units;
         double2* mine = A.partial + ((size_t)r * nslices + slice) * (BM * BN);
@@ -509,9 +560,9 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
                 for (int e = 0; e < 2; ++e)
                     mine[((i * NI + j) * 2 + e) * CT + tid] = double2{re[i][j][e], im[i][j][e]};
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
         if (tid == 0) s_last = (atomicAdd(A.counters + r, 1u) == (unsigned)(nslices - 1));
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
         if (!s_last) return;
         __threadfence();
 #pragma unroll
@@ -560,14 +611,15 @@ __global__ void __launch_bounds__(WS_NT, 1) k_gram3m_ws(const __grid_constant__ 
     }
 }
 
-// KERNEL: 0 = classic template, 1 = warp-specialised 3M
+// KERNEL: 0 = classic template, 1 = warp-specialised 3M with 8 consumer warps, 2 = with 16
 template <int BM, int BN, int WM, int WN, int MODE, int KERNEL>
 int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream) {
-    constexpr int SMEM = KERNEL == 1 ? WS_SMEM : STAGES * (BM + BN) * BK * (int)sizeof(double2);
-    constexpr int THREADS = KERNEL == 1 ? WS_NT : NT;
+    constexpr int SMEM = KERNEL != 0 ? WS_SMEM : STAGES * (BM + BN) * BK * (int)sizeof(double2);
+    constexpr int THREADS = KERNEL == 1 ? 8 * 32 + 128 : (KERNEL == 2 ? 16 * 32 + 128 : NT);
     cudaError_t e;
-    if (KERNEL == 1) e = cudaFuncSetAttribute(k_gram3m_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if constexpr (KERNEL == 1) e = cudaFuncSetAttribute(k_gram3m_ws<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else if constexpr (KERNEL == 2) e = cudaFuncSetAttribute(k_gram3m_ws<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     else e = cudaFuncSetAttribute(k_gram<BM, BN, WM, WN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
@@ -600,12 +652,17 @@ int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, i
         const int s_max = KT / 16 < 16 ? KT / 16 : 16;
         double best = 1.0;
         for (int sl = 2; sl <= s_max; ++sl) {
-            const double t = (double)((rem * sl + G - 1) / G) / sl;
+            // + 1 % of a tile-time per slice: partial-sum traffic, pipeline fill, launch
+            const double t = (double)((rem * sl + G - 1) / G) / sl + 0.01 * sl;
             if (t < best - 1e-9) {
                 best = t;
                 slices = sl;
             }
         }
+    }
+    if (const char* env = getenv("B200SQ_GRAM_SLICES")) {  // tuning override
+        const int forced = atoi(env);
+        if (forced >= 1 && rem) slices = forced;
     }
     if (slices == 1) rem = 0;
     A.full_units = A.n_tiles - rem;
@@ -615,6 +672,16 @@ int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     const int units = A.full_units + rem * slices;
     void* ws = nullptr;
     if (rem) {
+        static bool pool_configured[64] = {};
+        if (dev >= 0 && dev < 64 && !pool_configured[dev]) {
+            // keep freed workspace in the stream-ordered pool instead of returning it to the driver
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_configured[dev] = true;
+        }
         const size_t part_bytes = (size_t)rem * slices * BM * BN * sizeof(double2);
         const size_t cnt_bytes = ((size_t)rem * sizeof(unsigned) + 255) & ~(size_t)255;
         e = cudaMallocAsync(&ws, part_bytes + cnt_bytes, stream);
@@ -623,7 +690,8 @@ int launch_variant(const double2* x, int64_t nx, const double2* y, int64_t ny, i
         A.partial = (double2*)((char*)ws + cnt_bytes);
         cudaMemsetAsync(ws, 0, cnt_bytes, stream);
     }
-    if (KERNEL == 1) k_gram3m_ws<<<units, THREADS, SMEM, stream>>>(A);
+    if constexpr (KERNEL == 1) k_gram3m_ws<16, 32><<<units, THREADS, SMEM, stream>>>(A);
+    else if constexpr (KERNEL == 2) k_gram3m_ws<16, 16><<<units, THREADS, SMEM, stream>>>(A);
     else k_gram<BM, BN, WM, WN, MODE><<<units, THREADS, SMEM, stream>>>(A);
     count_launch();
     e = cudaGetLastError();
@@ -637,8 +705,12 @@ int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int6
                 int64_t ldk, uint32_t flags, cudaStream_t stream) {
     if (nx <= 0 || ny <= 0) return 0;
     if (flags & B200SQ_GRAM_3M) {
-        if (!(flags & B200SQ_GRAM_CLASSIC))
+        if (!(flags & B200SQ_GRAM_CLASSIC)) {
+            static const int ws_warps = getenv("B200SQ_GRAM_WARPS") ? atoi(getenv("B200SQ_GRAM_WARPS")) : 8;
+            if (ws_warps == 16)
+                return launch_variant<64, 64, 16, 16, 1, 2>(x, nx, y, ny, dim, k, ldk, flags, stream);
             return launch_variant<64, 64, 16, 32, 1, 1>(x, nx, y, ny, dim, k, ldk, flags, stream);
+        }
         return launch_variant<64, 64, 16, 32, 1, 0>(x, nx, y, ny, dim, k, ldk, flags, stream);
     }
     return launch_variant<128, 64, 32, 32, 0, 0>(x, nx, y, ny, dim, k, ldk, flags, stream);

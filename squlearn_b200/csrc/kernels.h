@@ -38,7 +38,7 @@ struct TileArgs {
 
 // Returns cudaError_t as int.
 int launch_tile_pass(const TileArgs& args, cudaStream_t stream);
-int tile_pass_smem_bytes(int T, int mat_elems, int* team_size, int* teams_per_cta, int* team_elems);
+int tile_pass_smem_bytes(int T, int mat_elems, int first, int* team_size, int* teams_per_cta, int* team_elems);
 
 int launch_expvals(const double2* psi, int64_t n_states, int n_qubits, int n_terms,
                    const uint32_t* xmask_dev, const uint32_t* zmask_dev, double* out,

@@ -40,7 +40,7 @@ struct Uop {         // host-side micro-op (the device gets the packed DUop belo
     uint32_t ctrl;   // U1CTRL/U2: control mask (ext positions). DIAG: skip mask (bit j: phase j == 1)
     int32_t mat;     // offset of this op's matrix in the team's matrix area (double2 units)
     int32_t swap;    // U2: 1 when the gate's first qubit sits on r1 (matrix must be permuted)
-    int32_t pat;     // DIAG: 2 bits per register slot k: phase-index bits contributed by slot k
+    int32_t pat;     // DIAG: (ra + 1) | (rb + 1) << 2, ra / rb = register slot of the 1st / 2nd qubit or -1
 };
 
 struct Round {       // host-side round
@@ -58,9 +58,10 @@ struct DUop {        // 16 bytes
     uint16_t mat;
     uint16_t pat;
 };
-struct DRound {      // 8 bytes
+struct DRound {      // 24 bytes
     uint8_t nb, rb[3];
     uint16_t u0, u1;  // micro-op range relative to the pass
+    uint16_t ksw[8];  // swizzled SMEM offset of register slot k: ko[k] ^ ((ko[k] >> 3) & 7)
 };
 struct DPass {       // device view of a pass
     int32_t T, first, n_rounds, n_uops, mat_elems, n_lruns, n_oruns;
@@ -74,8 +75,8 @@ struct DInit {       // a 1-qubit gate folded into the product-state start of th
     uint16_t gate;
     uint8_t qubit, pad;
 };
-constexpr int kMaxPassUops = 128;    // per pass, so that a pass fits the 4 KiB kernel-parameter space
-constexpr int kMaxPassRounds = 64;
+constexpr int kMaxPassUops = 96;     // per pass, so that a pass fits the 4 KiB kernel-parameter space
+constexpr int kMaxPassRounds = 48;
 constexpr int kMaxInit = 96;
 
 inline DUop pack_uop(const Uop& u, int pass_u0) {
@@ -99,6 +100,12 @@ inline DRound pack_round(const Round& r, int pass_u0) {
     d.rb[2] = (uint8_t)r.rb[2];
     d.u0 = (uint16_t)(r.u0 - pass_u0);
     d.u1 = (uint16_t)(r.u1 - pass_u0);
+    for (int k = 0; k < 8; ++k) {
+        uint32_t ko = 0;
+        for (int c = 0; c < r.nb; ++c)
+            if (k >> c & 1) ko |= 1u << r.rb[c];
+        d.ksw[k] = (uint16_t)(ko ^ ((ko >> 3) & 7u));
+    }
     return d;
 }
 
@@ -214,7 +221,9 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
     if (n < 1 || n > B200SQ_MAX_QUBITS) throw std::invalid_argument("n_qubits out of range");
     Plan plan;
     plan.n = n;
-    int T = tile_bits <= 0 ? 12 : tile_bits;
+    // default tile: the whole state when it fits 64 KiB (n <= 12); otherwise 2^11 amplitudes so that
+    // two tile buffers (double buffering) still leave three CTAs per SM
+    int T = tile_bits <= 0 ? (n <= 12 ? 12 : 11) : tile_bits;
     if (T > 13) throw std::invalid_argument("tile_bits must be <= 13");
     T = std::min(T, n);
     plan.T = T;
@@ -301,7 +310,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                 }
             }
         }
-        if (absorbed.empty() && !pending.empty())
+        if (absorbed.empty() && !pending.empty() && !first)  // the first pass may only write the product start
             throw std::runtime_error("planner made no progress (gate needs more target qubits than a tile)");
 
         // ---- ext positions
@@ -392,13 +401,13 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                         case B200SQ_CRZ: u.ctrl = 0x5; break;                       // control = 0
                         default: u.ctrl = 0; break;
                     }
-                    // phase-index bits that depend on the register slot k
-                    for (int k = 0; k < 8; ++k)
-                        for (int c = 0; c < rd.nb; ++c)
-                            if (k >> c & 1) {
-                                if (rd.rb[c] == u.r0) u.pat |= 1 << (2 * k);
-                                if (rd.rb[c] == u.r1) u.pat |= 2 << (2 * k);
-                            }
+                    // register slot (or -1) of each of the gate's qubits: pat = (ra + 1) | (rb + 1) << 2
+                    int ra = -1, rb = -1;
+                    for (int c = 0; c < rd.nb; ++c) {
+                        if (rd.rb[c] == u.r0) ra = c;
+                        if (u.r1 >= 0 && rd.rb[c] == u.r1) rb = c;
+                    }
+                    u.pat = (ra + 1) | ((rb + 1) << 2);
                     mat_off += 4;
                 } else if (info.nq - info.nctrl == 1) {
                     u.r0 = regbit(g.q[info.nctrl]);

@@ -264,26 +264,50 @@ B200SQ_HD void u2_general(double2 (&a)[1 << NB], const double2* __restrict__ m, 
     }
 }
 
-template <int NB>
-B200SQ_HD void diag_apply(double2 (&a)[1 << NB], const DUop& u, const double2* __restrict__ m,
-                          uint32_t e) {
-    uint32_t base = (e >> u.r0) & 1u;
-    if (u.r1 >= 0) base |= ((e >> u.r1) & 1u) << 1;
-    const uint32_t skip = u.ctrl, pat = u.pat;
-    if (pat == 0) {
-        // none of the gate's qubits is a register bit: one phase for all of this thread's amplitudes
-        if (!((skip >> base) & 1u)) {
-            const double2 ph = m[base];
+// Diagonal gate.  RA / RB = register slot that carries the gate's first / second qubit, or -1 when
+// that qubit is not a register bit of this round (then its bit comes from the thread's index e).
+// With both known at compile time the phase index of every register amplitude is a constant, so a
+// DIAG costs <= 4 phase loads + one (predicated) complex multiply per amplitude and no per-amplitude
+// integer work.
+template <int NB, int RA, int RB>
+B200SQ_HD void diag_case(double2 (&a)[1 << NB], const DUop& u, const double2* __restrict__ m,
+                         uint32_t e) {
+    uint32_t base = 0;
+    if (RA < 0) base |= (e >> u.r0) & 1u;
+    if (RB < 0 && u.r1 >= 0) base |= ((e >> u.r1) & 1u) << 1;
+    const uint32_t skip = u.ctrl;
+    double2 ph[4];
+    bool on[4];
 #pragma unroll
-            for (int k = 0; k < (1 << NB); ++k) a[k] = cmul(a[k], ph);
-        }
-        return;
+    for (int v = 0; v < 4; ++v) {
+        if ((RA < 0 && (v & 1)) || (RB < 0 && (v & 2))) continue;
+        const uint32_t idx = base | (uint32_t)v;
+        on[v] = !((skip >> idx) & 1u);
+        ph[v] = m[idx];
     }
 #pragma unroll
     for (int k = 0; k < (1 << NB); ++k) {
-        const uint32_t idx = base | ((pat >> (2 * k)) & 3u);
-        if (!((skip >> idx) & 1u)) a[k] = cmul(a[k], m[idx]);
+        const int v = (RA >= 0 ? ((k >> (RA >= 0 ? RA : 0)) & 1) : 0) |
+                      (RB >= 0 ? (((k >> (RB >= 0 ? RB : 0)) & 1) << 1) : 0);
+        if (on[v]) a[k] = cmul(a[k], ph[v]);
     }
+}
+
+template <int NB>
+B200SQ_HD void diag_apply(double2 (&a)[1 << NB], const DUop& u, const double2* __restrict__ m,
+                          uint32_t e) {
+    // u.pat = (RA + 1) | (RB + 1) << 2
+#define B200SQ_DC(RA, RB)                                                              \
+    case ((RA) + 1) | (((RB) + 1) << 2):                                               \
+        if ((RA) < NB && (RB) < NB) diag_case<NB, ((RA) < NB ? (RA) : -1), ((RB) < NB ? (RB) : -1)>(a, u, m, e); \
+        break;
+    switch (u.pat) {
+        B200SQ_DC(-1, -1) B200SQ_DC(0, -1) B200SQ_DC(1, -1) B200SQ_DC(2, -1)
+        B200SQ_DC(-1, 0) B200SQ_DC(-1, 1) B200SQ_DC(-1, 2)
+        B200SQ_DC(0, 1) B200SQ_DC(0, 2) B200SQ_DC(1, 0) B200SQ_DC(1, 2) B200SQ_DC(2, 0) B200SQ_DC(2, 1)
+        default: break;
+    }
+#undef B200SQ_DC
 }
 
 template <int NB>
@@ -316,6 +340,8 @@ B200SQ_HD void apply_uop(double2 (&a)[1 << NB], const DUop& u, const double2* __
 }
 
 // One thread's share of a round: groups g = tid, tid + nthreads, ...
+// SMEM address of register slot k of group g:  sw(base | ko[k]) = (base ^ ((base >> 3) & 7)) ^ ksw[k]
+// because base and ko[k] have disjoint bits (ksw[k] is precomputed on the host, see pack_round).
 template <int NB>
 B200SQ_HD void exec_round_nb(double2* tile, const DRound& rd, const DUop* uops, const double2* mats,
                              uint32_t ext_base, int T, int tid, int nthreads) {
@@ -338,20 +364,17 @@ B200SQ_HD void exec_round_nb(double2* tile, const DRound& rd, const DUop* uops, 
             const uint32_t low = base & ((1u << rd.rb[c]) - 1u);
             base = ((base >> rd.rb[c]) << (rd.rb[c] + 1)) | low;
         }
-        uint32_t addr[NK];
+        const uint32_t bsw = tile_sw(base);
         double2 a[NK];
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            addr[k] = tile_sw(base | ko[k]);
-            a[k] = tile[addr[k]];
-        }
+        for (int k = 0; k < NK; ++k) a[k] = tile[bsw ^ rd.ksw[k]];
         const uint32_t e = ext_base | base;
         for (int ui = rd.u0; ui < rd.u1; ++ui) {
             const DUop u = uops[ui];
             apply_uop<NB>(a, u, mats + u.mat, e, ko);
         }
 #pragma unroll
-        for (int k = 0; k < NK; ++k) tile[addr[k]] = a[k];
+        for (int k = 0; k < NK; ++k) tile[bsw ^ rd.ksw[k]] = a[k];
     }
 }
 
