@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sq.so")
 SOURCES = ["api.cu", "sim_kernels.cu", "gram_kernels.cu"]
-HEADERS = ["plan.hpp", "uop_exec.cuh", "kernels.h", os.path.join(ROOT, "include", "b200sq.h")]
+HEADERS = ["plan.hpp", "tile_exec.cuh", "kernels.h", os.path.join(ROOT, "include", "b200sq.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

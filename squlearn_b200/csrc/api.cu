@@ -2,6 +2,7 @@
 // device mirrors of the plan, launch sequencing.  There is no CPU compute path in this library.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -37,6 +38,9 @@ struct b200sq_program {
     int device = -1;
     b200sq_gate* d_gates = nullptr;
     bool gates_dirty = true;
+    std::vector<std::vector<uint8_t>> blobs;  // one device blob per pass (plan.hpp: build_pass_blob)
+    unsigned char* d_blobs = nullptr;
+    std::vector<size_t> blob_off;
     int32_t* d_var_gate = nullptr;
     double* d_var_shift = nullptr;
     int var_cap = 0;
@@ -49,6 +53,7 @@ struct b200sq_program {
             cudaGetDevice(&cur);
             cudaSetDevice(device);
             cudaFree(d_gates);
+            cudaFree(d_blobs);
             cudaFree(d_var_gate);
             cudaFree(d_var_shift);
             cudaFree(d_masks);
@@ -69,8 +74,27 @@ int ensure_device(b200sq_program* p, cudaStream_t stream) {
         const Plan& pl = p->plan;
         size_t ng = std::max<size_t>(pl.gates.size(), 1);
         if ((e = cudaMalloc(&p->d_gates, ng * sizeof(b200sq_gate))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        size_t total = 0;
+        p->blob_off.clear();
+        for (const auto& b : p->blobs) {
+            p->blob_off.push_back(total);
+            total += (b.size() + 255) & ~(size_t)255;
+        }
+        if ((e = cudaMalloc(&p->d_blobs, std::max<size_t>(total, 256))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        for (size_t i = 0; i < p->blobs.size(); ++i) {
+            e = cudaMemcpyAsync(p->d_blobs + p->blob_off[i], p->blobs[i].data(), p->blobs[i].size(),
+                                cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "upload pass blobs");
+        }
         p->device = dev;
         p->gates_dirty = true;
+        // The inter-pass workspaces come from the device's default stream-ordered pool: keep freed
+        // blocks cached across synchronisation points instead of returning them to the driver.
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     if (p->gates_dirty && !p->plan.gates.empty()) {
         e = cudaMemcpyAsync(p->d_gates, p->plan.gates.data(), p->plan.gates.size() * sizeof(b200sq_gate),
@@ -123,43 +147,51 @@ int upload_masks(b200sq_program* p, int n_terms, const uint32_t* xm, const uint3
 }
 
 // Run every pass of the plan on samples [s0, s0 + ns) and variants [v0, v0 + nv).
+// Passes whose output layout is the full state write psi; compact inter-pass layouts go through a
+// stream-ordered scratch allocation (at most two buffers, ping-pong).
 int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v0, int nv, int d,
                const double* x, const double* table, bool have_variants, double2* psi, int64_t psi_off,
                bool fuse_expvals, int n_terms, double* out, cudaStream_t stream) {
     const Plan& pl = p->plan;
-    for (size_t ip = 0; ip < pl.passes.size(); ++ip) {
+    const int64_t n_states = (int64_t)nv * ns;
+    double2* ws[2] = {nullptr, nullptr};
+    int flip = 0;
+    const double2* src = nullptr;
+    int64_t src_vstride = 0, src_off = 0;
+    int src_bits = 0;
+    int rc = 0;
+    for (size_t ip = 0; ip < pl.passes.size() && rc == 0; ++ip) {
         TileArgs a;
         std::memset(&a, 0, sizeof(a));
-        const Pass& ps = pl.passes[ip];
-        a.pass.T = ps.T;
-        a.pass.first = ps.first;
-        a.pass.n_rounds = ps.r1 - ps.r0;
-        a.pass.n_uops = ps.u1 - ps.u0;
-        a.pass.mat_elems = ps.mat_elems;
-        a.pass.n_lruns = ps.n_lruns;
-        a.pass.n_oruns = ps.n_oruns;
-        for (int i = 0; i < kMaxRuns; ++i) {
-            a.pass.lmask[i] = ps.lmask[i];
-            a.pass.lshift[i] = ps.lshift[i];
-            a.pass.omask[i] = ps.omask[i];
-            a.pass.oshift[i] = ps.oshift[i];
+        const DPass& P = *reinterpret_cast<const DPass*>(p->blobs[ip].data());
+        a.blob = p->d_blobs + p->blob_off[ip];
+        a.blob_bytes = P.blob_bytes;
+        const bool last = ip + 1 == pl.passes.size();
+        const bool to_out = fuse_expvals && last;
+        if (P.has_src && P.in_bits != src_bits) { rc = fail(5, "internal: layout chain broken"); break; }
+        if (to_out) {
+            a.dst = nullptr;
+        } else if (P.out_bits == pl.n) {
+            a.dst = psi;
+            a.dst_vstride = n_total;
+            a.dst_off = psi_off;
+        } else if (src && P.out_bits == src_bits && P.n_fresh == 0) {
+            a.dst = const_cast<double2*>(src);  // same layout: in place
+            a.dst_vstride = src_vstride;
+            a.dst_off = src_off;
+        } else {
+            if (ws[flip]) { cudaFreeAsync(ws[flip], stream); ws[flip] = nullptr; }
+            cudaError_t e = cudaMallocAsync(&ws[flip], ((size_t)n_states << P.out_bits) * sizeof(double2), stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync (inter-pass workspace)"); break; }
+            a.dst = ws[flip];
+            a.dst_vstride = ns;
+            a.dst_off = (int64_t)v0 * ns + s0;
+            flip ^= 1;
         }
-        for (int i = 0; i < 32; ++i) a.pass.extq[i] = ps.extq[i];
-        a.n_init = 0;
-        if (ps.first) {
-            a.n_init = (int)pl.init_gates.size();
-            for (int i = 0; i < a.n_init; ++i) {
-                a.inits[i].gate = (uint16_t)pl.init_gates[i];
-                a.inits[i].qubit = (uint8_t)pl.gates[pl.init_gates[i]].q[0];
-            }
-        }
-        if (a.pass.n_rounds > kMaxPassRounds || a.pass.n_uops > kMaxPassUops)
-            return fail(5, "internal: pass exceeds the kernel-parameter capacity");
-        for (int r = ps.r0; r < ps.r1; ++r) a.rounds[r - ps.r0] = pack_round(pl.rounds[r], ps.u0);
-        for (int u = ps.u0; u < ps.u1; ++u) a.uops[u - ps.u0] = pack_uop(pl.uops[u], ps.u0);
+        a.src = src;
+        a.src_vstride = src_vstride;
+        a.src_off = src_off;
         a.gates = p->d_gates;
-        a.psi = psi;
-        a.psi_off = psi_off;
         a.x = x;
         a.table = table;
         a.n_total = n_total;
@@ -171,18 +203,23 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.variant0 = v0;
         a.var_gate = have_variants ? p->d_var_gate : nullptr;
         a.var_shift = have_variants ? p->d_var_shift : nullptr;
-        const bool last = ip + 1 == pl.passes.size();
-        a.store = (fuse_expvals && last) ? 0 : 1;
-        a.n_terms = (fuse_expvals && last) ? n_terms : 0;
+        a.store = to_out ? 0 : 1;
+        a.n_terms = to_out ? n_terms : 0;
         a.xmask = p->d_masks;
         a.zmask = p->d_masks ? p->d_masks + n_terms : nullptr;
         a.out = out;
-        tile_pass_smem_bytes(a.pass.T, a.pass.mat_elems, a.pass.first, &a.team_size, &a.teams_per_cta, &a.team_elems);
-        a.total_items = (int64_t)nv * ns * ((int64_t)1 << (pl.n - a.pass.T));
+        tile_pass_geometry(P, &a);
+        a.total_items = n_states << P.n_obits;
         int e = launch_tile_pass(a, stream);
-        if (e) return cuda_fail(e, "tile pass launch");
+        if (e) { rc = cuda_fail(e, "tile pass launch"); break; }
+        src = a.dst;
+        src_vstride = a.dst_vstride;
+        src_off = a.dst_off;
+        src_bits = P.out_bits;
     }
-    return 0;
+    for (int i = 0; i < 2; ++i)
+        if (ws[i]) cudaFreeAsync(ws[i], stream);
+    return rc;
 }
 
 }  // namespace
@@ -217,6 +254,7 @@ int b200sq_program_create(int n_qubits, int n_gates, const b200sq_gate* gates, i
         }
         b200sq_program* p = new b200sq_program();
         p->plan = make_plan(n_qubits, g, tile_bits);
+        for (size_t ip = 0; ip < p->plan.passes.size(); ++ip) p->blobs.push_back(build_pass_blob(p->plan, (int)ip));
         *out = p;
         return 0;
     } catch (const std::exception& e) {
@@ -240,20 +278,22 @@ int b200sq_program_num_passes(const b200sq_program* prog) {
     return prog ? (int)prog->plan.passes.size() : -1;
 }
 
-// Dump layout (int32 words): [n, T, n_passes, n_rounds, n_uops] then per pass
-// [T, first, r0, r1, u0, u1, mat_elems, tile_qubits[T]...], then per round [nb, rb0, rb1, rb2, u0, u1],
-// then per uop [kind, gate, r0, r1, ctrl, mat, swap].
+// Dump layout (int32 words): [n, T, n_passes, n_rounds, n_steps] then per pass
+// [T, a_in, a_out, last, r0, r1, s0, s1, mat_elems, n_fresh, n_tabs, tile_qubits[T]...], then per round
+// [nb, rb0, rb1, rb2, s0, s1], then per step [kind, gate, r0, r1, ctrl, mat, swap], then the folded gates
+// [count, gate...].
 int b200sq_program_dump(const b200sq_program* prog, int32_t* buf, int capacity, int* n_written) {
     if (!prog || !n_written) return fail(2, "NULL argument");
     std::vector<int32_t> w;
     const Plan& pl = prog->plan;
-    w.insert(w.end(), {pl.n, pl.T, (int32_t)pl.passes.size(), (int32_t)pl.rounds.size(), (int32_t)pl.uops.size()});
+    w.insert(w.end(), {pl.n, pl.T, (int32_t)pl.passes.size(), (int32_t)pl.rounds.size(), (int32_t)pl.steps.size()});
     for (const Pass& ps : pl.passes) {
-        w.insert(w.end(), {ps.T, ps.first, ps.r0, ps.r1, ps.u0, ps.u1, ps.mat_elems});
+        w.insert(w.end(), {ps.T, (int32_t)ps.a_in, (int32_t)ps.a_out, ps.last, ps.r0, ps.r1, ps.s0, ps.s1, ps.mat_elems,
+                           __builtin_popcount(ps.L & ~ps.a_in), ps.t1 - ps.t0});
         for (int i = 0; i < ps.T; ++i) w.push_back(ps.tile_qubits[i]);
     }
-    for (const Round& r : pl.rounds) w.insert(w.end(), {r.nb, r.rb[0], r.rb[1], r.rb[2], r.u0, r.u1});
-    for (const Uop& u : pl.uops) w.insert(w.end(), {u.kind, u.gate, u.r0, u.r1, (int32_t)u.ctrl, u.mat, u.swap});
+    for (const Round& r : pl.rounds) w.insert(w.end(), {r.nb, r.rb[0], r.rb[1], r.rb[2], r.s0, r.s1});
+    for (const Step& u : pl.steps) w.insert(w.end(), {u.kind, u.gate, u.r0, u.r1, (int32_t)u.ctrl, u.mat, u.swap});
     w.push_back((int32_t)pl.init_gates.size());
     for (int32_t g : pl.init_gates) w.push_back(g);
     *n_written = (int)w.size();

@@ -9,17 +9,16 @@
 namespace b200sq {
 
 struct TileArgs {
-    DPass pass;                        // this pass, its rounds and micro-ops travel in the kernel
-    DRound rounds[kMaxPassRounds];     // parameters (constant bank: uniform, broadcast reads)
-    DUop uops[kMaxPassUops];
-    DInit inits[kMaxInit];             // product-state prefix (first pass only)
-    int32_t n_init;
-    const b200sq_gate* gates;          // device gate table (angle coefficients)
-    double2* psi;              // states; state (v, i) lives at psi + ((v * n_total + i - psi_off) << n)
-    int64_t psi_off;
+    const unsigned char* blob;   // device copy of the pass blob (plan.hpp: build_pass_blob)
+    int32_t blob_bytes;
+    const b200sq_gate* gates;    // device gate table (angle coefficients)
+    // state (v, i) of the input / output layout lives at base + ((v * vstride + i - off) << layout bits)
+    const double2* src;
+    double2* dst;
+    int64_t src_vstride, src_off, dst_vstride, dst_off;
     const double* x;           // [n_total][d]
     const double* table;       // [slots][n_total]
-    int64_t n_total;           // samples in the whole call (row stride of table, variant stride of psi/out)
+    int64_t n_total;           // samples in the whole call (row stride of table, variant stride of out)
     int64_t sample0;           // first sample of this launch
     int64_t n_samples;         // samples in this launch
     int32_t n, d;
@@ -27,18 +26,18 @@ struct TileArgs {
     int32_t variant0;          // first variant of this launch
     const int32_t* var_gate;   // device, indexed by absolute variant; nullptr = unshifted
     const double* var_shift;
-    int32_t store;             // write the tile back to psi
+    int32_t store;             // write the tile to dst
     int32_t n_terms;           // > 0: reduce the tile to expectation values (requires T == n)
     const uint32_t* xmask;     // device
     const uint32_t* zmask;
     double* out;               // [n_variants_total][n_total][n_terms]
-    int32_t team_size, teams_per_cta, team_elems;
+    int32_t team_size, log2ts, teams_per_cta, team_elems;
     int64_t total_items;
 };
 
 // Returns cudaError_t as int.
 int launch_tile_pass(const TileArgs& args, cudaStream_t stream);
-int tile_pass_smem_bytes(int T, int mat_elems, int first, int* team_size, int* teams_per_cta, int* team_elems);
+void tile_pass_geometry(const DPass& pass, TileArgs* args);
 
 int launch_expvals(const double2* psi, int64_t n_states, int n_qubits, int n_terms,
                    const uint32_t* xmask_dev, const uint32_t* zmask_dev, double* out,

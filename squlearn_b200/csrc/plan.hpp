@@ -1,16 +1,34 @@
-// Gate-list -> pass / round / micro-op plan for the tile kernel (host-only C++, no CUDA).
+// Gate-list -> pass / round / step plan for the tile kernel (host-only C++, no CUDA).
 //
 // A PASS sweeps every state once: each thread team stages a TILE of 2^T amplitudes (the
 // amplitudes that differ only in the T "tile qubits") in shared memory, applies every gate the
 // tile can absorb, and writes the tile back.  Inside a pass, gates are grouped into ROUNDS: in a
 // round every thread holds the 2^nb (nb <= 3) amplitudes spanned by the round's register bits
-// and applies the round's MICRO-OPS to them in registers; rounds are separated by one team
-// barrier.  A gate can be absorbed by a pass when all qubits it acts on NON-diagonally are tile
-// qubits (controls and diagonal gates only read index bits, so they may sit anywhere).
+// and applies the round's STEPS to them in registers; rounds are separated by one team barrier.
+// A gate can be absorbed by a pass when all qubits it acts on NON-diagonally are tile qubits
+// (controls and diagonal gates only read index bits, so they may sit anywhere).
+//
+// ACTIVE QUBITS.  A qubit no gate has acted on non-diagonally is still |0>, so the state is
+// psi_active (x) |0..0>.  Between passes only psi_active is stored: the "compact layout" of an
+// active set A keeps amplitude bits in ascending qubit order over A (2^|A| amplitudes per
+// state).  A pass reads layout a_in and writes layout a_out = a_in | tile qubits (the last pass
+// writes the full 2^n layout).  Tile qubits that are not active yet are FRESH: the 1-qubit gates
+// that hit them before anything else are folded into 2-vectors v_q, and the tile is staged as
+//     tile[l] = src[l restricted to a_in] * prod_{q fresh} v_q[bit_q(l)]
+// (two small product tables in shared memory, one or two complex multiplies per amplitude).  For
+// the first pass (a_in empty) this is the product-state start; for ChebyshevPQC(16,2) it means the
+// first pass touches 2^11 amplitudes per state and the second pass never READS the full state.
+//
+// STEPS.  Register work is coarse so that the per-step decode cost is amortised:
+//   L_RX / L_REAL / L_GEN  one 2x2 gate of one family on each register slot of a slot mask
+//   DTAB                   multiply by a precomputed phase table: a run of commuting diagonal
+//                          gates (rz, p, cz, crz, rzz, ...) on one group of tile bits collapses to
+//                          a single complex multiply per amplitude
+//   DIAG / U1CTRL / U2     single diagonal gate, controlled 2x2, 4x4
 //
 // Index spaces:  "local" = position inside the tile (0..T-1, tile qubits in ascending order);
 // "ext" = local bits followed by the remaining ("outer") qubits in ascending order, so
-// ext = local | outer_index << T.  All masks / bit positions in micro-ops are ext positions.
+// ext = local | outer_index << T.  All masks / bit positions in steps are ext positions.
 #pragma once
 
 #include <algorithm>
@@ -24,106 +42,63 @@
 
 namespace b200sq {
 
-// Micro-op kinds.  The U1 family differs only in how much FP64 work the 2x2 product needs:
-//   U1RX   [[c, -is], [-is, c]]  (rx)            8 FP64 instructions per amplitude pair
-//   U1REAL real 2x2 (ry, h, x)                   8
-//   U1G    general complex 2x2 (y, sx, u)       16
-//   U1CTRL general 2x2 under a control mask (cx, cy, ch, csx, crx, cry, ccx)
-enum UopKind : int32_t { UOP_U1G = 0, UOP_U2 = 1, UOP_DIAG = 2, UOP_U1RX = 3, UOP_U1REAL = 4,
-                         UOP_U1CTRL = 5 };
+enum StepKind : int32_t {
+    ST_U2 = 1,      // 4x4 on register slots r0 > r1 (r0 = matrix MSB), optional control mask
+    ST_DIAG = 2,    // single diagonal gate; r0 / r1 = ext positions of its qubits
+    ST_U1CTRL = 5,  // general 2x2 on register slot r0 under a control mask (cx, cy, ch, crx, ccx ...)
+    ST_LRX = 6,     // [[c, -is], [-is, c]] on every register slot of mask r0 (matrix of slot c at mat + 4c)
+    ST_LREAL = 7,   // real 2x2 (ry, h, x)
+    ST_LGEN = 8,    // general complex 2x2 (y, sx, u)
+    ST_DTAB = 9,    // a[k] *= table[(local_index >> r0) & ((1 << r1) - 1)], table at mat
+};
+enum MatKind : int32_t { MAT_U1 = 0, MAT_U2 = 1, MAT_DIAG = 2 };
 
-struct Uop {         // host-side micro-op (the device gets the packed DUop below)
-    int32_t kind;    // UopKind
-    int32_t gate;    // index into the gate table (kind, angle coefficients)
-    int32_t r0, r1;  // U1*: r0 = register bit. U2: r0 > r1 register bits (r0 = matrix MSB).
-                     // DIAG: ext positions of the first / second qubit (r1 = -1 for 1-qubit)
+struct Step {        // host-side step (the device gets the packed DStep below)
+    int32_t kind;    // StepKind
+    int32_t gate;    // gate index (single-gate steps), -1 otherwise
+    int32_t r0, r1;
     uint32_t ctrl;   // U1CTRL/U2: control mask (ext positions). DIAG: skip mask (bit j: phase j == 1)
-    int32_t mat;     // offset of this op's matrix in the team's matrix area (double2 units)
+    int32_t mat;     // offset in the team's matrix area (double2 units)
     int32_t swap;    // U2: 1 when the gate's first qubit sits on r1 (matrix must be permuted)
     int32_t pat;     // DIAG: (ra + 1) | (rb + 1) << 2, ra / rb = register slot of the 1st / 2nd qubit or -1
 };
-
-struct Round {       // host-side round
+struct MatRec {      // one gate matrix to build per (sample, tile)
+    int32_t gate, kind, swap, mat;
+};
+struct TabGate {     // a diagonal gate folded into a phase table
+    int32_t m4;      // offset of its four phases (built as a MAT_DIAG MatRec)
+    int32_t p0, p1;  // ext positions of its qubits (p1 = -1 for one-qubit gates)
+};
+struct Tab {
+    int32_t mat, lo, nbits, g0, g1;  // table offset, first local bit, width, TabGate range
+};
+struct Round {
     int32_t nb;      // number of register bits (0..3)
     int32_t rb[3];   // their tile-local positions, ascending
-    int32_t u0, u1;  // micro-op range
+    int32_t s0, s1;  // step range
 };
-
-// Packed forms that travel to the device inside the kernel parameters (constant bank).
-struct DUop {        // 16 bytes
-    uint8_t kind, r0, swap, pad0;
-    int8_t r1, pad1;
-    uint16_t gate;
-    uint32_t ctrl;
-    uint16_t mat;
-    uint16_t pat;
-};
-struct DRound {      // 24 bytes
-    uint8_t nb, rb[3];
-    uint16_t u0, u1;  // micro-op range relative to the pass
-    uint16_t ksw[8];  // swizzled SMEM offset of register slot k: ko[k] ^ ((ko[k] >> 3) & 7)
-};
-struct DPass {       // device view of a pass
-    int32_t T, first, n_rounds, n_uops, mat_elems, n_lruns, n_oruns;
-    uint32_t lmask[8];
-    int32_t lshift[8];
-    uint32_t omask[8];
-    int32_t oshift[8];
-    uint8_t extq[32];  // ext position -> qubit (tile qubits first, then outer qubits)
-};
-struct DInit {       // a 1-qubit gate folded into the product-state start of the first pass
-    uint16_t gate;
-    uint8_t qubit, pad;
-};
-constexpr int kMaxPassUops = 96;     // per pass, so that a pass fits the 4 KiB kernel-parameter space
-constexpr int kMaxPassRounds = 48;
-constexpr int kMaxInit = 96;
-
-inline DUop pack_uop(const Uop& u, int pass_u0) {
-    (void)pass_u0;
-    DUop d{};
-    d.kind = (uint8_t)u.kind;
-    d.r0 = (uint8_t)u.r0;
-    d.r1 = (int8_t)u.r1;
-    d.swap = (uint8_t)u.swap;
-    d.gate = (uint16_t)u.gate;
-    d.ctrl = u.ctrl;
-    d.mat = (uint16_t)u.mat;
-    d.pat = (uint16_t)u.pat;
-    return d;
-}
-inline DRound pack_round(const Round& r, int pass_u0) {
-    DRound d{};
-    d.nb = (uint8_t)r.nb;
-    d.rb[0] = (uint8_t)r.rb[0];
-    d.rb[1] = (uint8_t)r.rb[1];
-    d.rb[2] = (uint8_t)r.rb[2];
-    d.u0 = (uint16_t)(r.u0 - pass_u0);
-    d.u1 = (uint16_t)(r.u1 - pass_u0);
-    for (int k = 0; k < 8; ++k) {
-        uint32_t ko = 0;
-        for (int c = 0; c < r.nb; ++c)
-            if (k >> c & 1) ko |= 1u << r.rb[c];
-        d.ksw[k] = (uint16_t)(ko ^ ((ko >> 3) & 7u));
-    }
-    return d;
-}
 
 constexpr int kMaxRuns = 8;
+constexpr int kMaxTileBits = 13;
+constexpr int kMaxPassSteps = 160;
+constexpr int kMaxPassRounds = 64;
+constexpr int kMaxPassMats = 224;
+constexpr int kMaxInit = 128;
+constexpr int kNoBit = 255;
 
 struct Pass {
     int32_t T;               // tile bits
-    int32_t first;           // 1: tile starts as |0..0> (no load)
+    uint32_t L;              // tile qubits
+    uint32_t a_in, a_out;    // active-qubit sets of the input / output layout
+    int32_t last;
     int32_t r0, r1;          // round range
-    int32_t u0, u1;          // micro-op range
-    int32_t mat_elems;       // double2 elements of matrix storage per team
-    int32_t n_lruns, n_oruns;
-    uint32_t lmask[kMaxRuns];  // local-index bit runs -> global amplitude index
-    int32_t lshift[kMaxRuns];
-    uint32_t omask[kMaxRuns];  // outer-index bit runs -> global amplitude index
-    int32_t oshift[kMaxRuns];
-    int32_t tile_qubits[32];   // the T tile qubits (ascending), for introspection / tests
-    uint8_t extq[32];          // ext position -> qubit
+    int32_t s0, s1;          // step range
+    int32_t m0, m1;          // MatRec range
+    int32_t t0, t1;          // Tab range
+    int32_t i0, i1;          // folded (init) gate range in Plan::init_gates
+    int32_t mat_elems;       // double2 elements of matrix + table storage per team
+    int32_t tile_qubits[32]; // the T tile qubits (ascending)
+    uint8_t extq[32];        // ext position -> qubit
 };
 
 struct GateInfo {
@@ -157,19 +132,72 @@ inline GateInfo gate_info(int kind) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device view of a pass: one contiguous blob (header + arrays) that the kernel copies to shared
+// memory.  The same blob drives the host emulator of the CPU tests.
+
+struct DStep {       // 16 bytes
+    uint8_t kind, r0, swap, pad0;
+    int8_t r1, pad1;
+    uint16_t gate;
+    uint32_t ctrl;
+    uint16_t mat;
+    uint16_t pat;
+};
+struct DRound {      // 24 bytes
+    uint8_t nb, rb[3];
+    uint16_t s0, s1;  // step range relative to the pass
+    uint16_t ksw[8];  // swizzled SMEM offset of register slot k: ko[k] ^ ((ko[k] >> 3) & 7)
+};
+struct DMat {        // 8 bytes
+    uint16_t gate;
+    uint8_t kind, swap;
+    uint16_t mat, pad;
+};
+struct DTabGate {    // 4 bytes
+    uint16_t m4;
+    uint8_t p0, p1;  // ext positions (p1 = kNoBit for one-qubit gates)
+};
+struct DTab {        // 8 bytes
+    uint16_t mat;
+    uint8_t lo, nbits;  // nbits bit 7: the table depends on outer index bits
+    uint16_t g0, g1;
+};
+struct DInit {       // a 1-qubit gate folded into the product start of a fresh tile qubit
+    uint16_t gate;
+    uint8_t qubit, pad;
+};
+struct DPass {
+    int32_t T, n_rounds, n_steps, n_mats, n_tabs, n_tabgates, n_init, mat_elems;
+    int32_t off_rounds, off_steps, off_mats, off_tabs, off_tabgates, off_inits, blob_bytes;  // byte offsets
+    uint8_t has_src;    // the input layout is not empty (something to load)
+    uint8_t n_fresh;    // fresh tile qubits; 0 -> plain pass (cp.async double-buffered loads)
+    uint8_t nlo, nhi;   // fresh qubits in the low / high product table
+    uint8_t n_obits;    // outer bits of a work item = outer qubits present in the output layout
+    uint8_t in_bits, out_bits;  // log2(amplitudes per state) of the input / output layout
+    uint8_t last;
+    uint8_t l_in[16];   // local bit -> bit of the input-layout index (kNoBit: fresh)
+    uint8_t l_out[16];  // local bit -> bit of the output-layout index
+    uint8_t l_plo[16];  // local bit -> bit of the low product-table index (kNoBit: none)
+    uint8_t l_phi[16];  // local bit -> bit of the high product-table index
+    uint8_t o_in[32];   // item outer bit -> bit of the input-layout index (kNoBit: qubit still |0> there)
+    uint8_t o_out[32];  // item outer bit -> bit of the output-layout index
+    uint8_t o_ext[32];  // item outer bit -> ext position
+    uint8_t fresh_q[16];  // fresh qubits, ascending (first nlo -> low table, then nhi -> high table)
+    uint8_t extq[32];   // ext position -> qubit
+};
+
 struct Plan {
     int n = 0;
     int T = 0;
     std::vector<b200sq_gate> gates;
     std::vector<Pass> passes;
     std::vector<Round> rounds;
-    std::vector<Uop> uops;
-    // Product-state prefix: 1-qubit gates that act on a qubit before any multi-qubit gate touches
-    // it.  U_k ... U_1 |0> stays a tensor product, so the first pass starts from
-    // (x)_q v_q with v_q = (folded gates of q)|0> instead of applying these gates amplitude by
-    // amplitude (circuit order is preserved per qubit).
-    std::vector<int32_t> init_gates;
-    uint32_t first_tile_mask = 0;  // the first pass must use exactly this tile (folded qubits are local)
+    std::vector<Step> steps;
+    std::vector<MatRec> mats;
+    std::vector<Tab> tabs;
+    std::vector<TabGate> tabgates;
+    std::vector<int32_t> init_gates;  // folded 1-qubit gates, grouped per pass (Pass::i0..i1)
 };
 
 namespace detail {
@@ -194,22 +222,7 @@ inline GMask gate_masks(const b200sq_gate& g, int n) {
 }
 
 inline int popc(uint32_t v) { return __builtin_popcount(v); }
-
-// Build the bit-run tables that scatter a compact index over the set bits of `qmask`.
-inline int make_runs(uint32_t qmask, uint32_t* masks, int32_t* shifts) {
-    int nruns = 0, compact = 0, q = 0;
-    while (q < 32) {
-        if (!(qmask >> q & 1u)) { ++q; continue; }
-        int start = q, len = 0;
-        while (q < 32 && (qmask >> q & 1u)) { ++q; ++len; }
-        if (nruns == kMaxRuns) throw std::runtime_error("tile qubit set has too many runs");
-        masks[nruns] = ((len >= 32 ? 0u : (1u << len)) - 1u) << compact;
-        shifts[nruns] = start - compact;
-        ++nruns;
-        compact += len;
-    }
-    return nruns;
-}
+inline int rank_in(uint32_t set, int q) { return popc(set & ((1u << q) - 1u)); }
 
 }  // namespace detail
 
@@ -224,7 +237,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
     // default tile: the whole state when it fits 64 KiB (n <= 12); otherwise 2^11 amplitudes so that
     // two tile buffers (double buffering) still leave three CTAs per SM
     int T = tile_bits <= 0 ? (n <= 12 ? 12 : 11) : tile_bits;
-    if (T > 13) throw std::invalid_argument("tile_bits must be <= 13");
+    if (T > kMaxTileBits) throw std::invalid_argument("tile_bits must be <= 13");
     T = std::min(T, n);
     plan.T = T;
     plan.gates = gates_in;
@@ -235,52 +248,19 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
     // leave room for two freely chosen target qubits; with T == n the tile is the whole state
     low_bits = (T == n) ? T : std::max(0, std::min(low_bits, T - 2));
     const uint32_t mandatory = (low_bits >= 32 ? ~0u : (1u << low_bits) - 1u);
+    const uint32_t full = (n >= 32 ? ~0u : (1u << n) - 1u);
 
-    // Gates of the first pass' tile qubits that can be folded into the product-state start.  Only
-    // TILE qubits are folded: an outer qubit that stays |0> keeps 2^(n-T) - 1 of every 2^(n-T) tiles
-    // identically zero during the first pass (they are skipped), which is worth more than folding.
-    auto first_tile = [&](const std::vector<int>& gates_all) {
-        uint32_t L = mandatory, blockedT = 0, blockedD = 0;
-        for (int gi : gates_all) {
-            const GMask& m = gm[gi];
-            bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
-            if (free_ && popc(L | m.tgt) <= T) {
-                L |= m.tgt;
-            } else {
-                blockedT |= m.all;
-                blockedD |= m.tgt;
-            }
-        }
-        for (int q = 0; q < n && popc(L) < T; ++q) L |= 1u << q;
-        return L;
-    };
     std::vector<int> pending;
-    {
-        std::vector<int> all;
-        for (int i = 0; i < G; ++i)
-            if (gates_in[i].kind != B200SQ_ID) all.push_back(i);
-        const uint32_t L0 = first_tile(all);
-        uint32_t entangled = 0;  // qubits already touched by a multi-qubit gate (or a kept gate)
-        for (int i : all) {
-            GateInfo gi = gate_info(gates_in[i].kind);
-            if (fold_prefix && gi.nq == 1 && !(entangled & gm[i].all) && (gm[i].all & L0) &&
-                (int)plan.init_gates.size() < kMaxInit) {
-                plan.init_gates.push_back(i);
-                continue;
-            }
-            entangled |= gm[i].all;
-            pending.push_back(i);
-        }
-        plan.first_tile_mask = L0;
-    }
+    for (int i = 0; i < G; ++i)
+        if (gates_in[i].kind != B200SQ_ID) pending.push_back(i);
+
+    uint32_t active = 0;
     bool first = true;
     // A circuit without gates still needs one pass to write |0..0>.
     while (!pending.empty() || first) {
         // ---- choose the tile qubit set by first demand
         uint32_t L = mandatory;
-        if (first) {
-            L = plan.first_tile_mask;
-        } else {
+        {
             uint32_t blockedT = 0, blockedD = 0;
             for (int gi : pending) {
                 const GMask& m = gm[gi];
@@ -292,8 +272,37 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                     blockedD |= m.tgt;
                 }
             }
+            // fill up: prefer qubits that are already active (keeps the layouts small), then the rest
+            for (int q = 0; q < n && popc(L) < T; ++q) if (active >> q & 1u) L |= 1u << q;
             for (int q = 0; q < n && popc(L) < T; ++q) L |= 1u << q;
         }
+        Pass ps;
+        std::memset(&ps, 0, sizeof(ps));
+        ps.T = T;
+        ps.L = L;
+        ps.a_in = active;
+        const uint32_t fresh = L & ~active;
+
+        // ---- fold the 1-qubit prefix of the fresh tile qubits into their start vectors
+        ps.i0 = (int)plan.init_gates.size();
+        if (fold_prefix) {
+            std::vector<int> kept;
+            uint32_t touched = 0;
+            for (int gi : pending) {
+                GateInfo info = gate_info(gates_in[gi].kind);
+                if (info.nq == 1 && (gm[gi].all & fresh) && !(gm[gi].all & touched) &&
+                    (int)plan.init_gates.size() - ps.i0 < kMaxInit) {
+                    plan.init_gates.push_back(gi);
+                } else {
+                    touched |= gm[gi].all;
+                    kept.push_back(gi);
+                }
+            }
+            pending.swap(kept);
+        }
+        ps.i1 = (int)plan.init_gates.size();
+        active |= L;
+
         // ---- absorb gates
         std::vector<int> absorbed, rest;
         {
@@ -301,7 +310,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
             for (int gi : pending) {
                 const GMask& m = gm[gi];
                 bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
-                if (free_ && (m.tgt & ~L) == 0 && (int)absorbed.size() < kMaxPassUops) {
+                if (free_ && (m.tgt & ~L) == 0 && (int)absorbed.size() < kMaxPassSteps - 8) {
                     absorbed.push_back(gi);
                 } else {
                     rest.push_back(gi);
@@ -310,7 +319,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                 }
             }
         }
-        if (absorbed.empty() && !pending.empty() && !first)  // the first pass may only write the product start
+        if (absorbed.empty() && !pending.empty() && ps.i1 == ps.i0)
             throw std::runtime_error("planner made no progress (gate needs more target qubits than a tile)");
 
         // ---- ext positions
@@ -319,49 +328,239 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
             int c = 0;
             for (int q = 0; q < n; ++q) if (L >> q & 1u) pos[q] = c++;
             for (int q = 0; q < n; ++q) if (!(L >> q & 1u)) pos[q] = c++;
-        }
-        Pass ps;
-        std::memset(&ps, 0, sizeof(ps));
-        ps.T = T;
-        ps.first = first ? 1 : 0;
-        ps.n_lruns = make_runs(L, ps.lmask, ps.lshift);
-        uint32_t full = (n >= 32 ? ~0u : (1u << n) - 1u);
-        ps.n_oruns = make_runs(full & ~L, ps.omask, ps.oshift);
-        {
-            int c = 0;
+            c = 0;
             for (int q = 0; q < n; ++q) if (L >> q & 1u) ps.tile_qubits[c++] = q;
             for (int q = 0; q < n; ++q) ps.extq[pos[q]] = (uint8_t)q;
         }
         ps.r0 = (int)plan.rounds.size();
-        ps.u0 = (int)plan.uops.size();
+        ps.s0 = (int)plan.steps.size();
+        ps.m0 = (int)plan.mats.size();
+        ps.t0 = (int)plan.tabs.size();
+        int mat_off = 0;
 
-        // ---- pack absorbed gates into rounds (list scheduling with the same hop-over rule)
+        // ---- step emission helpers
+        auto add_mat = [&](int gate, int kind, int swap, int elems) {
+            MatRec mr{gate, kind, swap, mat_off};
+            plan.mats.push_back(mr);
+            mat_off += elems;
+            return mr.mat;
+        };
+        auto diag_skip = [&](int kind) -> uint32_t {  // phases that are exactly 1: index = bit(q0) | bit(q1) << 1
+            switch (kind) {
+                case B200SQ_Z: case B200SQ_S: case B200SQ_SDG: case B200SQ_T: case B200SQ_TDG:
+                case B200SQ_P: return 0x5;                                  // bit(q0) = 0
+                case B200SQ_CZ: case B200SQ_CS: case B200SQ_CP: return 0x7;
+                case B200SQ_CRZ: return 0x5;                                // control = 0
+                default: return 0;
+            }
+        };
+        // Emit one round's ordered member list as steps.
+        auto emit_members = [&](const std::vector<int>& members, const Round& rd) {
+            auto regbit = [&](int q) {
+                for (int c = 0; c < rd.nb; ++c) if (rd.rb[c] == pos[q]) return c;
+                throw std::logic_error("target qubit is not a register bit");
+            };
+            size_t i = 0;
+            int layer_step = -1;  // index of the open L_* step
+            while (i < members.size()) {
+                const int gi = members[i];
+                const b200sq_gate& g = gates_in[gi];
+                const GateInfo info = gate_info(g.kind);
+                if (info.diag) {
+                    layer_step = -1;
+                    size_t j = i;
+                    while (j < members.size() && gate_info(gates_in[members[j]].kind).diag) ++j;
+                    std::vector<int> run(members.begin() + i, members.begin() + j);
+                    i = j;
+                    // --- phase tables over one or two groups of local bits
+                    std::vector<int> stray;
+                    if (run.size() >= 3) {
+                        int split = T;  // single group
+                        if (T > 7) {
+                            int best = -1, best_cross = 1 << 30;
+                            for (int s = std::max(1, T - 7); s <= std::min(7, T - 1); ++s) {
+                                int cross = 0;
+                                for (int r : run) {
+                                    bool lo = false, hi = false;
+                                    const GateInfo ri = gate_info(gates_in[r].kind);
+                                    for (int k = 0; k < ri.nq; ++k) {
+                                        int p = pos[gates_in[r].q[k]];
+                                        if (p < s) lo = true; else if (p < T) hi = true;
+                                    }
+                                    cross += lo && hi;
+                                }
+                                if (cross < best_cross) { best_cross = cross; best = s; }
+                            }
+                            split = best;
+                        }
+                        std::vector<int> grp[2];
+                        for (int r : run) {
+                            bool lo = false, hi = false;
+                            const GateInfo ri = gate_info(gates_in[r].kind);
+                            for (int k = 0; k < ri.nq; ++k) {
+                                int p = pos[gates_in[r].q[k]];
+                                if (p < split) lo = true; else if (p < T) hi = true;
+                            }
+                            if (lo && hi) stray.push_back(r);
+                            else grp[hi ? 1 : 0].push_back(r);
+                        }
+                        for (int gidx = 0; gidx < 2; ++gidx) {
+                            if (grp[gidx].size() < 2 || (int)plan.mats.size() - ps.m0 + (int)grp[gidx].size() > kMaxPassMats) {
+                                stray.insert(stray.end(), grp[gidx].begin(), grp[gidx].end());
+                                continue;
+                            }
+                            Tab tb;
+                            tb.lo = gidx == 0 ? 0 : split;
+                            tb.nbits = gidx == 0 ? std::min(split, T) : T - split;
+                            tb.g0 = (int)plan.tabgates.size();
+                            for (int r : grp[gidx]) {
+                                const GateInfo ri = gate_info(gates_in[r].kind);
+                                TabGate tg;
+                                tg.m4 = add_mat(r, MAT_DIAG, 0, 4);
+                                tg.p0 = pos[gates_in[r].q[0]];
+                                tg.p1 = ri.nq > 1 ? pos[gates_in[r].q[1]] : -1;
+                                plan.tabgates.push_back(tg);
+                            }
+                            tb.g1 = (int)plan.tabgates.size();
+                            tb.mat = mat_off;
+                            mat_off += 1 << tb.nbits;
+                            plan.tabs.push_back(tb);
+                            Step st;
+                            std::memset(&st, 0, sizeof(st));
+                            st.kind = ST_DTAB;
+                            st.gate = -1;
+                            st.r0 = tb.lo;
+                            st.r1 = tb.nbits;
+                            st.mat = tb.mat;
+                            plan.steps.push_back(st);
+                        }
+                        std::sort(stray.begin(), stray.end());
+                    } else {
+                        stray = run;
+                    }
+                    for (int r : stray) {
+                        const b200sq_gate& gg = gates_in[r];
+                        const GateInfo ri = gate_info(gg.kind);
+                        Step st;
+                        std::memset(&st, 0, sizeof(st));
+                        st.kind = ST_DIAG;
+                        st.gate = r;
+                        st.r0 = pos[gg.q[0]];
+                        st.r1 = ri.nq > 1 ? pos[gg.q[1]] : -1;
+                        st.ctrl = diag_skip(gg.kind);
+                        int ra = -1, rb = -1;
+                        for (int c = 0; c < rd.nb; ++c) {
+                            if (rd.rb[c] == st.r0) ra = c;
+                            if (st.r1 >= 0 && rd.rb[c] == st.r1) rb = c;
+                        }
+                        st.pat = (ra + 1) | ((rb + 1) << 2);
+                        st.mat = add_mat(r, MAT_DIAG, 0, 4);
+                        plan.steps.push_back(st);
+                    }
+                    continue;
+                }
+                ++i;
+                if (info.nq - info.nctrl == 1) {
+                    const int slot = regbit(g.q[info.nctrl]);
+                    if (info.nctrl > 0) {
+                        layer_step = -1;
+                        Step st;
+                        std::memset(&st, 0, sizeof(st));
+                        st.kind = ST_U1CTRL;
+                        st.gate = gi;
+                        st.r0 = slot;
+                        for (int k = 0; k < info.nctrl; ++k) st.ctrl |= 1u << pos[g.q[k]];
+                        st.mat = add_mat(gi, MAT_U1, 0, 4);
+                        plan.steps.push_back(st);
+                        continue;
+                    }
+                    const int fam = g.kind == B200SQ_RX ? ST_LRX
+                                  : (g.kind == B200SQ_RY || g.kind == B200SQ_H || g.kind == B200SQ_X) ? ST_LREAL
+                                  : ST_LGEN;
+                    if (layer_step >= 0 && plan.steps[layer_step].kind == fam &&
+                        !(plan.steps[layer_step].r0 >> slot & 1)) {
+                        Step& st = plan.steps[layer_step];
+                        st.r0 |= 1 << slot;
+                        MatRec mr{gi, MAT_U1, 0, st.mat + 4 * slot};
+                        plan.mats.push_back(mr);
+                    } else {
+                        Step st;
+                        std::memset(&st, 0, sizeof(st));
+                        st.kind = fam;
+                        st.gate = -1;
+                        st.r0 = 1 << slot;
+                        st.mat = mat_off;
+                        mat_off += 12;  // one 2x2 per register slot
+                        MatRec mr{gi, MAT_U1, 0, st.mat + 4 * slot};
+                        plan.mats.push_back(mr);
+                        layer_step = (int)plan.steps.size();
+                        plan.steps.push_back(st);
+                    }
+                } else {
+                    layer_step = -1;
+                    Step st;
+                    std::memset(&st, 0, sizeof(st));
+                    st.kind = ST_U2;
+                    st.gate = gi;
+                    int ra = regbit(g.q[info.nctrl]), rb = regbit(g.q[info.nctrl + 1]);
+                    st.r0 = std::max(ra, rb);
+                    st.r1 = std::min(ra, rb);
+                    st.swap = ra < rb ? 1 : 0;
+                    for (int k = 0; k < info.nctrl; ++k) st.ctrl |= 1u << pos[g.q[k]];
+                    st.mat = add_mat(gi, MAT_U2, st.swap, 16);
+                    plan.steps.push_back(st);
+                }
+            }
+        };
+
+        // ---- pack absorbed gates into rounds: list scheduling with the same hop-over rule.  Free
+        // diagonal gates are DEFERRED (they commute with everything that does not act non-diagonally
+        // on their qubits) and flushed together right before the first gate that needs them, so that
+        // whole entangling layers end up in one phase-table step.
         std::vector<char> done(absorbed.size(), 0);
         size_t n_done = 0;
-        int mat_off = 0;
+        std::vector<int> lazy;  // deferred diagonal gates (gate indices), in circuit order
+        uint32_t lazy_mask = 0;
+        bool overflow = false;
         while (n_done < absorbed.size()) {
-            if ((int)plan.rounds.size() - ps.r0 >= kMaxPassRounds) {
-                // the pass is full: hand the remaining gates back (gate order == circuit order)
-                for (size_t a = 0; a < absorbed.size(); ++a)
-                    if (!done[a]) rest.push_back(absorbed[a]);
-                std::sort(rest.begin(), rest.end());
+            if ((int)plan.rounds.size() - ps.r0 >= kMaxPassRounds - 1 ||
+                (int)plan.steps.size() - ps.s0 >= kMaxPassSteps - 40 ||
+                (int)plan.mats.size() - ps.m0 >= kMaxPassMats - 48) {
+                overflow = true;
                 break;
             }
             Round rd;
             std::memset(&rd, 0, sizeof(rd));
-            rd.u0 = (int)plan.uops.size();
             uint32_t bits = 0;  // local positions of this round's register bits
             uint32_t blockedT = 0, blockedD = 0;
             std::vector<int> members;
             for (size_t a = 0; a < absorbed.size(); ++a) {
                 if (done[a]) continue;
-                const GMask& m = gm[absorbed[a]];
+                const int gi = absorbed[a];
+                const GMask& m = gm[gi];
+                bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
+                if (!free_) {
+                    blockedT |= m.all;
+                    blockedD |= m.tgt;
+                    continue;
+                }
+                if (m.tgt == 0) {  // diagonal: defer
+                    lazy.push_back(gi);
+                    lazy_mask |= m.all;
+                    done[a] = 1;
+                    ++n_done;
+                    continue;
+                }
                 uint32_t tl = 0;
                 for (int q = 0; q < n; ++q) if (m.tgt >> q & 1u) tl |= 1u << pos[q];
-                bool free_ = !(m.tgt & blockedT) && !(m.all & blockedD);
-                if (free_ && popc(bits | tl) <= 3) {
+                if (popc(bits | tl) <= 3) {
+                    if (m.tgt & lazy_mask) {  // needs the deferred phases first: flush them all
+                        members.insert(members.end(), lazy.begin(), lazy.end());
+                        lazy.clear();
+                        lazy_mask = 0;
+                    }
                     bits |= tl;
-                    members.push_back((int)a);
+                    members.push_back(gi);
                     done[a] = 1;
                     ++n_done;
                 } else {
@@ -369,6 +568,12 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                     blockedD |= m.tgt;
                 }
             }
+            if (n_done == absorbed.size() && !lazy.empty()) {  // end of the pass: flush what is left
+                members.insert(members.end(), lazy.begin(), lazy.end());
+                lazy.clear();
+                lazy_mask = 0;
+            }
+            if (members.empty()) continue;  // only deferrals happened in this scan
             // give rounds without non-diagonal work (pure phase rounds) three low bits so that
             // each thread still handles eight amplitudes
             for (int b = 0; b < T && popc(bits) < std::min(3, T); ++b) bits |= 1u << b;
@@ -377,68 +582,183 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                 int c = 0;
                 for (int b = 0; b < T; ++b) if (bits >> b & 1u) rd.rb[c++] = b;
             }
-            auto regbit = [&](int q) {
-                for (int c = 0; c < rd.nb; ++c) if (rd.rb[c] == pos[q]) return c;
-                throw std::logic_error("target qubit is not a register bit");
-            };
-            for (int a : members) {
-                int gi = absorbed[a];
-                const b200sq_gate& g = gates_in[gi];
-                GateInfo info = gate_info(g.kind);
-                Uop u;
-                std::memset(&u, 0, sizeof(u));
-                u.gate = gi;
-                u.mat = mat_off;
-                if (info.diag) {
-                    u.kind = UOP_DIAG;
-                    u.r0 = pos[g.q[0]];
-                    u.r1 = info.nq > 1 ? pos[g.q[1]] : -1;
-                    // phases that are exactly 1: index = bit(q0) | bit(q1) << 1
-                    switch (g.kind) {
-                        case B200SQ_Z: case B200SQ_S: case B200SQ_SDG: case B200SQ_T:
-                        case B200SQ_TDG: case B200SQ_P: u.ctrl = 0x5; break;        // bit(q0)=0
-                        case B200SQ_CZ: case B200SQ_CS: case B200SQ_CP: u.ctrl = 0x7; break;
-                        case B200SQ_CRZ: u.ctrl = 0x5; break;                       // control = 0
-                        default: u.ctrl = 0; break;
-                    }
-                    // register slot (or -1) of each of the gate's qubits: pat = (ra + 1) | (rb + 1) << 2
-                    int ra = -1, rb = -1;
-                    for (int c = 0; c < rd.nb; ++c) {
-                        if (rd.rb[c] == u.r0) ra = c;
-                        if (u.r1 >= 0 && rd.rb[c] == u.r1) rb = c;
-                    }
-                    u.pat = (ra + 1) | ((rb + 1) << 2);
-                    mat_off += 4;
-                } else if (info.nq - info.nctrl == 1) {
-                    u.r0 = regbit(g.q[info.nctrl]);
-                    for (int k = 0; k < info.nctrl; ++k) u.ctrl |= 1u << pos[g.q[k]];
-                    if (info.nctrl > 0) u.kind = UOP_U1CTRL;
-                    else if (g.kind == B200SQ_RX) u.kind = UOP_U1RX;
-                    else if (g.kind == B200SQ_RY || g.kind == B200SQ_H || g.kind == B200SQ_X) u.kind = UOP_U1REAL;
-                    else u.kind = UOP_U1G;
-                    mat_off += 4;
-                } else {
-                    u.kind = UOP_U2;
-                    int ra = regbit(g.q[info.nctrl]), rb = regbit(g.q[info.nctrl + 1]);
-                    u.r0 = std::max(ra, rb);
-                    u.r1 = std::min(ra, rb);
-                    u.swap = ra < rb ? 1 : 0;
-                    for (int k = 0; k < info.nctrl; ++k) u.ctrl |= 1u << pos[g.q[k]];
-                    mat_off += 16;
-                }
-                plan.uops.push_back(u);
-            }
-            rd.u1 = (int)plan.uops.size();
+            rd.s0 = (int)plan.steps.size();
+            emit_members(members, rd);
+            rd.s1 = (int)plan.steps.size();
             plan.rounds.push_back(rd);
         }
+        if (overflow) {
+            // the pass is full: flush deferred phases into a last round and hand the remaining gates back
+            if (!lazy.empty()) {
+                Round rd;
+                std::memset(&rd, 0, sizeof(rd));
+                uint32_t bits = 0;
+                for (int b = 0; b < T && popc(bits) < std::min(3, T); ++b) bits |= 1u << b;
+                rd.nb = popc(bits);
+                int c = 0;
+                for (int b = 0; b < T; ++b) if (bits >> b & 1u) rd.rb[c++] = b;
+                rd.s0 = (int)plan.steps.size();
+                emit_members(lazy, rd);
+                rd.s1 = (int)plan.steps.size();
+                plan.rounds.push_back(rd);
+                lazy.clear();
+            }
+            for (size_t a = 0; a < absorbed.size(); ++a)
+                if (!done[a]) rest.push_back(absorbed[a]);
+            std::sort(rest.begin(), rest.end());
+        }
         ps.r1 = (int)plan.rounds.size();
-        ps.u1 = (int)plan.uops.size();
+        ps.s1 = (int)plan.steps.size();
+        ps.m1 = (int)plan.mats.size();
+        ps.t1 = (int)plan.tabs.size();
         ps.mat_elems = mat_off;
+        ps.last = rest.empty() ? 1 : 0;
+        ps.a_out = ps.last ? full : active;
+        if (ps.s1 - ps.s0 > kMaxPassSteps || ps.r1 - ps.r0 > kMaxPassRounds || ps.m1 - ps.m0 > kMaxPassMats)
+            throw std::runtime_error("internal: pass exceeds its capacity");
         plan.passes.push_back(ps);
         pending.swap(rest);
         first = false;
     }
     return plan;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pack pass `ip` into its device blob.
+
+inline std::vector<uint8_t> build_pass_blob(const Plan& plan, int ip) {
+    using namespace detail;
+    const Pass& ps = plan.passes[ip];
+    const int n = plan.n, T = ps.T;
+    DPass h;
+    std::memset(&h, 0, sizeof(h));
+    h.T = T;
+    h.n_rounds = ps.r1 - ps.r0;
+    h.n_steps = ps.s1 - ps.s0;
+    h.n_mats = ps.m1 - ps.m0;
+    h.n_tabs = ps.t1 - ps.t0;
+    h.n_init = ps.i1 - ps.i0;
+    h.mat_elems = ps.mat_elems;
+    h.has_src = ps.a_in != 0;
+    h.last = (uint8_t)ps.last;
+    h.in_bits = (uint8_t)popc(ps.a_in);
+    h.out_bits = (uint8_t)popc(ps.a_out);
+    std::memset(h.l_in, kNoBit, sizeof(h.l_in));
+    std::memset(h.l_out, kNoBit, sizeof(h.l_out));
+    std::memset(h.l_plo, kNoBit, sizeof(h.l_plo));
+    std::memset(h.l_phi, kNoBit, sizeof(h.l_phi));
+    std::memset(h.o_in, kNoBit, sizeof(h.o_in));
+    std::memset(h.o_out, kNoBit, sizeof(h.o_out));
+    std::memset(h.o_ext, kNoBit, sizeof(h.o_ext));
+    std::memset(h.fresh_q, kNoBit, sizeof(h.fresh_q));
+    const uint32_t fresh = ps.L & ~ps.a_in;
+    h.n_fresh = (uint8_t)popc(fresh);
+    h.nlo = (uint8_t)std::min<int>(h.n_fresh, 6);
+    h.nhi = (uint8_t)(h.n_fresh - h.nlo);
+    int nf = 0;
+    for (int i = 0; i < T; ++i) {
+        const int q = ps.tile_qubits[i];
+        h.l_out[i] = (uint8_t)rank_in(ps.a_out, q);
+        if (ps.a_in >> q & 1u) {
+            h.l_in[i] = (uint8_t)rank_in(ps.a_in, q);
+        } else {
+            h.fresh_q[nf] = (uint8_t)q;
+            if (nf < h.nlo) h.l_plo[i] = (uint8_t)nf;
+            else h.l_phi[i] = (uint8_t)(nf - h.nlo);
+            ++nf;
+        }
+    }
+    int nob = 0, orank = 0;
+    for (int q = 0; q < n; ++q) {
+        if (ps.L >> q & 1u) continue;
+        if (ps.a_out >> q & 1u) {
+            h.o_out[nob] = (uint8_t)rank_in(ps.a_out, q);
+            if (ps.a_in >> q & 1u) h.o_in[nob] = (uint8_t)rank_in(ps.a_in, q);
+            h.o_ext[nob] = (uint8_t)(T + orank);
+            ++nob;
+        }
+        ++orank;
+    }
+    h.n_obits = (uint8_t)nob;
+    for (int i = 0; i < 32; ++i) h.extq[i] = ps.extq[i];
+
+    std::vector<DRound> rounds;
+    for (int r = ps.r0; r < ps.r1; ++r) {
+        const Round& rd = plan.rounds[r];
+        DRound d{};
+        d.nb = (uint8_t)rd.nb;
+        for (int c = 0; c < 3; ++c) d.rb[c] = (uint8_t)rd.rb[c];
+        d.s0 = (uint16_t)(rd.s0 - ps.s0);
+        d.s1 = (uint16_t)(rd.s1 - ps.s0);
+        for (int k = 0; k < 8; ++k) {
+            uint32_t ko = 0;
+            for (int c = 0; c < rd.nb; ++c)
+                if (k >> c & 1) ko |= 1u << rd.rb[c];
+            d.ksw[k] = (uint16_t)(ko ^ ((ko >> 3) & 7u));
+        }
+        rounds.push_back(d);
+    }
+    std::vector<DStep> steps;
+    for (int s = ps.s0; s < ps.s1; ++s) {
+        const Step& u = plan.steps[s];
+        DStep d{};
+        d.kind = (uint8_t)u.kind;
+        d.r0 = (uint8_t)u.r0;
+        d.r1 = (int8_t)u.r1;
+        d.swap = (uint8_t)u.swap;
+        d.gate = (uint16_t)(u.gate < 0 ? 0xffff : u.gate);
+        d.ctrl = u.ctrl;
+        d.mat = (uint16_t)u.mat;
+        d.pat = (uint16_t)u.pat;
+        steps.push_back(d);
+    }
+    std::vector<DMat> mats;
+    for (int m = ps.m0; m < ps.m1; ++m) {
+        const MatRec& mr = plan.mats[m];
+        mats.push_back(DMat{(uint16_t)mr.gate, (uint8_t)mr.kind, (uint8_t)mr.swap, (uint16_t)mr.mat, 0});
+    }
+    std::vector<DTab> tabs;
+    std::vector<DTabGate> tabgates;
+    for (int t = ps.t0; t < ps.t1; ++t) {
+        const Tab& tb = plan.tabs[t];
+        DTab d{};
+        d.mat = (uint16_t)tb.mat;
+        d.lo = (uint8_t)tb.lo;
+        d.nbits = (uint8_t)tb.nbits;
+        d.g0 = (uint16_t)tabgates.size();
+        for (int g = tb.g0; g < tb.g1; ++g) {
+            const TabGate& tg = plan.tabgates[g];
+            if (tg.p0 >= T || tg.p1 >= T) d.nbits |= 0x80;  // reads an outer index bit: rebuilt per tile
+            tabgates.push_back(DTabGate{(uint16_t)tg.m4, (uint8_t)tg.p0, (uint8_t)(tg.p1 < 0 ? kNoBit : tg.p1)});
+        }
+        d.g1 = (uint16_t)tabgates.size();
+        tabs.push_back(d);
+    }
+    h.n_tabgates = (int32_t)tabgates.size();
+    std::vector<DInit> inits;
+    for (int i = ps.i0; i < ps.i1; ++i) {
+        const int gi = plan.init_gates[i];
+        inits.push_back(DInit{(uint16_t)gi, (uint8_t)plan.gates[gi].q[0], 0});
+    }
+
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t off = align16(sizeof(DPass));
+    h.off_rounds = (int32_t)off; off = align16(off + rounds.size() * sizeof(DRound));
+    h.off_steps = (int32_t)off; off = align16(off + steps.size() * sizeof(DStep));
+    h.off_mats = (int32_t)off; off = align16(off + mats.size() * sizeof(DMat));
+    h.off_tabs = (int32_t)off; off = align16(off + tabs.size() * sizeof(DTab));
+    h.off_tabgates = (int32_t)off; off = align16(off + tabgates.size() * sizeof(DTabGate));
+    h.off_inits = (int32_t)off; off = align16(off + inits.size() * sizeof(DInit));
+    h.blob_bytes = (int32_t)off;
+    std::vector<uint8_t> blob(off, 0);
+    std::memcpy(blob.data(), &h, sizeof(h));
+    if (!rounds.empty()) std::memcpy(blob.data() + h.off_rounds, rounds.data(), rounds.size() * sizeof(DRound));
+    if (!steps.empty()) std::memcpy(blob.data() + h.off_steps, steps.data(), steps.size() * sizeof(DStep));
+    if (!mats.empty()) std::memcpy(blob.data() + h.off_mats, mats.data(), mats.size() * sizeof(DMat));
+    if (!tabs.empty()) std::memcpy(blob.data() + h.off_tabs, tabs.data(), tabs.size() * sizeof(DTab));
+    if (!tabgates.empty()) std::memcpy(blob.data() + h.off_tabgates, tabgates.data(), tabgates.size() * sizeof(DTabGate));
+    if (!inits.empty()) std::memcpy(blob.data() + h.off_inits, inits.data(), inits.size() * sizeof(DInit));
+    return blob;
 }
 
 }  // namespace b200sq

@@ -9,15 +9,17 @@
 // writes).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "kernels.h"
-#include "uop_exec.cuh"
+#include "tile_exec.cuh"
 
 namespace b200sq {
 
 namespace {
 
 #ifndef B200SQ_TILE_MINBLOCKS
-#define B200SQ_TILE_MINBLOCKS 3
+#define B200SQ_TILE_MINBLOCKS 2
 #endif
 constexpr int kCtaThreads = 256;
 constexpr int kMaxSmem = 227 * 1024;
@@ -43,40 +45,64 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
                      (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
-// Persistent teams: a team walks over its work items (variant, sample, outer tile) with the grid
-// stride and keeps TWO tile buffers — while tile i is being processed, tile i+1 streams in with
-// 16-byte cp.async (no register staging), so HBM reads overlap the FP64 work and ~64 KiB per team
-// are always in flight.
+// Persistent teams: a team walks over a contiguous chunk of work items (variant, sample, outer tile).
+// The pass blob (rounds, steps, matrix / table records) is copied to shared memory once per CTA, so the
+// interpreter reads it with broadcast LDS instead of indexed constant loads.
+//
+// Plain passes (input layout == tile bits all active) keep TWO tile buffers: while tile i is being
+// processed, tile i+1 streams in with 16-byte cp.async, so HBM reads overlap the FP64 work.
+// Expanding passes (fresh tile qubits) gather the few source amplitudes of the tile through L1/L2
+// and multiply them with the product tables of the fresh qubits: no full-state read at all.
 __global__ void __launch_bounds__(kCtaThreads, B200SQ_TILE_MINBLOCKS) k_tile_pass(const __grid_constant__ TileArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* smem = reinterpret_cast<double2*>(smem_raw);
+    {   // pass blob -> SMEM
+        const uint4* g = reinterpret_cast<const uint4*>(A.blob);
+        uint4* sdst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < A.blob_bytes / 16; i += blockDim.x) sdst[i] = g[i];
+    }
+    __syncthreads();
+    const PassView pv = view_pass(smem_raw);
+    const DPass& P = *pv.P;
+    double2* smem = reinterpret_cast<double2*>(smem_raw + A.blob_bytes);
 
     const int TS = A.team_size;
-    const int team = threadIdx.x / TS;
-    const int tid = threadIdx.x - team * TS;
+    const int team = threadIdx.x >> A.log2ts;
+    const int tid = threadIdx.x - (team << A.log2ts);
     // contiguous chunk of work items per team (balanced to within one item; consecutive items are
-    // the tiles of one state, so expensive and zero tiles of the first pass are spread evenly)
+    // the tiles of one state)
     const int64_t n_teams = (int64_t)gridDim.x * A.teams_per_cta;
     const int64_t my_team = (int64_t)blockIdx.x * A.teams_per_cta + team;
     const int64_t chunk = A.total_items / n_teams, extra = A.total_items % n_teams;
     int64_t item = my_team * chunk + (my_team < extra ? my_team : extra);
     const int64_t item_end = item + chunk + (my_team < extra ? 1 : 0);
-    const int64_t stride = 1;
-    if (item >= item_end) return;  // the whole team leaves together
+    if (item >= item_end) return;  // the whole team leaves together (after the CTA-wide barrier above)
 
-    const DPass& P = A.pass;
     const int T = P.T;
     const uint32_t tile_elems = 1u << T;
-    const uint32_t n_outer = 1u << (A.n - T);
-
+    const bool plain = P.has_src && P.n_fresh == 0;
+    TeamMem tm;
     double2* buf0 = smem + (size_t)team * A.team_elems;
-    double2* buf1 = P.first ? buf0 : buf0 + tile_elems;   // the first pass loads nothing
-    double2* mats = buf1 + tile_elems;
+    double2* buf1 = plain ? buf0 + tile_elems : buf0;
+    tm.mats = buf1 + tile_elems;
+    tm.qv = tm.mats + P.mat_elems;
+    tm.plo = tm.qv + 32;
+    tm.phi = tm.plo + 64;
+    tm.jt = reinterpret_cast<uint32_t*>(tm.phi + 128);
+    tm.J = (int)(tile_elems >> A.log2ts) > 0 ? (int)(tile_elems >> A.log2ts) : 1;
+    tm.tile = buf0;
+    ThreadMap map;
+    setup_thread(pv, tm, tid, TS, A.log2ts, map);
+    const int J = tm.J;
+    const bool wide = TS >= 64;  // then (l >> 3) & 7 does not depend on j
+    const uint32_t sw_tid = tile_sw((uint32_t)tid);
+    auto smem_idx = [&](int j) { return wide ? sw_tid + ((uint32_t)j << A.log2ts) : tile_sw((uint32_t)tid + ((uint32_t)j << A.log2ts)); };
+    const bool in_range = (uint32_t)tid < tile_elems;  // tiles smaller than a team (n < 5)
+    team_sync(TS, team);
 
-    const int outer_bits = A.n - T;
-    auto state_of = [&](int64_t it, uint32_t& outer, int64_t& sample, int& variant) {
-        outer = (uint32_t)it & (n_outer - 1u);
-        const int64_t rest = it >> outer_bits;
+    const uint32_t omask = (1u << P.n_obits) - 1u;
+    auto decode = [&](int64_t it, uint32_t& o, int64_t& sample, int& variant) {
+        o = (uint32_t)it & omask;
+        const int64_t rest = it >> P.n_obits;
         int64_t v, smp;
         if (A.n_variants == 1) {          // the common case: no division at all
             v = 0;
@@ -91,107 +117,95 @@ __global__ void __launch_bounds__(kCtaThreads, B200SQ_TILE_MINBLOCKS) k_tile_pas
         }
         sample = A.sample0 + smp;
         variant = A.variant0 + (int)v;
-        return A.psi ? A.psi + (((int64_t)variant * A.n_total + sample - A.psi_off) << A.n) : nullptr;
     };
-    // Global / shared addressing of tile element l = tid + j * TS:  the low log2(TS) bits of l are
-    // the thread's, so their share of the scattered global index (g_lo) and of the swizzle is fixed
-    // per thread; the high bits' share (ghi[j]) is the same for the whole team and sits in SMEM.
-    const int J = (int)(tile_elems / (uint32_t)TS) > 0 ? (int)(tile_elems / (uint32_t)TS) : 1;
-    uint32_t* ghi = reinterpret_cast<uint32_t*>(mats + P.mat_elems + 256);
-    for (int j = tid; j < J; j += TS) ghi[j] = scatter_runs((uint32_t)j * (uint32_t)TS, P.n_lruns, P.lmask, P.lshift);
-    const uint32_t g_lo = scatter_runs((uint32_t)tid, P.n_lruns, P.lmask, P.lshift);
-    const bool wide = TS >= 64;  // then (l >> 3) & 7 does not depend on j
-    const uint32_t sw_tid = tile_sw((uint32_t)tid);
-    auto smem_idx = [&](int j) { return wide ? sw_tid + (uint32_t)j * TS : tile_sw((uint32_t)tid + (uint32_t)j * TS); };
-    const bool in_range = (uint32_t)tid < tile_elems;  // tiles smaller than a warp (n < 5)
-    team_sync(TS, team);
-    auto prefetch = [&](int64_t it, double2* dst) {
-        uint32_t o;
+    auto prefetch = [&](int64_t it, double2* dstbuf) {
+        uint32_t o, eb, oin, oout;
         int64_t smp;
         int var;
-        const double2* st = state_of(it, o, smp, var);
-        const double2* src = st + (scatter_runs(o, P.n_oruns, P.omask, P.oshift) | g_lo);
+        decode(it, o, smp, var);
+        item_outer(P, o, eb, oin, oout);
+        const double2* st = A.src + (((int64_t)var * A.src_vstride + smp - A.src_off) << P.in_bits);
+        const double2* sp = st + (oin | map.in_lo);
         if (in_range)
-            for (int j = 0; j < J; ++j) cp_async16(dst + smem_idx(j), src + ghi[j]);
+            for (int j = 0; j < J; ++j) cp_async16(dstbuf + smem_idx(j), sp + tm.jt[j]);
     };
 
-    if (!P.first) prefetch(item, buf0);
+    if (plain) prefetch(item, buf0);
     asm volatile("cp.async.commit_group;" ::: "memory");
 
-    for (int iter = 0; item < item_end; item += stride, ++iter) {
-        double2* tile = (iter & 1) ? buf1 : buf0;
-        if (!P.first && item + stride < item_end) prefetch(item + stride, (iter & 1) ? buf0 : buf1);
+    int64_t prev_sample = -1;
+    int prev_variant = -1;
+    for (int iter = 0; item < item_end; ++item, ++iter) {
+        tm.tile = (plain && (iter & 1)) ? buf1 : buf0;
+        if (plain && item + 1 < item_end) prefetch(item + 1, (iter & 1) ? buf0 : buf1);
         asm volatile("cp.async.commit_group;" ::: "memory");
 
-        uint32_t outer;
-        int64_t sample;
+        uint32_t o, obase_in, obase_out;
         int variant;
-        double2* state = state_of(item, outer, sample, variant);
-        const double* xrow = A.x ? A.x + sample * A.d : nullptr;
-        const int vgate = A.var_gate ? A.var_gate[variant] : -1;
-        const double vshift = A.var_gate ? A.var_shift[variant] : 0.0;
-        const uint32_t obase = scatter_runs(outer, P.n_oruns, P.omask, P.oshift);
+        ItemCtx ic;
+        decode(item, o, ic.sample, variant);
+        const bool zero = item_outer(P, o, ic.ext_base, obase_in, obase_out);
+        double2* dstate = A.dst ? A.dst + (((int64_t)variant * A.dst_vstride + ic.sample - A.dst_off) << P.out_bits) : nullptr;
 
-        // ---- first pass: a tile whose outer qubits are not all |0> is identically zero
-        // (outer qubits are never folded into the product start)
-        if (P.first && outer != 0) {
-            if (A.store && in_range)
-                for (int j = 0; j < J; ++j) __stcs(state + (obase | g_lo | ghi[j]), double2{0.0, 0.0});
+        // ---- a tile with a set bit of an outer qubit that is still |0> is identically zero
+        if (zero) {
+            if (A.store && in_range) {
+                double2* dp = dstate + (obase_out | map.out_lo);
+                for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], double2{0.0, 0.0});
+            }
             continue;
         }
+        ic.gates = A.gates;
+        ic.xrow = A.x ? A.x + ic.sample * A.d : nullptr;
+        ic.table = A.table;
+        ic.n_total = A.n_total;
+        ic.vgate = A.var_gate ? A.var_gate[variant] : -1;
+        ic.vshift = A.var_gate ? A.var_shift[variant] : 0.0;
 
-        // ---- per-sample gate matrices (the previous item's rounds are behind a team barrier)
-        for (int ui = tid; ui < P.n_uops; ui += TS) {
-            const DUop u = A.uops[ui];
-            const b200sq_gate g = A.gates[u.gate];
-            double theta = gate_angle(g, xrow, A.table, A.n_total, sample);
-            if ((int)u.gate == vgate) theta += vshift;
-            build_matrix(u, g, theta, mats + u.mat);
+        // ---- phase A: per-sample gate matrices + start vectors of the fresh qubits.  Consecutive items
+        // of a team are tiles of the same state, so this runs once per state, not once per tile.
+        // (the previous item's rounds / epilogue are behind a team barrier)
+        const bool new_sample = ic.sample != prev_sample || variant != prev_variant;
+        prev_sample = ic.sample;
+        prev_variant = variant;
+        if (new_sample) {
+            build_mats_thread(pv, tm, ic, tid, TS);
+            if (P.n_tabs > 0 || P.n_fresh > 0) team_sync(TS, team);
         }
-
-        // ---- stage the tile
-        if (P.first) {
-            // product-state start: |psi> = (x)_q v_q with v_q = (folded 1-qubit gates of q)|0>
-            double2* qv = mats + P.mat_elems;  // [32][2]
-            double2* lo = qv + 64;             // [64] partial products over the low tile bits
-            double2* hi = lo + 64;             // [<=128] partial products over the high tile bits
-            for (int q = tid; q < A.n; q += TS)
-                fold_qubit_vector(q, A.inits, A.n_init, A.gates, xrow, A.table, A.n_total, sample, vgate,
-                                  vshift, qv + 2 * q);
-            team_sync(TS, team);
-            const int nlo = T < 6 ? T : 6, nhi = T - nlo;
-            for (int t = tid; t < (1 << nlo); t += TS) lo[t] = product_amp(t, nlo, P.extq, qv);
-            for (int t = tid; t < (1 << nhi); t += TS) hi[t] = product_amp(t, nhi, P.extq + nlo, qv);
-            team_sync(TS, team);
-            for (uint32_t l = tid; l < tile_elems; l += TS)
-                tile[tile_sw(l)] = cmul(lo[l & ((1u << nlo) - 1u)], hi[l >> nlo]);
-        } else {
+        // ---- phase B: product tables, phase tables
+        if (P.n_tabs > 0 || P.n_fresh > 0) build_tables_thread(pv, tm, ic, tid, TS, new_sample);
+        // ---- phase C: stage the tile
+        if (plain) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // this item's tile has landed
+        } else {
+            team_sync(TS, team);
+            const double2* sstate = P.has_src
+                ? A.src + (((int64_t)variant * A.src_vstride + ic.sample - A.src_off) << P.in_bits) : nullptr;
+            stage_thread(pv, tm, sstate, obase_in, map, tid, TS);
         }
         team_sync(TS, team);
 
         // ---- rounds
-        const uint32_t ext_base = outer << T;
         for (int r = 0; r < P.n_rounds; ++r) {
-            exec_round_thread(tile, A.rounds[r], A.uops, mats, ext_base, T, tid, TS);
+            exec_round_thread(tm.tile, &pv.rounds[r], pv.steps, tm.mats, ic.ext_base, T, tid, TS);
             team_sync(TS, team);
         }
 
         // ---- epilogue
         if (A.store && in_range) {
-            double2* dst = state + (obase | g_lo);
-            for (int j = 0; j < J; ++j) __stcs(dst + ghi[j], tile[smem_idx(j)]);
+            double2* dp = dstate + (obase_out | map.out_lo);
+            for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], tm.tile[smem_idx(j)]);
         }
         if (A.n_terms > 0) {
             // T == n here: the tile is the state and local index == amplitude index.
             const int nwarps = TS >> 5, warp = tid >> 5, lane = tid & 31;
-            double* out = A.out + ((int64_t)variant * A.n_total + sample) * A.n_terms;
+            double* out = A.out + ((int64_t)variant * A.n_total + ic.sample) * A.n_terms;
             for (int t = warp; t < A.n_terms; t += nwarps) {
                 const uint32_t xm = A.xmask[t], zm = A.zmask[t];
                 const int ny = __popc(xm & zm);
                 double acc = 0.0;
                 for (uint32_t l = lane; l < tile_elems; l += 32)
-                    acc += pauli_term(tile[tile_sw(l ^ xm)], tile[tile_sw(l)], l, zm, ny);
+                    acc += pauli_term(tm.tile[tile_sw(l ^ xm)], tm.tile[tile_sw(l)], l, zm, ny);
                 acc = warp_sum(acc);
                 if (lane == 0) out[t] = acc;
             }
@@ -239,23 +253,30 @@ __global__ void k_rbf(const double* __restrict__ fx, int64_t nx, const double* _
 
 }  // namespace
 
-int tile_pass_smem_bytes(int T, int mat_elems, int first, int* team_size, int* teams_per_cta,
-                         int* team_elems) {
+// Team geometry and dynamic shared memory of a pass.
+//   team_elems: double2 elements per team = tile buffer(s) + matrices/tables + scratch + per-j tables
+void tile_pass_geometry(const DPass& P, TileArgs* a) {
+    const int T = P.T;
+    // one thread per two register groups of eight amplitudes (the interpreter decodes a step once for
+    // both), at least a warp, at most the CTA
     int groups = T >= 3 ? (1 << (T - 3)) : 1;
-    int ts = groups < 32 ? 32 : (groups > kCtaThreads ? kCtaThreads : groups);
-    // one tile (first pass: nothing is loaded) or two (double buffering) + matrices + product-start scratch
-    int elems = (first ? 1 : 2) * (1 << T) + mat_elems + 64 + 64 + 128 + 16;  // + ghi table
+    int ts = groups / 2 < 32 ? 32 : (groups / 2 > kCtaThreads ? kCtaThreads : groups / 2);
+    int log2ts = 0;
+    while ((1 << log2ts) < ts) ++log2ts;
+    const bool plain = P.has_src && P.n_fresh == 0;
+    const int J = std::max(1, (1 << T) >> log2ts);
+    int elems = (plain ? 2 : 1) * (1 << T) + P.mat_elems + kScratchElems + J;
     elems = (elems + 7) & ~7;  // keep every team 128-byte aligned
     int teams = kCtaThreads / ts;
-    while (teams > 1 && (size_t)teams * elems * sizeof(double2) > (size_t)kMaxSmem / 2) teams >>= 1;
-    *team_size = ts;
-    *teams_per_cta = teams;
-    *team_elems = elems;
-    return teams * elems * (int)sizeof(double2);
+    while (teams > 1 && (size_t)teams * elems * sizeof(double2) + P.blob_bytes > (size_t)kMaxSmem / 2) teams >>= 1;
+    a->team_size = ts;
+    a->log2ts = log2ts;
+    a->teams_per_cta = teams;
+    a->team_elems = elems;
 }
 
 int launch_tile_pass(const TileArgs& args, cudaStream_t stream) {
-    const int smem = args.teams_per_cta * args.team_elems * (int)sizeof(double2);
+    const int smem = args.blob_bytes + args.teams_per_cta * args.team_elems * (int)sizeof(double2);
     if (smem > kMaxSmem) return (int)cudaErrorInvalidConfiguration;
     {
         cudaError_t e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -265,7 +286,7 @@ int launch_tile_pass(const TileArgs& args, cudaStream_t stream) {
     const int threads = args.team_size * args.teams_per_cta;
     int64_t ctas = (args.total_items + args.teams_per_cta - 1) / args.teams_per_cta;
     if (ctas <= 0) return 0;
-    // persistent grid: as many CTAs as fit on the GPU at once; teams stride over the work items
+    // persistent grid: as many CTAs as fit on the GPU at once; teams take contiguous item chunks
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "libb200sq_hostemu.so")
 SRC = os.path.join(HERE, "hostemu.cpp")
 DEPS = [SRC, os.path.join(ROOT, "squlearn_b200", "csrc", "plan.hpp"),
-        os.path.join(ROOT, "squlearn_b200", "csrc", "uop_exec.cuh"),
+        os.path.join(ROOT, "squlearn_b200", "csrc", "tile_exec.cuh"),
         os.path.join(ROOT, "include", "b200sq.h")]
 
 

@@ -95,12 +95,59 @@ def test_random_circuits_all_gates(seed):
     p = rng.uniform(-2, 2, num_params)
     want = oracle.simulate(ogates, n, X, p)
     try:
-        got, _ = hostemu.simulate(prog, p, X, tile_bits=tile_bits, team_size=int(rng.choice([1, 7, 32])))
+        got, _ = hostemu.simulate(prog, p, X, tile_bits=tile_bits, team_size=int(rng.choice([1, 8, 32])))
     except RuntimeError as e:
         if "more target qubits" in str(e):
             pytest.skip("tile too small for a multi-target gate")
         raise
     assert np.max(np.abs(got - want)) < TOL
+
+
+DIAG_HEAVY = ["rz", "p", "cz", "crz", "cp", "rzz", "s", "t", "z", "cs", "rx", "ry", "h", "cx", "rzz", "crz"]
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_diagonal_heavy_circuits(seed):
+    """Phase-table steps (runs of commuting diagonal gates, one or two bit groups), deferred phases,
+    layer steps and the compact active-qubit layouts between passes."""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(3, 11))
+    tile_bits = int(rng.integers(3, n + 1))
+    num_params, d = 6, 3
+    prog, ogates = random_circuit(n, 60, num_params, d, rng, kinds=DIAG_HEAVY)
+    X = rng.uniform(-0.9, 0.9, (2, d))
+    p = rng.uniform(-2, 2, num_params)
+    want = oracle.simulate(ogates, n, X, p)
+    got, _ = hostemu.simulate(prog, p, X, tile_bits=tile_bits, team_size=int(rng.choice([1, 4, 32, 256])))
+    assert np.max(np.abs(got - want)) < TOL
+
+
+@pytest.mark.parametrize("n,tile_bits", [(10, 4), (11, 5), (12, 8), (13, 9), (12, 12)])
+def test_layered_circuits_multi_pass_layouts(n, tile_bits):
+    """ChebyshevPQC / Hubregtsen at sizes where several passes with growing active sets are needed."""
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-0.95, 0.95, (2, 3))
+    for enc, og in ((ChebyshevPQC(n, 2), oracle.chebyshev_pqc(n, 2, 3)),
+                    (HubregtsenEncodingCircuit(n, 1), oracle.hubregtsen(n, 1, 3))):
+        p = enc.generate_initial_parameters(3, seed=0)
+        want = oracle.simulate(og, n, X, p)
+        got, passes = hostemu.simulate(enc.get_program(3), p, X, tile_bits=tile_bits, team_size=32)
+        assert np.max(np.abs(got - want)) < TOL
+        if tile_bits < n:
+            assert passes >= 2
+
+
+def test_untouched_qubits_stay_zero():
+    """Qubits no gate acts on never become active: the last pass must still write the full layout."""
+    from squlearn_b200.program import Angle, GateOp, Program
+    from oracle.statevector import Gate
+    n = 7
+    prog = Program(n, [GateOp("h", (1,)), GateOp("cx", (1, 5)), GateOp("rz", (6,), Angle(scale=0.3))], 0, 1)
+    og = [Gate("h", (1,), ()), Gate("cx", (1, 5), ()), Gate("rz", (6,), (lambda x, p: 0.3 + 0 * x[:, 0],))]
+    X = np.zeros((2, 1))
+    for tb in (3, 4, 7):
+        got, _ = hostemu.simulate(prog, None, X, tile_bits=tb)
+        assert np.max(np.abs(got - oracle.simulate(og, n, X))) < TOL
 
 
 def test_general_angle_callable_goes_through_table():

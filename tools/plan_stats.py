@@ -14,19 +14,30 @@ def stats(enc, d, tile_bits=0, params=None):
     pos = 5
     passes = []
     for _ in range(npass):
-        Tp, first, r0, r1, u0, u1, mat = w[pos:pos + 7]
-        tq = list(w[pos + 7:pos + 7 + Tp]); pos += 7 + Tp
-        passes.append((Tp, first, r0, r1, u0, u1, mat, tq))
+        Tp, a_in, a_out, last, r0, r1, s0, s1, mat, nfresh, ntabs = w[pos:pos + 11]
+        tq = [int(q) for q in w[pos + 11:pos + 11 + Tp]]; pos += 11 + Tp
+        passes.append((Tp, a_in, a_out, last, r0, r1, s0, s1, mat, nfresh, ntabs, tq))
     rounds = [tuple(w[pos + 6 * i: pos + 6 * i + 6]) for i in range(nr)]; pos += 6 * nr
-    uops = [tuple(w[pos + 7 * i: pos + 7 * i + 7]) for i in range(nu)]
-    print(f"n={n} T={T} gates={len(prog)} passes={npass} rounds={nr} uops={nu}")
-    for i, (Tp, first, r0, r1, u0, u1, mat, tq) in enumerate(passes):
-        print(f" pass {i}: first={first} tile_qubits={tq} rounds={r1 - r0} uops={u1 - u0} mat_elems={mat}")
+    steps = [tuple(w[pos + 7 * i: pos + 7 * i + 7]) for i in range(nu)]; pos += 7 * nu
+    ninit = w[pos]
+    print(f"n={n} T={T} gates={len(prog)} passes={npass} rounds={nr} steps={nu} folded={ninit}")
+    names = {1: "U2", 2: "DIAG", 5: "CTRL", 6: "L_RX", 7: "L_REAL", 8: "L_GEN", 9: "DTAB"}
+    qs = lambda m: [q for q in range(n) if m >> q & 1]
+    for i, (Tp, a_in, a_out, last, r0, r1, s0, s1, mat, nfresh, ntabs, tq) in enumerate(passes):
+        print(f" pass {i}: tile={tq} in={len(qs(a_in))}q out={len(qs(a_out))}q fresh={nfresh} last={last} "
+              f"rounds={r1 - r0} steps={s1 - s0} tables={ntabs} mat_elems={mat}")
         for r in range(r0, r1):
-            nb, b0, b1, b2, ru0, ru1 = rounds[r]
-            kinds = [("U1", "U2", "DG", "RX", "RE", "CT")[uops[u][0]] for u in range(ru0, ru1)]
-            print(f"   round {r}: bits={[b0, b1, b2][:nb]} uops={ru1 - ru0} " + " ".join(
-                f"{k}{prog.gates[uops[u][1]].name}{list(prog.gates[uops[u][1]].qubits)}" for k, u in zip(kinds, range(ru0, ru1))))
+            nb, b0, b1, b2, rs0, rs1 = rounds[r]
+            desc = []
+            for u in range(rs0, rs1):
+                kind, gate, a, b, ctrl, m, sw = steps[u]
+                if kind in (6, 7, 8):
+                    desc.append(f"{names[kind]}[slots {[c for c in range(3) if a >> c & 1]}]")
+                elif kind == 9:
+                    desc.append(f"DTAB[bits {a}..{a + b - 1}]")
+                else:
+                    desc.append(f"{names[kind]}:{prog.gates[gate].name}{list(prog.gates[gate].qubits)}")
+            print(f"   round {r}: bits={[int(b0), int(b1), int(b2)][:nb]} " + " ".join(desc))
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
