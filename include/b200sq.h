@@ -85,6 +85,9 @@ typedef struct b200sq_program b200sq_program;
 #define B200SQ_GRAM_3M 8u          /* 3-multiplication complex product (fewer flops)            */
 #define B200SQ_GRAM_CLASSIC 16u    /* with 3M: use the barrier-pipelined kernel, not the          */
                                    /* warp-specialised bulk-copy one (kept for A/B measurements) */
+#define B200SQ_GRAM_INT8 32u       /* split-integer FP64 emulation on the INT8 tcgen05 tensor     */
+                                   /* cores (47-bit fixed point per state row; |dK| ~ 1e-12, see  */
+                                   /* DESIGN.md); needs dim >= 64, otherwise the FP64 path runs   */
 
 B200SQ_API const char* b200sq_last_error(void);
 B200SQ_API int b200sq_abi_version(void);

@@ -34,7 +34,7 @@ GATE_ARITY = {
 
 FN_CONST, FN_LINEAR, FN_ARCCOS, FN_ARCTAN, FN_TABLE = range(5)
 
-GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M, GRAM_CLASSIC = 1, 2, 4, 8, 16
+GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M, GRAM_CLASSIC, GRAM_INT8 = 1, 2, 4, 8, 16, 32
 
 
 class Gate(ctypes.Structure):

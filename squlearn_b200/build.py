@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sq.so")
-SOURCES = ["api.cu", "sim_kernels.cu", "gram_kernels.cu"]
+SOURCES = ["api.cu", "sim_kernels.cu", "gram_kernels.cu", "gram_i8.cu"]
 HEADERS = ["plan.hpp", "tile_exec.cuh", "kernels.h", os.path.join(ROOT, "include", "b200sq.h")]
 
 NVCC_FLAGS = [

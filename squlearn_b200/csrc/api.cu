@@ -379,7 +379,12 @@ int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_
     if (Nx < 0 || Ny < 0 || dim < 1 || ldk < Ny) return fail(2, "bad sizes");
     if ((flags & B200SQ_GRAM_SYMMETRIC) && (Nx != Ny || ldk < Nx))
         return fail(2, "symmetric Gram needs Nx == Ny");
-    int e = launch_gram((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
+    int e;
+    if ((flags & B200SQ_GRAM_INT8) && gram_i8_supported(dim))
+        e = launch_gram_i8((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
+                           (cudaStream_t)stream_);
+    else
+        e = launch_gram((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
                         (cudaStream_t)stream_);
     if (e) return cuda_fail(e, "gram launch (no CUDA device? b200sq has no CPU path)");
     return 0;

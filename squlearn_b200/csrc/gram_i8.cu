@@ -1,0 +1,525 @@
+// Fidelity Gram matrix on the 5th-generation tensor cores: split-integer ("Ozaki scheme") FP64 emulation.
+//
+// tcgen05 has no f64 kind and B200's FP64 DMMA peaks at ~37 TFLOP/s, while the INT8 kind runs at
+// ~4.5 POP/s.  Every amplitude component v of a state row is therefore written in fixed point relative to
+// the row's power-of-two scale 2^e,
+//        v = 2^e * sum_{s=0}^{S-1} d_s * 2^(-6 - 8 s),      d_0 in [-65, 65], d_s in [-128, 127]  (S = 6)
+// (exact integer digit decomposition of round(v * 2^(46 - e)): 47 significant bits per row), and the complex
+// inner products become sums of EXACT int8 x int8 -> int32 tensor-core products, grouped by weight class
+// c = i + j:
+//        <x|y> = 2^(ex + ey - 12) * sum_c 2^(-8 c) * sum_{i + j = c} D_i(x)^T D_j(y)
+// Classes c <= 5 (21 slice pairs) plus the pair (3, 3) are kept; what is dropped is below 2^-48 of the row
+// scales (measured |K - K_fp64| ~ 1e-13 .. 1e-11, see DESIGN.md for the bound).
+//
+// Complex arithmetic without data rearrangement in the GEMM: a state row is the real vector
+// (re_0, im_0, re_1, im_1, ...), K' = 2 * dim.  With  nat(y) = (yr_k, yi_k)  and  rot(y) = (yi_k, -yr_k):
+//        Re <x|y> = x . nat(y),     Im <x|y> = x . rot(y)
+// so one A tile feeds two accumulators through two B tiles (digit planes of y and of rot(y)).
+//
+// Kernel k_gram_i8 (one CTA per SM, persistent over work units = (128 x 128 tile, 16 KiB K-chunk)):
+//   warp 0    TMA producer: 3 x 16 KiB boxes (A_i, Bnat_j, Brot_j; 128 rows x 128 B, SWIZZLE_128B) per stage
+//   warp 1    MMA issuer:   8 x tcgen05.mma.kind::i8 (M = N = 128, K = 32) per stage into TMEM (s32)
+//   warp 2    TMEM allocator (512 columns: 2 accumulator stages x (Re 128 + Im 128))
+//   warps 4-7 epilogue: tcgen05.ld -> int32 -> double * 2^(-8 c) -> red.add.f64 into the per-tile FP64
+//             accumulator W (int32 accumulation is exact for <= 7 pairs x 16 KiB: 7 * 2^14 * 2^14 < 2^31)
+// k_slice_i8 produces the digit planes, k_gram_i8_final turns W into K = |.|^2 with the symmetric
+// mirror / diagonal policy of the FP64 kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "kernels.h"
+
+namespace b200sq {
+
+namespace {
+
+constexpr int kSlices = 6;
+constexpr int kTopBits = 6 + 8 * (kSlices - 1);  // v * 2^(kTopBits - e) is the integer that gets sliced
+constexpr int kTile = 128;
+constexpr int kStageK = 128;                     // bytes of K per pipeline stage (one swizzle atom)
+constexpr int kTileBytes = kTile * kStageK;      // 16 KiB
+constexpr int kStageBytes = 3 * kTileBytes;      // A, Bnat, Brot
+constexpr int kStages = 4;
+constexpr int kChunkK = 16384;                   // bytes of K per int32 accumulation chunk
+constexpr int kMaxClasses = 8, kMaxPairs = 8;
+constexpr int kThreads = 256;
+
+struct I8Schedule {
+    int n_classes;
+    int cls_shift[kMaxClasses];   // weight of the class = 2^(-8 * cls_shift)
+    int n_pairs[kMaxClasses];
+    uint8_t pi[kMaxClasses][kMaxPairs], pj[kMaxClasses][kMaxPairs];
+};
+
+struct I8Args {
+    int64_t rows_a, rows_b;   // rows per digit plane of the A / B operand
+    int kbytes;               // K' = 2 * dim bytes per row
+    int n_chunks, chunk_bytes;
+    int tiles_n, n_tiles, symmetric;
+    double* W;                // [n_tiles][2][128 cols][128 rows]
+    I8Schedule sched;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B (8-row atoms of 1024 bytes): LBO unused, SBO = 1024.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::i8: D = s32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9 = 1, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void decode_tile(const I8Args& A, int t, int& bm, int& bn) {
+    if (A.symmetric) {
+        bm = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bm + 1) * (bm + 2) / 2 <= t) ++bm;
+        while (bm * (bm + 1) / 2 > t) --bm;
+        bn = t - bm * (bm + 1) / 2;
+    } else {
+        bm = t / A.tiles_n;
+        bn = t - bm * A.tiles_n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+          const __grid_constant__ I8Args A) {
+    extern __shared__ unsigned char smem_dyn[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    const int n_units = A.n_tiles * A.n_chunks;
+    const I8Schedule& S = A.sched;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
+                int bm, bn;
+                decode_tile(A, tile, bm, bn);
+                const int k0 = chunk * A.chunk_bytes;
+                const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
+                for (int ci = 0; ci < S.n_classes; ++ci)
+                    for (int p = 0; p < S.n_pairs[ci]; ++p) {
+                        const int row_a = (int)(S.pi[ci][p] * A.rows_a) + bm * kTile;
+                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b) + bn * kTile;
+                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b) + bn * kTile;
+                        for (int k = k0; k < k1; k += kStageK) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t dst = smem_base + stage * kStageBytes;
+                            mbar_expect_tx(full_bar(stage), kStageBytes);
+                            tma_load_2d(dst, &mapA, full_bar(stage), k, row_a);
+                            tma_load_2d(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
+                            tma_load_2d(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc_it = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int chunk = u / A.n_tiles;
+                const int k0 = chunk * A.chunk_bytes;
+                const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
+                for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
+                    const uint32_t acc = acc_it & 1u, acc_phase = (acc_it >> 1) & 1u;
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_re = tmem_base + acc * 256u, d_im = d_re + 128u;
+                    uint32_t accumulate = 0;
+                    for (int p = 0; p < S.n_pairs[ci]; ++p)
+                        for (int k = k0; k < k1; k += kStageK) {
+                            mbar_wait(full_bar(stage), phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * kStageBytes;
+                            const uint64_t da = umma_smem_desc(sa);
+                            const uint64_t dbn = umma_smem_desc(sa + kTileBytes);
+                            const uint64_t dbr = umma_smem_desc(sa + 2 * kTileBytes);
+#pragma unroll
+                            for (int kk = 0; kk < kStageK / 32; ++kk) {
+                                // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+                                umma_i8(d_re, da + 2u * kk, dbn + 2u * kk, kInstrDesc, accumulate | (uint32_t)kk);
+                                umma_i8(d_im, da + 2u * kk, dbr + 2u * kk, kInstrDesc, accumulate | (uint32_t)kk);
+                            }
+                            accumulate = 1;
+                            umma_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        }
+                    umma_commit(tfull_bar(acc));  // accumulator of this class complete
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> FP64 accumulators in global memory =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        uint32_t acc_it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
+            double* wt = A.W + (size_t)tile * (2 * kTile * kTile) + row;
+            for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
+                const uint32_t acc = acc_it & 1u, acc_phase = (acc_it >> 1) & 1u;
+                const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+#pragma unroll 1
+                for (int cb = 0; cb < 8; ++cb) {  // 8 blocks of 32 columns: Re 0..127, Im 128..255
+                    uint32_t v[32];
+                    tmem_ld32(t0 + cb * 32, v);
+                    tmem_ld_wait();
+                    double* wp = wt + (size_t)(cb * 32) * kTile;  // [part][col][row], part = cb >> 2
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int iv = (int)v[c];
+                        if (iv != 0) red_add_f64(wp + (size_t)c * kTile, (double)iv * w);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Digit planes.  planes: [2 * kSlices][n_rows][2 * dim] int8; plane s = digits of (re, im), plane
+// kSlices + s = digits of (im, -re).  One CTA per state row.
+
+__device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int byte) {
+    const long long d = ((q + 128) & 255) - 128;
+    q = (q - d) >> 8;
+    return word | (((uint32_t)d & 255u) << (8 * byte));
+}
+
+__global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t n_rows, int64_t dim,
+                                                  int8_t* __restrict__ planes, int* __restrict__ expo) {
+    const int64_t row = blockIdx.x;
+    const double2* src = psi + row * dim;
+    __shared__ double red[8];
+    __shared__ int s_e;
+    double m = 0.0;
+    for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        const double2 v = src[i];
+        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);  // m = f * 2^e, f in [0.5, 1): every |v| < 2^e
+        s_e = e;
+        expo[row] = e;
+    }
+    __syncthreads();
+    const double scale = ldexp(1.0, kTopBits - s_e);
+    const size_t plane_stride = (size_t)n_rows * 2 * dim;
+    int8_t* dst_row = planes + (size_t)row * 2 * dim;
+    // 8 complex amplitudes per thread and iteration -> 16 bytes per plane
+    for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
+        long long qn[16], qr[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = src[i0 + c];
+            const long long a = __double2ll_rn(v.x * scale), b = __double2ll_rn(v.y * scale);
+            qn[2 * c] = a;
+            qn[2 * c + 1] = b;
+            qr[2 * c] = b;
+            qr[2 * c + 1] = -a;
+        }
+#pragma unroll
+        for (int s = kSlices - 1; s >= 0; --s) {
+            uint32_t wn[4] = {0, 0, 0, 0}, wr[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                wn[b >> 2] = pack_digit(qn[b], wn[b >> 2], b & 3);
+                wr[b >> 2] = pack_digit(qr[b], wr[b >> 2], b & 3);
+            }
+            *reinterpret_cast<uint4*>(dst_row + (size_t)s * plane_stride + 2 * i0) = make_uint4(wn[0], wn[1], wn[2], wn[3]);
+            *reinterpret_cast<uint4*>(dst_row + (size_t)(kSlices + s) * plane_stride + 2 * i0) =
+                make_uint4(wr[0], wr[1], wr[2], wr[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// W -> K.  One CTA per tile; 32 x 32 sub-blocks go through shared memory so that both the direct and the
+// mirrored store are coalesced.
+
+__global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict__ W, const int* __restrict__ ex,
+                                                       const int* __restrict__ ey, double* __restrict__ K,
+                                                       int64_t ldk, int64_t nx, int64_t ny, I8Args A, uint32_t flags) {
+    __shared__ double sm[32][33];
+    int bm, bn;
+    decode_tile(A, blockIdx.x, bm, bn);
+    const double* wt = W + (size_t)blockIdx.x * (2 * kTile * kTile);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    for (int sb = 0; sb < 16; ++sb) {
+        const int sr = sb >> 2, sc = sb & 3;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+            const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+            double k = 0.0;
+            if (i < nx && j < ny) {
+                // diagonal tiles of a symmetric Gram: take both triangles from the lower one, so that K is
+                // bit-exactly symmetric whatever order the atomic FP64 accumulation happened in
+                const int r2 = (sym && bm == bn && col > row) ? col : row, c2 = (sym && bm == bn && col > row) ? row : col;
+                const double re = wt[(size_t)c2 * kTile + r2], im = wt[(size_t)(kTile + c2) * kTile + r2];
+                k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j] - 12));
+                if (sym && i == j) {
+                    if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
+                    else if (flags & B200SQ_GRAM_DIAG_ZERO) k = 0.0;
+                }
+            }
+            sm[ty + 8 * qd][tx] = k;  // [col][row]
+        }
+        __syncthreads();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            {   // direct: K[i][j], consecutive threads -> consecutive j
+                const int row = sr * 32 + ty + 8 * qd, col = sc * 32 + tx;
+                const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+                if (i < nx && j < ny) K[i * ldk + j] = sm[tx][ty + 8 * qd];
+            }
+            if (sym && bm != bn) {  // mirror: K[j][i], consecutive threads -> consecutive i
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+                if (i < nx && j < ny) K[j * ldk + i] = sm[ty + 8 * qd][tx];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_planes(CUtensorMap* map, void* base, uint64_t kbytes, uint64_t rows_total) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return (int)cudaErrorNotSupported;
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {kbytes, rows_total};
+    const cuuint64_t strides[1] = {kbytes};
+    const cuuint32_t box[2] = {(cuuint32_t)kStageK, (cuuint32_t)kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
+
+int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
+                   int64_t ldk, uint32_t flags, cudaStream_t stream) {
+    if (nx <= 0 || ny <= 0) return 0;
+    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    const int64_t kbytes = 2 * dim;
+    const size_t plane_bytes = (size_t)kbytes;  // per row
+    int8_t *px = nullptr, *py = nullptr;
+    int *ex = nullptr, *ey = nullptr;
+    double* W = nullptr;
+    cudaError_t e;
+    auto cleanup = [&]() {
+        if (px) cudaFreeAsync(px, stream);
+        if (py && py != px) cudaFreeAsync(py, stream);
+        if (ex) cudaFreeAsync(ex, stream);
+        if (ey && ey != ex) cudaFreeAsync(ey, stream);
+        if (W) cudaFreeAsync(W, stream);
+    };
+    if ((e = cudaMallocAsync(&py, 2 * kSlices * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMallocAsync(&ey, ny * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
+    k_slice_i8<<<(unsigned)ny, 256, 0, stream>>>(y, ny, dim, py, ey);
+    count_launch();
+    if (sym) {
+        px = py;
+        ex = ey;
+    } else {
+        if ((e = cudaMallocAsync(&px, 2 * kSlices * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
+        if ((e = cudaMallocAsync(&ex, nx * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
+        k_slice_i8<<<(unsigned)nx, 256, 0, stream>>>(x, nx, dim, px, ex);
+        count_launch();
+    }
+    I8Args a;
+    memset(&a, 0, sizeof(a));
+    a.rows_a = nx;
+    a.rows_b = ny;
+    a.kbytes = (int)kbytes;
+    a.chunk_bytes = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
+    a.n_chunks = (int)((kbytes + a.chunk_bytes - 1) / a.chunk_bytes);
+    const int tiles_m = (int)((nx + kTile - 1) / kTile);
+    a.tiles_n = (int)((ny + kTile - 1) / kTile);
+    a.symmetric = sym ? 1 : 0;
+    a.n_tiles = sym ? tiles_m * (tiles_m + 1) / 2 : tiles_m * a.tiles_n;
+    // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
+    {
+        I8Schedule& s = a.sched;
+        int nc = 0;
+        s.cls_shift[nc] = 6;
+        s.n_pairs[nc] = 1;
+        s.pi[nc][0] = 3;
+        s.pj[nc][0] = 3;
+        ++nc;
+        for (int c = kSlices - 1; c >= 0; --c, ++nc) {
+            s.cls_shift[nc] = c;
+            s.n_pairs[nc] = 0;
+            for (int i = 0; i <= c; ++i) {
+                s.pi[nc][s.n_pairs[nc]] = (uint8_t)i;
+                s.pj[nc][s.n_pairs[nc]] = (uint8_t)(c - i);
+                ++s.n_pairs[nc];
+            }
+        }
+        s.n_classes = nc;
+    }
+    const size_t wbytes = (size_t)a.n_tiles * 2 * kTile * kTile * sizeof(double);
+    if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
+    a.W = W;
+    cudaMemsetAsync(W, 0, wbytes, stream);
+    CUtensorMap mapA, mapB;
+    int rc = encode_planes(&mapA, px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * nx);
+    if (!rc) rc = encode_planes(&mapB, py, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * ny);
+    if (rc) { cleanup(); return rc; }
+    const int smem = kStages * kStageBytes + 1024 + 256;
+    if ((e = cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) {
+        cleanup();
+        return (int)e;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_units = a.n_tiles * a.n_chunks;
+    const int grid = n_units < sms ? n_units : sms;
+    k_gram_i8<<<grid, kThreads, smem, stream>>>(mapA, mapB, a);
+    count_launch();
+    k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, ex, ey, k, ldk, nx, ny, a, flags);
+    count_launch();
+    e = cudaGetLastError();
+    cleanup();
+    return (int)e;
+}
+
+}  // namespace b200sq

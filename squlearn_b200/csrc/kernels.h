@@ -46,6 +46,11 @@ int launch_expvals(const double2* psi, int64_t n_states, int n_qubits, int n_ter
 int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                 int64_t ldk, uint32_t flags, cudaStream_t stream);
 
+// Split-integer (INT8 tcgen05) Gram: see gram_i8.cu.  Falls back to nothing: callers check gram_i8_supported.
+bool gram_i8_supported(int64_t dim);
+int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
+                   int64_t ldk, uint32_t flags, cudaStream_t stream);
+
 int launch_rbf(const double* fx, int64_t nx, const double* fy, int64_t ny, int nf, double gamma,
                double* k, int64_t ldk, cudaStream_t stream);
 

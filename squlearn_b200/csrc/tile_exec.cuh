@@ -444,21 +444,17 @@ B200SQ_HD void u2_general(double2 (&a)[G][1 << NB], const double2* __restrict__ 
 template <int NB, int G>
 B200SQ_HD void diag_apply(double2 (&a)[G][1 << NB], const DStep& u, const double2* __restrict__ m,
                           const uint32_t (&e)[G], const uint32_t (&ko)[1 << NB]) {
-    const double2 p0 = m[0], p1 = m[1], p2 = m[2], p3 = m[3];
-    const uint32_t skip = u.ctrl;
-    const int q0 = u.r0, q1 = u.r1;
+    const int q0 = u.r0, q1 = u.r1 >= 0 ? u.r1 : u.r0;
+    const uint32_t two = u.r1 >= 0 ? 2u : 0u;
+    uint32_t kp[1 << NB];  // the register slots' share of the phase index
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi)
+    for (int k = 0; k < (1 << NB); ++k) kp[k] = ((ko[k] >> q0) & 1u) | (((ko[k] >> q1) << 1) & two);
 #pragma unroll
-        for (int k = 0; k < (1 << NB); ++k) {
-            const uint32_t x = e[gi] | ko[k];
-            uint32_t idx = (x >> q0) & 1u;
-            if (q1 >= 0) idx |= ((x >> q1) & 1u) << 1;
-            if (!((skip >> idx) & 1u)) {
-                const double2 ph = idx == 0 ? p0 : idx == 1 ? p1 : idx == 2 ? p2 : p3;
-                a[gi][k] = cmul(a[gi][k], ph);
-            }
-        }
+    for (int gi = 0; gi < G; ++gi) {
+        const uint32_t i0 = ((e[gi] >> q0) & 1u) | (((e[gi] >> q1) << 1) & two);
+#pragma unroll
+        for (int k = 0; k < (1 << NB); ++k) a[gi][k] = cmul(a[gi][k], m[i0 | kp[k]]);
+    }
 }
 
 // Phase table: one complex multiply per amplitude for a whole run of diagonal gates.

@@ -198,9 +198,12 @@ class Engine:
                                                 zm, out.data_ptr(), self._stream()))
         return out.reshape(tuple(psi.shape[:-1]) + (len(terms),))
 
-    def gram(self, psi_x, psi_y=None, diagonal: str = "one", out=None, three_m: Optional[bool] = None):
+    def gram(self, psi_x, psi_y=None, diagonal: str = "one", out=None, three_m: Optional[bool] = None,
+             precision: Optional[str] = None):
         """K[i, j] = |<psi_x[i]|psi_y[j]>|^2.  ``psi_y=None`` means the symmetric Gram of psi_x;
-        ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy."""
+        ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy.
+        ``precision``: "fp64" (FP64 DMMA) or "int8" (split-integer FP64 emulation on the INT8 tcgen05
+        tensor cores, |dK| ~ 1e-12; used when 2^n >= 64); default from B200SQ_GRAM_PRECISION, else "fp64"."""
         torch = self._torch
         psi_x = psi_x.contiguous()
         sym = psi_y is None
@@ -217,6 +220,12 @@ class Engine:
             flags |= _lib.GRAM_3M
             if os.environ.get("B200SQ_GRAM_MODE", "").lower() == "3m-classic" or three_m == "classic":
                 flags |= _lib.GRAM_CLASSIC
+        if precision is None:
+            precision = os.environ.get("B200SQ_GRAM_PRECISION", "fp64").lower()
+        if precision not in ("fp64", "int8"):
+            raise ValueError("precision must be 'fp64' or 'int8'")
+        if precision == "int8":
+            flags |= _lib.GRAM_INT8
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
