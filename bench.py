@@ -301,12 +301,15 @@ def run_gpu_arm(args):
         e2e_ms = float(t.item())
 
     line = None
+    dtype_str = ("f64 (complex128 states; Gram via exact int8 slices of a 47-bit fixed-point split, FP64 recombination)"
+                 if eng.gram_precision(n_points // world if multi else n_points, n_points, dim) == "int8"
+                 else "f64 (complex128)")
     if rank == 0:
         assert k_host is not None and k_host.shape == (n_points, n_points)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": dtype_str, "data": "synthetic",
             "config": config_dict(args, world), "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": n_points * n_points / (e2e_ms * 1e-3), "unit": UNIT,
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(X.nbytes),
@@ -319,42 +322,84 @@ def run_gpu_arm(args):
             pass
         if not multi:
             fp64_peak = fp64_peak_probe(torch, dev)
-            mode_4m = os.environ.get("B200SQ_GRAM_MODE", "3m").lower() == "4m"
-            bm = 128 if mode_4m else 64
-            tiles_m = (n_points + bm - 1) // bm
-            # symmetric: only tiles touching the lower triangle run
-            tiles = sum(1 for bi in range(tiles_m) for bj in range((n_points + 63) // 64)
-                        if bj * 64 <= bi * bm + bm - 1)
-            entries_computed = tiles * bm * 64
-            flops = 8.0 * dim * entries_computed
             g_ms = float(np.mean(gram_ms))
-            achieved = flops / (g_ms * 1e-3) / 1e12
-            line["roofline"] = {
-                "kernel": ("k_gram 4M" if mode_4m else "k_gram3m_ws (3M, warp-specialised)")
-                          + ", FP64 DMMA, fused |.|^2 epilogue", "bound": "tensor",
-                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "ms_per_launch": g_ms,
-                "algorithmic": f"8*2^n flop per entry x {entries_computed} entries computed "
-                               f"({tiles} lower-triangle {bm}x64 tiles of the symmetric Gram)",
-                "executed_tflops": achieved * (1.0 if mode_4m else 0.75),
-                "executed_note": "3M (Gauss) complex product issues 6*2^n tensor flops per entry; the DMMA "
-                                 "hardware ceiling measured with tools/dmma_probe.cu is 37.1 TFLOP/s",
-                "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3; "
-                               "MEASURED_PEAKS.json carries no FP64 figure",
-                "share_of_step": g_ms / ms_per_step,
-            }
+            traffic = {}
+            try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            except Exception:
+                pass
+            if eng.gram_precision(n_points, n_points, dim) == "int8":
+                mn = 256
+                tm = (n_points + mn - 1) // mn
+                tiles = tm * (tm + 1) // 2
+                entries_computed = tiles * mn * mn
+                pairs = 22
+                ops = 2.0 * pairs * 2 * (2 * dim) * entries_computed  # int8 multiply-adds x 2
+                achieved = ops / (g_ms * 1e-3) / 1e12
+                bf16 = float(peaks.get("bf16_tflops", 1590.0))
+                i8_peak = 2.0 * bf16
+                fp64_equiv = 8.0 * dim * (n_points * (n_points + 1) / 2) / (g_ms * 1e-3) / 1e12
+                line["roofline"] = {
+                    "kernel": "k_gram_i8<2> (tcgen05.mma kind::i8 on CTA pairs, TMA operands, TMEM s32 accumulators) "
+                              "+ k_slice_i8 + k_gram_i8_final", "bound": "tensor",
+                    "achieved": achieved, "peak": i8_peak, "unit": "TFLOP/s", "frac": achieved / i8_peak,
+                    "traffic": traffic.get("k_gram_i8"), "ms_per_launch": g_ms,
+                    "algorithmic": f"split-integer FP64 emulation: {pairs} int8 slice pairs x 2 (Re, Im) x 2*2^n "
+                                   f"multiply-adds per entry x {entries_computed} entries computed ({tiles} "
+                                   f"lower-triangle 256x256 tiles); the duration is the whole b200sq_gram call "
+                                   f"(digit slicing, memset, tcgen05 kernel, |.|^2 kernel)",
+                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst): INT8 dense is 2x BF16 dense on "
+                                   "B200 (4.5 vs 2.25 POP/s nominal); no measured INT8 figure exists"
+                                   if "bf16_tflops" in peaks else "2 x fallback 1.59 PFLOP/s",
+                    "fp64_equivalent_tflops": fp64_equiv,
+                    "fp64_equivalent_note": f"8*2^n flop per entry of the N(N+1)/2 = {n_points * (n_points + 1) // 2} "
+                                            f"distinct entries; measured FP64 DGEMM peak here {fp64_peak:.1f} TFLOP/s",
+                    "frac_of_fp64_tensor_peak": fp64_equiv / fp64_peak,
+                    "share_of_step": g_ms / ms_per_step,
+                }
+            else:
+                mode_4m = os.environ.get("B200SQ_GRAM_MODE", "3m").lower() == "4m"
+                bm = 128 if mode_4m else 64
+                tiles_m = (n_points + bm - 1) // bm
+                # symmetric: only tiles touching the lower triangle run
+                tiles = sum(1 for bi in range(tiles_m) for bj in range((n_points + 63) // 64)
+                            if bj * 64 <= bi * bm + bm - 1)
+                entries_computed = tiles * bm * 64
+                flops = 8.0 * dim * entries_computed
+                achieved = flops / (g_ms * 1e-3) / 1e12
+                line["roofline"] = {
+                    "kernel": ("k_gram 4M" if mode_4m else "k_gram3m_ws (3M, warp-specialised)")
+                              + ", FP64 DMMA, fused |.|^2 epilogue", "bound": "tensor",
+                    "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                    "traffic": traffic.get("k_gram3m_ws"), "ms_per_launch": g_ms,
+                    "algorithmic": f"8*2^n flop per entry x {entries_computed} entries computed "
+                                   f"({tiles} lower-triangle {bm}x64 tiles of the symmetric Gram)",
+                    "executed_tflops": achieved * (1.0 if mode_4m else 0.75),
+                    "executed_note": "3M (Gauss) complex product issues 6*2^n tensor flops per entry; the DMMA "
+                                     "hardware ceiling measured with tools/dmma_probe.cu is 37.1 TFLOP/s",
+                    "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 3; "
+                                   "MEASURED_PEAKS.json carries no FP64 figure",
+                    "share_of_step": g_ms / ms_per_step,
+                }
             hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
             gt_ms = float(np.mean(gate_ms))
             state_bytes = 16.0 * n_points * dim
-            gate_bytes = state_bytes * (2 * n_passes - 1)  # first pass only writes
+            layouts = cprog.pass_layouts()
+            gate_bytes = sum(16.0 * n_points * ((2.0 ** qi if qi else 0.0) + 2.0 ** qo) for qi, qo in layouts)
             line["roofline_gate"] = {
-                "kernel": f"k_tile_pass x {n_passes} (fused gate application)", "bound": "hbm",
+                "kernel": f"k_tile_pass x {n_passes} (fused gate application, compact active-qubit layouts)",
+                "bound": "hbm",
                 "achieved": gate_bytes / (gt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": gate_bytes / (gt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "frac": gate_bytes / (gt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k_tile_pass"),
                 "ms_all_passes": gt_ms, "passes": n_passes,
-                "algorithmic": f"16*N*2^n bytes written by pass 1 + 2*16*N*2^n per later pass "
-                               f"= {gate_bytes / 1e9:.2f} GB for {6 * n} gates",
+                "algorithmic": "sum over passes of 16*N*(2^in + 2^out) bytes, (in, out) active qubits per pass = "
+                               f"{layouts}: {gate_bytes / 1e9:.2f} GB for {6 * n} gates (the final state is written "
+                               "once; qubits still |0> are never stored or read)",
+                "full_sweep_equivalent_gbs": state_bytes * (2 * n_passes - 1) / (gt_ms * 1e-3) / 1e9,
+                "full_sweep_equivalent_frac": state_bytes * (2 * n_passes - 1) / (gt_ms * 1e-3) / 1e9 / hbm_peak,
                 "unfused_equivalent_gbs": 2 * state_bytes * 6 * n / (gt_ms * 1e-3) / 1e9,
+                "note": "the last pass is FP64-pipe bound (ncu: profiles/), not HBM bound: it applies 16 one-qubit "
+                        "gates and 2 fused phase-table layers per amplitude",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
                 "share_of_step": gt_ms / ms_per_step,
             }

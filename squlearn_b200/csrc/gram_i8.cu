@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -58,7 +59,8 @@ struct I8Args {
     int kbytes;               // K' = 2 * dim bytes per row
     int n_chunks, chunk_bytes;
     int tiles_n, n_tiles, symmetric;
-    double* W;                // [n_tiles][2][128 cols][128 rows]
+    int mn;                   // edge of an output tile: 128 (one CTA) or 256 (CTA pair)
+    double* W;                // [n_tiles][2][mn cols][mn rows]
     I8Schedule sched;
 };
 
@@ -97,19 +99,62 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, N = 128, K = 32
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
+// Both CTAs of a pair run this; the transaction bytes land on the LEADER's barrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {  // arrive on CTA `cta` of the cluster
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, K = 32; CG = 1: M = N = 128 on one SM,
+// CG = 2: M = N = 256 on a CTA pair (each CTA holds 128 rows of A and 128 of the 256 rows of B).
+template <int CG>
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// Arrive on `bar` (same offset in every CTA of the pair) when all MMAs issued so far have completed.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                     : "memory");
+    else
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"((uint16_t)3)
+            : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -134,7 +179,9 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
 }
 // kind::i8: D = s32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9 = 1, 10-12 = 1), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t instr_desc(uint32_t mn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((mn >> 3) << 17) | ((mn >> 4) << 24);
+}
 
 __device__ __forceinline__ void decode_tile(const I8Args& A, int t, int& bm, int& bn) {
     if (A.symmetric) {
@@ -150,9 +197,13 @@ __device__ __forceinline__ void decode_tile(const I8Args& A, int t, int& bm, int
 
 // ---------------------------------------------------------------------------------------------
 
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
           const __grid_constant__ I8Args A) {
+    constexpr int MN = kTile * CG;            // edge of the output tile of a CTA (pair)
+    constexpr int ACC = CG == 1 ? 2 : 1;      // accumulator stages: 2 * MN columns each, 512 columns in total
+    constexpr uint32_t kIdesc = instr_desc(MN);
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -164,36 +215,45 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), CG);   // producer arrivals of every CTA of the pair (leader's barrier is used)
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+            mbar_init(tempty_bar(s), 4 * CG);  // one arrival per epilogue warp of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     const int n_units = A.n_tiles * A.n_chunks;
+    const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
     const I8Schedule& S = A.sched;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA loads its own 128 rows of A, Bnat, Brot) =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int u = worker; u < n_units; u += n_workers) {
                 const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
                 int bm, bn;
                 decode_tile(A, tile, bm, bn);
@@ -201,36 +261,44 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
                 for (int ci = 0; ci < S.n_classes; ++ci)
                     for (int p = 0; p < S.n_pairs[ci]; ++p) {
-                        const int row_a = (int)(S.pi[ci][p] * A.rows_a) + bm * kTile;
-                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b) + bn * kTile;
-                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b) + bn * kTile;
+                        const int row_a = (int)(S.pi[ci][p] * A.rows_a) + bm * MN + (int)cta_rank * kTile;
+                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b) + bn * MN + (int)cta_rank * kTile;
+                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b) + bn * MN + (int)cta_rank * kTile;
                         for (int k = k0; k < k1; k += kStageK) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t dst = smem_base + stage * kStageBytes;
-                            mbar_expect_tx(full_bar(stage), kStageBytes);
-                            tma_load_2d(dst, &mapA, full_bar(stage), k, row_a);
-                            tma_load_2d(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
-                            tma_load_2d(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                            if (CG == 1) {
+                                mbar_expect_tx(full_bar(stage), kStageBytes);
+                                tma_load_2d(dst, &mapA, full_bar(stage), k, row_a);
+                                tma_load_2d(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
+                                tma_load_2d(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                            } else {
+                                tma_load_2d_2sm(dst, &mapA, full_bar(stage), k, row_a);
+                                tma_load_2d_2sm(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
+                                tma_load_2d_2sm(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                                if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+                                else mbar_arrive_cta(full_bar(stage), 0);
+                            }
                             if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
                     }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && leader) {
             int stage = 0;
             uint32_t phase = 0;
             uint32_t acc_it = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int u = worker; u < n_units; u += n_workers) {
                 const int chunk = u / A.n_tiles;
                 const int k0 = chunk * A.chunk_bytes;
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
                 for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
-                    const uint32_t acc = acc_it & 1u, acc_phase = (acc_it >> 1) & 1u;
+                    const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
-                    const uint32_t d_re = tmem_base + acc * 256u, d_im = d_re + 128u;
+                    const uint32_t d_re = tmem_base + acc * (2u * MN), d_im = d_re + MN;
                     uint32_t accumulate = 0;
                     for (int p = 0; p < S.n_pairs[ci]; ++p)
                         for (int k = k0; k < k1; k += kStageK) {
@@ -243,54 +311,60 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 #pragma unroll
                             for (int kk = 0; kk < kStageK / 32; ++kk) {
                                 // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                                umma_i8(d_re, da + 2u * kk, dbn + 2u * kk, kInstrDesc, accumulate | (uint32_t)kk);
-                                umma_i8(d_im, da + 2u * kk, dbr + 2u * kk, kInstrDesc, accumulate | (uint32_t)kk);
+                                umma_i8<CG>(d_re, da + 2u * kk, dbn + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
+                                umma_i8<CG>(d_im, da + 2u * kk, dbr + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
                             }
                             accumulate = 1;
-                            umma_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+                            umma_commit<CG>(empty_bar(stage));  // frees the stage when these MMAs have read it
                             if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
-                    umma_commit(tfull_bar(acc));  // accumulator of this class complete
+                    umma_commit<CG>(tfull_bar(acc));  // accumulator of this class complete
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> FP64 accumulators in global memory =====
+        // ===== epilogue: TMEM -> FP64 accumulators in global memory (every CTA drains its 128 rows) =====
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
+        const int row = (int)cta_rank * kTile + q * 32 + lane;
         uint32_t acc_it = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int u = worker; u < n_units; u += n_workers) {
             const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
-            double* wt = A.W + (size_t)tile * (2 * kTile * kTile) + row;
+            double* wt = A.W + (size_t)tile * (2 * MN * MN) + row;
             for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
-                const uint32_t acc = acc_it & 1u, acc_phase = (acc_it >> 1) & 1u;
+                const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                 const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2u * MN);
 #pragma unroll 1
-                for (int cb = 0; cb < 8; ++cb) {  // 8 blocks of 32 columns: Re 0..127, Im 128..255
+                for (int cb = 0; cb < 2 * MN / 32; ++cb) {  // blocks of 32 columns: Re [0, MN), Im [MN, 2 MN)
                     uint32_t v[32];
                     tmem_ld32(t0 + cb * 32, v);
                     tmem_ld_wait();
-                    double* wp = wt + (size_t)(cb * 32) * kTile;  // [part][col][row], part = cb >> 2
+                    double* wp = wt + (size_t)(cb * 32) * MN;  // [part][col][row]
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int iv = (int)v[c];
-                        if (iv != 0) red_add_f64(wp + (size_t)c * kTile, (double)iv * w);
+                        if (iv != 0) red_add_f64(wp + (size_t)c * MN, (double)iv * w);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (lane == 0) {
+                    if (CG == 1) mbar_arrive(tempty_bar(acc));
+                    else mbar_arrive_cta(tempty_bar(acc), 0);
+                }
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -366,21 +440,24 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
     __shared__ double sm[32][33];
     int bm, bn;
     decode_tile(A, blockIdx.x, bm, bn);
-    const double* wt = W + (size_t)blockIdx.x * (2 * kTile * kTile);
+    const int MN = A.mn, nsb = MN / 32;
+    const double* wt = W + (size_t)blockIdx.x * (2 * (size_t)MN * MN);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
-    for (int sb = 0; sb < 16; ++sb) {
-        const int sr = sb >> 2, sc = sb & 3;
+    const bool diag_tile = sym && bm == bn;
+    for (int sb = 0; sb < nsb * nsb; ++sb) {
+        const int sr = sb / nsb, sc = sb - sr * nsb;
+        if ((int64_t)bm * MN + sr * 32 >= nx || (int64_t)bn * MN + sc * 32 >= ny) continue;  // CTA-uniform
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
             const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
-            const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+            const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
             double k = 0.0;
             if (i < nx && j < ny) {
                 // diagonal tiles of a symmetric Gram: take both triangles from the lower one, so that K is
                 // bit-exactly symmetric whatever order the atomic FP64 accumulation happened in
-                const int r2 = (sym && bm == bn && col > row) ? col : row, c2 = (sym && bm == bn && col > row) ? row : col;
-                const double re = wt[(size_t)c2 * kTile + r2], im = wt[(size_t)(kTile + c2) * kTile + r2];
+                const int r2 = (diag_tile && col > row) ? col : row, c2 = (diag_tile && col > row) ? row : col;
+                const double re = wt[(size_t)c2 * MN + r2], im = wt[(size_t)(MN + c2) * MN + r2];
                 k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j] - 12));
                 if (sym && i == j) {
                     if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
@@ -394,12 +471,12 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
         for (int qd = 0; qd < 4; ++qd) {
             {   // direct: K[i][j], consecutive threads -> consecutive j
                 const int row = sr * 32 + ty + 8 * qd, col = sc * 32 + tx;
-                const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
                 if (i < nx && j < ny) K[i * ldk + j] = sm[tx][ty + 8 * qd];
             }
             if (sym && bm != bn) {  // mirror: K[j][i], consecutive threads -> consecutive i
                 const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
-                const int64_t i = (int64_t)bm * kTile + row, j = (int64_t)bn * kTile + col;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
                 if (i < nx && j < ny) K[j * ldk + i] = sm[ty + 8 * qd][tx];
             }
         }
@@ -471,10 +548,22 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     a.kbytes = (int)kbytes;
     a.chunk_bytes = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
     a.n_chunks = (int)((kbytes + a.chunk_bytes - 1) / a.chunk_bytes);
-    const int tiles_m = (int)((nx + kTile - 1) / kTile);
-    a.tiles_n = (int)((ny + kTile - 1) / kTile);
+    // CTA pairs (256 x 256 tiles, cta_group::2) halve the L2 -> SMEM operand traffic per MMA; small
+    // problems keep single-CTA 128 x 128 tiles so that the machine still fills
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int force_cg = getenv("B200SQ_I8_CG") ? atoi(getenv("B200SQ_I8_CG")) : 0;
+    auto count_tiles = [&](int mn) {
+        const int64_t tm = (nx + mn - 1) / mn, tn = (ny + mn - 1) / mn;
+        return sym ? tm * (tm + 1) / 2 : tm * tn;
+    };
+    const int cg = force_cg ? force_cg : (count_tiles(256) * a.n_chunks >= sms / 2 ? 2 : 1);
+    a.mn = kTile * cg;
+    const int tiles_m = (int)((nx + a.mn - 1) / a.mn);
+    a.tiles_n = (int)((ny + a.mn - 1) / a.mn);
     a.symmetric = sym ? 1 : 0;
-    a.n_tiles = sym ? tiles_m * (tiles_m + 1) / 2 : tiles_m * a.tiles_n;
+    a.n_tiles = (int)count_tiles(a.mn);
     // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
     {
         I8Schedule& s = a.sched;
@@ -495,7 +584,7 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
         }
         s.n_classes = nc;
     }
-    const size_t wbytes = (size_t)a.n_tiles * 2 * kTile * kTile * sizeof(double);
+    const size_t wbytes = (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
     if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
     a.W = W;
     cudaMemsetAsync(W, 0, wbytes, stream);
@@ -504,17 +593,33 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     if (!rc) rc = encode_planes(&mapB, py, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * ny);
     if (rc) { cleanup(); return rc; }
     const int smem = kStages * kStageBytes + 1024 + 256;
-    if ((e = cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) {
-        cleanup();
-        return (int)e;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_units = a.n_tiles * a.n_chunks;
-    const int grid = n_units < sms ? n_units : sms;
-    k_gram_i8<<<grid, kThreads, smem, stream>>>(mapA, mapB, a);
-    count_launch();
+    {
+        auto kern = cg == 2 ? k_gram_i8<2> : k_gram_i8<1>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) {
+            cleanup();
+            return (int)e;
+        }
+        const int workers = n_units < sms / cg ? n_units : sms / cg;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(workers * cg));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cg;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if ((e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, a)) != cudaSuccess) {
+            cleanup();
+            return (int)e;
+        }
+        count_launch();
+    }
     k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, ex, ey, k, ldk, nx, ny, a, flags);
     count_launch();
     e = cudaGetLastError();

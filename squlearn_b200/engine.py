@@ -47,6 +47,18 @@ class CompiledProgram:
         _lib.check(self._lib.b200sq_program_set_coeffs(self._handle, a0, a1))
         self.params = None if params is None else np.array(params, dtype=np.float64)
 
+    def pass_layouts(self):
+        """[(in_qubits, out_qubits)] per pass: the active-qubit counts of the layout each pass reads and
+        writes (a pass moves 16 * (2^in + 2^out) bytes per state; in = 0 means nothing is read)."""
+        w = self.dump()
+        n_pass = int(w[2])
+        pos, out = 5, []
+        for _ in range(n_pass):
+            T, a_in, a_out = int(w[pos]), int(w[pos + 1]) & 0xffffffff, int(w[pos + 2]) & 0xffffffff
+            out.append((bin(a_in).count("1"), bin(a_out).count("1")))
+            pos += 11 + T
+        return out
+
     def dump(self) -> np.ndarray:
         n = ctypes.c_int(0)
         _lib.check(self._lib.b200sq_program_dump(self._handle, None, 0, ctypes.byref(n)))
@@ -202,8 +214,9 @@ class Engine:
              precision: Optional[str] = None):
         """K[i, j] = |<psi_x[i]|psi_y[j]>|^2.  ``psi_y=None`` means the symmetric Gram of psi_x;
         ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy.
-        ``precision``: "fp64" (FP64 DMMA) or "int8" (split-integer FP64 emulation on the INT8 tcgen05
-        tensor cores, |dK| ~ 1e-12; used when 2^n >= 64); default from B200SQ_GRAM_PRECISION, else "fp64"."""
+        ``precision``: "fp64" (FP64 DMMA), "int8" (split-integer FP64 emulation on the INT8 tcgen05 tensor
+        cores, |dK| ~ 1e-12, north-star bound 1e-10) or "auto" (int8 where it is faster: 2^n >= 4096 and at
+        least 1024 x 512 entries); default from B200SQ_GRAM_PRECISION, else "auto"."""
         torch = self._torch
         psi_x = psi_x.contiguous()
         sym = psi_y is None
@@ -220,11 +233,7 @@ class Engine:
             flags |= _lib.GRAM_3M
             if os.environ.get("B200SQ_GRAM_MODE", "").lower() == "3m-classic" or three_m == "classic":
                 flags |= _lib.GRAM_CLASSIC
-        if precision is None:
-            precision = os.environ.get("B200SQ_GRAM_PRECISION", "fp64").lower()
-        if precision not in ("fp64", "int8"):
-            raise ValueError("precision must be 'fp64' or 'int8'")
-        if precision == "int8":
+        if self.gram_precision(nx, ny, dim, precision) == "int8":
             flags |= _lib.GRAM_INT8
         with torch.cuda.device(self.device):
             if out is None:
@@ -232,6 +241,19 @@ class Engine:
             _lib.check(self._lib.b200sq_gram(psi_x.data_ptr(), nx, psi_y.data_ptr(), ny, dim,
                                              out.data_ptr(), out.stride(0), flags, self._stream()))
         return out
+
+    @staticmethod
+    def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:
+        """Resolve the Gram arithmetic: "fp64" (DMMA) or "int8" (split-integer tcgen05 path)."""
+        if precision is None:
+            precision = os.environ.get("B200SQ_GRAM_PRECISION", "auto").lower()
+        if precision not in ("fp64", "int8", "auto"):
+            raise ValueError("precision must be 'fp64', 'int8' or 'auto'")
+        if precision == "auto":
+            precision = "int8" if dim >= 4096 and nx * ny >= 1024 * 512 else "fp64"
+        if precision == "int8" and (dim < 64 or dim % 8):
+            precision = "fp64"
+        return precision
 
     def rbf(self, fx, fy, gamma: float):
         torch = self._torch

@@ -162,6 +162,94 @@ def test_gram_symmetric_and_diagonal_policies(executor, n, dim, three_m):
     assert np.array_equal(k_one[off], k_zero[off]) and np.array_equal(k_one[off], k_cmp[off])
 
 
+# ---- split-integer Gram on the INT8 tcgen05 tensor cores (B200SQ_GRAM_INT8): north-star bound 1e-10
+INT8_TOL = 1e-10
+
+
+@pytest.mark.parametrize("nx,ny,dim", [(1, 1, 64), (5, 3, 64), (37, 130, 128), (129, 65, 1024),
+                                        (200, 260, 72), (64, 257, 4096), (700, 520, 16384)])
+def test_gram_int8_rectangular(executor, nx, ny, dim):
+    import torch
+
+    rng = np.random.default_rng(nx * 11 + ny)
+    a = rng.normal(size=(nx, dim)) + 1j * rng.normal(size=(nx, dim))
+    b = rng.normal(size=(ny, dim)) + 1j * rng.normal(size=(ny, dim))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    got = executor.engine.gram(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), precision="int8").cpu().numpy()
+    want = oracle.fidelity_gram_zgemm(a, b, False)
+    assert got.shape == (nx, ny)
+    assert np.max(np.abs(got - want)) < INT8_TOL
+
+
+@pytest.mark.parametrize("n,dim", [(1, 64), (63, 128), (128, 256), (300, 512), (513, 64), (1100, 2048)])
+def test_gram_int8_symmetric_and_diagonal_policies(executor, n, dim):
+    import torch
+
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=(n, dim)) + 1j * rng.normal(size=(n, dim))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    t = torch.from_numpy(a).cuda()
+    eng = executor.engine
+    k_one = eng.gram(t, None, diagonal="one", precision="int8").cpu().numpy()
+    k_zero = eng.gram(t, None, diagonal="zero", precision="int8").cpu().numpy()
+    k_cmp = eng.gram(t, None, diagonal="computed", precision="int8").cpu().numpy()
+    want = oracle.fidelity_gram_zgemm(a, a, True, "off_diagonal")
+    assert np.max(np.abs(k_one - want)) < INT8_TOL
+    assert np.array_equal(k_one, k_one.T)                 # exactly symmetric (mirrored)
+    assert np.all(np.diag(k_one) == 1.0)
+    assert np.all(np.diag(k_zero) == 0.0)
+    assert np.max(np.abs(np.diag(k_cmp) - 1.0)) < INT8_TOL
+    if n > 1:
+        off = ~np.eye(n, dtype=bool)
+        assert np.max(np.abs(k_one[off] - k_cmp[off])) < INT8_TOL
+
+
+def test_gram_int8_adversarial_states(executor):
+    """Rows with very different scales: basis states (one amplitude of modulus 1), exact duplicates,
+    near-duplicates, a uniform superposition and states with a few large and many tiny amplitudes."""
+    import torch
+
+    dim = 4096
+    rng = np.random.default_rng(7)
+    rows = []
+    e0 = np.zeros(dim, complex); e0[5] = 1.0
+    e1 = np.zeros(dim, complex); e1[77] = 1j
+    rows += [e0, e1, np.full(dim, 1 / np.sqrt(dim), complex)]
+    g = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+    g /= np.linalg.norm(g)
+    rows += [g, g.copy(), g * np.exp(0.3j)]
+    near = g + 1e-7 * (rng.normal(size=dim) + 1j * rng.normal(size=dim))
+    rows.append(near / np.linalg.norm(near))
+    spiky = 1e-6 * (rng.normal(size=dim) + 1j * rng.normal(size=dim))
+    spiky[:3] = [0.6, 0.5j, -0.62]
+    rows.append(spiky / np.linalg.norm(spiky))
+    for _ in range(140):
+        v = rng.normal(size=dim) * np.exp(rng.uniform(-6, 0, dim)) + 1j * rng.normal(size=dim)
+        rows.append(v / np.linalg.norm(v))
+    a = np.array(rows)
+    got = executor.engine.gram(torch.from_numpy(a).cuda(), None, diagonal="computed", precision="int8").cpu().numpy()
+    want = oracle.fidelity_gram_zgemm(a, a, True, "all")
+    np.fill_diagonal(want, np.abs(np.einsum("ij,ij->i", a.conj(), a)) ** 2)
+    assert np.max(np.abs(got - want)) < INT8_TOL
+    assert abs(got[3, 4] - 1.0) < INT8_TOL and abs(got[3, 5] - 1.0) < INT8_TOL
+
+
+def test_gram_int8_matches_fp64_on_circuit_states(sq, executor):
+    import torch
+
+    n, d, N = 13, 4, 700
+    X = np.random.default_rng(5).uniform(-0.95, 0.95, (N, d))
+    enc = sq.ChebyshevPQC(n, 2)
+    p = enc.generate_initial_parameters(d, seed=0)
+    psi = _states(sq, executor, enc.get_program(d), p, X)
+    t = torch.from_numpy(psi).cuda()
+    k64 = executor.engine.gram(t, None, precision="fp64")
+    k8 = executor.engine.gram(t, None, precision="int8")
+    assert float((k64 - k8).abs().max()) < 2e-11
+    assert torch.equal(k8, k8.T)
+
+
 # ------------------------------------------------------------------------------ expectation values
 def test_expvals_fused_and_from_memory(sq, executor):
     rng = np.random.default_rng(11)
@@ -319,8 +407,10 @@ def test_config_c3_full_size_properties(sq, executor):
     assert torch.equal(k, k.T)                                      # exact symmetry
     assert float(k.min()) >= 0.0 and float(k.max()) <= 1.0 + 1e-12
     # rectangular kernel of a slice equals the corresponding block of the symmetric one
-    blk = executor.engine.gram(psi[1000:1130], psi[37:300])
-    assert float((blk - k[1000:1130, 37:300]).abs().max()) < 1e-13
+    blk = executor.engine.gram(psi[1000:1130], psi[37:300], precision="fp64")
+    assert float((blk - k[1000:1130, 37:300]).abs().max()) < 2e-11  # the full Gram runs on the INT8 path
+    k64 = executor.engine.gram(psi, None, precision="fp64")
+    assert float((k64 - k).abs().max()) < 2e-11
     # oracle on a 24-point subset
     sub = rng.choice(N, 24, replace=False)
     p = oracle.chebyshev_pqc_initial_parameters(n, 2, d, seed=0)
