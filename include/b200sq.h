@@ -21,8 +21,10 @@
 #ifndef B200SQ_PUBLIC_API_H_
 #define B200SQ_PUBLIC_API_H_
 
+#if !defined(__CUDACC_RTC__) /* NVRTC (run-time specialised kernels) brings its own fixed-width types */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -89,6 +91,8 @@ typedef struct b200sq_program b200sq_program;
                                    /* cores (47-bit fixed point per state row; |dK| ~ 1e-12, see  */
                                    /* DESIGN.md); needs dim >= 64, otherwise the FP64 path runs   */
 
+#if !defined(__CUDACC_RTC__) /* host entry points: invisible to the run-time compiled device code */
+
 B200SQ_API const char* b200sq_last_error(void);
 B200SQ_API int b200sq_abi_version(void);
 
@@ -111,6 +115,11 @@ B200SQ_API int b200sq_program_set_coeffs(b200sq_program* prog, const double* c0,
  * and a dump of the plan as int32 words (see csrc/plan.hpp for the layout). */
 B200SQ_API int b200sq_program_num_passes(const b200sq_program* prog);
 B200SQ_API int b200sq_program_dump(const b200sq_program* prog, int32_t* buf, int capacity, int* n_written);
+
+/* Large batches run pass kernels that are specialised for the program at run time (NVRTC, see
+ * csrc/jit.cu; environment B200SQ_JIT=0 disables it).  This entry point only compiles the kernel of one
+ * pass (no GPU needed) and returns the cubin size, or a negative number with the compiler log in `log`. */
+B200SQ_API long b200sq_program_jit_compile(const b200sq_program* prog, int pass, char* log, int log_capacity);
 
 /* Apply the program to N data points: psi[v][i][:] = U(x_i; shift_v)|0...0>.
  * Replaces Executor.pennylane_execute(circuit returning qml.state(), ...) /
@@ -161,6 +170,8 @@ B200SQ_API int b200sq_rbf(const double* fx_dev, int64_t Nx, const double* fy_dev
  * `gpu_launches`), and the duration bookkeeping of the last Gram / gate-pass launches is left to
  * the caller's CUDA events. */
 B200SQ_API int64_t b200sq_launch_count(void);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,7 @@ class Gate(ctypes.Structure):
 EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
-    "b200sq_program_dump", "b200sq_simulate", "b200sq_simulate_expvals", "b200sq_expvals",
+    "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_expvals", "b200sq_expvals",
     "b200sq_gram", "b200sq_rbf", "b200sq_launch_count",
 ]
 
@@ -90,6 +90,8 @@ def load():
     lib.b200sq_program_num_passes.argtypes = [vp]
     lib.b200sq_program_dump.restype = c.c_int
     lib.b200sq_program_dump.argtypes = [vp, c.POINTER(i32), c.c_int, c.POINTER(c.c_int)]
+    lib.b200sq_program_jit_compile.restype = c.c_long
+    lib.b200sq_program_jit_compile.argtypes = [vp, c.c_int, c.c_char_p, c.c_int]
     lib.b200sq_simulate.restype = c.c_int
     lib.b200sq_simulate.argtypes = [vp, i64, c.c_int, vp, vp, c.c_int, c.POINTER(i32),
                                     c.POINTER(dbl), vp, vp]

@@ -12,13 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sq.so")
-SOURCES = ["api.cu", "sim_kernels.cu", "gram_kernels.cu", "gram_i8.cu"]
-HEADERS = ["plan.hpp", "tile_exec.cuh", "kernels.h", os.path.join(ROOT, "include", "b200sq.h")]
+SOURCES = ["api.cu", "sim_kernels.cu", "gram_kernels.cu", "gram_i8.cu", "jit.cu"]
+HEADERS = ["plan.hpp", "plan_dev.h", "tile_exec.cuh", "tile_kernel.cuh", "kernels.h", os.path.join(ROOT, "include", "b200sq.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "-ldl",
 ]
 
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -41,6 +42,8 @@ struct b200sq_program {
     std::vector<std::vector<uint8_t>> blobs;  // one device blob per pass (plan.hpp: build_pass_blob)
     unsigned char* d_blobs = nullptr;
     std::vector<size_t> blob_off;
+    std::vector<const void*> jit_kernels;  // per pass: run-time specialised kernel (jit.cu), or nullptr
+    std::vector<char> jit_tried;
     int32_t* d_var_gate = nullptr;
     double* d_var_shift = nullptr;
     int var_cap = 0;
@@ -210,7 +213,26 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.out = out;
         tile_pass_geometry(P, &a);
         a.total_items = n_states << P.n_obits;
-        int e = launch_tile_pass(a, stream);
+        // Large batches run a kernel specialised for this pass at run time (compiled once per program);
+        // B200SQ_JIT = 0 / 1 forces it off / on.
+        const void* jit = nullptr;
+        {
+            static const char* mode = getenv("B200SQ_JIT");
+            const bool big = ((int64_t)n_states << P.out_bits) >= ((int64_t)1 << 25);
+            const bool want = (!mode || mode[0] == 'a') ? big : (mode[0] != '0');
+            if (want) {
+                if (p->jit_tried.size() != pl.passes.size()) {
+                    p->jit_tried.assign(pl.passes.size(), 0);
+                    p->jit_kernels.assign(pl.passes.size(), nullptr);
+                }
+                if (!p->jit_tried[ip]) {
+                    p->jit_kernels[ip] = jit_pass_kernel(pl, (int)ip, a.team_size);
+                    p->jit_tried[ip] = 1;
+                }
+                jit = p->jit_kernels[ip];
+            }
+        }
+        int e = launch_tile_pass(a, stream, jit);
         if (e) { rc = cuda_fail(e, "tile pass launch"); break; }
         src = a.dst;
         src_vstride = a.dst_vstride;
@@ -272,6 +294,22 @@ int b200sq_program_set_coeffs(b200sq_program* prog, const double* c0, const doub
     }
     prog->gates_dirty = true;
     return 0;
+}
+
+// Compile the run-time specialised kernel of pass `pass` with NVRTC without loading it (needs no GPU):
+// returns the cubin size in bytes, or a negative number on failure; the compiler log goes to `log`.
+long b200sq_program_jit_compile(const b200sq_program* prog, int pass, char* log, int log_capacity) {
+    if (!prog || pass < 0 || pass >= (int)prog->plan.passes.size()) return -2;
+    TileArgs a;
+    std::memset(&a, 0, sizeof(a));
+    tile_pass_geometry(*reinterpret_cast<const DPass*>(prog->blobs[pass].data()), &a);
+    std::string lg;
+    const long r = jit_compile_only(prog->plan, pass, a.team_size, &lg);
+    if (log && log_capacity > 0) {
+        std::strncpy(log, lg.c_str(), (size_t)log_capacity - 1);
+        log[log_capacity - 1] = 0;
+    }
+    return r;
 }
 
 int b200sq_program_num_passes(const b200sq_program* prog) {

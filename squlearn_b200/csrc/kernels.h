@@ -4,39 +4,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "plan.hpp"
+#include "tile_kernel.cuh"
 
 namespace b200sq {
 
-struct TileArgs {
-    const unsigned char* blob;   // device copy of the pass blob (plan.hpp: build_pass_blob)
-    int32_t blob_bytes;
-    const b200sq_gate* gates;    // device gate table (angle coefficients)
-    // state (v, i) of the input / output layout lives at base + ((v * vstride + i - off) << layout bits)
-    const double2* src;
-    double2* dst;
-    int64_t src_vstride, src_off, dst_vstride, dst_off;
-    const double* x;           // [n_total][d]
-    const double* table;       // [slots][n_total]
-    int64_t n_total;           // samples in the whole call (row stride of table, variant stride of out)
-    int64_t sample0;           // first sample of this launch
-    int64_t n_samples;         // samples in this launch
-    int32_t n, d;
-    int32_t n_variants;        // variants in this launch
-    int32_t variant0;          // first variant of this launch
-    const int32_t* var_gate;   // device, indexed by absolute variant; nullptr = unshifted
-    const double* var_shift;
-    int32_t store;             // write the tile to dst
-    int32_t n_terms;           // > 0: reduce the tile to expectation values (requires T == n)
-    const uint32_t* xmask;     // device
-    const uint32_t* zmask;
-    double* out;               // [n_variants_total][n_total][n_terms]
-    int32_t team_size, log2ts, teams_per_cta, team_elems;
-    int64_t total_items;
-};
+// Returns cudaError_t as int.  `jit_kernel`: a run-time specialised kernel of this pass (jit.cu) or nullptr
+// for the generic interpreting kernel.
+int launch_tile_pass(const TileArgs& args, cudaStream_t stream, const void* jit_kernel = nullptr);
 
-// Returns cudaError_t as int.
-int launch_tile_pass(const TileArgs& args, cudaStream_t stream);
+// Run-time specialisation (jit.cu)
+const void* jit_pass_kernel(const Plan& plan, int pass, int team_size);
+std::string jit_pass_source(const Plan& plan, int pass, int team_size);
+long jit_compile_only(const Plan& plan, int pass, int team_size, std::string* log_out);
 void tile_pass_geometry(const DPass& pass, TileArgs* args);
 
 int launch_expvals(const double2* psi, int64_t n_states, int n_qubits, int n_terms,

@@ -4,11 +4,13 @@
 // separated by team barriers that live in the callers.
 #pragma once
 
+#if !defined(__CUDACC_RTC__)
 #include <math.h>
 #include <stdint.h>
 #include <vector_types.h>
+#endif
 
-#include "plan.hpp"
+#include "plan_dev.h"
 
 #if defined(__CUDACC__)
 #define B200SQ_HD __host__ __device__ __forceinline__
@@ -510,14 +512,12 @@ B200SQ_HD void apply_step(double2 (&a)[G][1 << NB], const DStep& u, const double
 // One thread's share of a round: groups g = tid, tid + nthreads, ... taken G at a time.
 // SMEM address of register slot k of group g:  sw(base | ko[k]) = (base ^ ((base >> 3) & 7)) ^ ksw[k]
 // because base and ko[k] have disjoint bits (ksw[k] is precomputed on the host, see build_pass_blob).
-// The round record is copied to registers first: the tile stores below would otherwise force the
-// compiler to reload it (same address space).
-template <int NB, int G>
-B200SQ_HD void exec_round_nb(double2* __restrict__ tile, const DRound* __restrict__ rdp,
-                             const DStep* __restrict__ steps, const double2* __restrict__ mats,
-                             uint32_t ext_base, int T, int tid, int nthreads) {
+// `steps(a, e, base, ko)` applies the round's steps to the register amplitudes: the interpreter loop
+// of exec_round_nb, or the straight-line sequence a run-time specialised kernel (jit.cu) passes in.
+template <int NB, int G, class Steps>
+B200SQ_HD void exec_round_with(double2* __restrict__ tile, const DRound& rd, uint32_t ext_base, int T, int tid,
+                               int nthreads, Steps steps) {
     constexpr int NK = 1 << NB;
-    const DRound rd = *rdp;
     const int ngroups = 1 << (T - NB);
     uint32_t ko[NK], ksw[NK];
 #pragma unroll
@@ -529,7 +529,6 @@ B200SQ_HD void exec_round_nb(double2* __restrict__ tile, const DRound* __restric
         ko[k] = o;
         ksw[k] = rd.ksw[k];
     }
-    const int s0 = rd.s0, s1 = rd.s1;
     for (int g0 = tid; g0 < ngroups; g0 += G * nthreads) {
         uint32_t base[G], e[G], bsw[G];
         double2 a[G][NK];
@@ -548,15 +547,30 @@ B200SQ_HD void exec_round_nb(double2* __restrict__ tile, const DRound* __restric
 #pragma unroll
             for (int k = 0; k < NK; ++k) a[gi][k] = tile[bsw[gi] ^ ksw[k]];
         }
-        for (int si = s0; si < s1; ++si) {
-            const DStep u = steps[si];
-            apply_step<NB, G>(a, u, mats + u.mat, e, base, ko);
-        }
+        steps(a, e, base, ko);
 #pragma unroll
         for (int gi = 0; gi < G; ++gi)
 #pragma unroll
             for (int k = 0; k < NK; ++k) tile[bsw[gi] ^ ksw[k]] = a[gi][k];
     }
+}
+
+// Interpreted round.  The round record is copied to registers first: the tile stores would otherwise
+// force the compiler to reload it (same address space).
+template <int NB, int G>
+B200SQ_HD void exec_round_nb(double2* __restrict__ tile, const DRound* __restrict__ rdp,
+                             const DStep* __restrict__ steps, const double2* __restrict__ mats,
+                             uint32_t ext_base, int T, int tid, int nthreads) {
+    const DRound rd = *rdp;
+    const int s0 = rd.s0, s1 = rd.s1;
+    exec_round_with<NB, G>(tile, rd, ext_base, T, tid, nthreads,
+                           [&](double2 (&a)[G][1 << NB], const uint32_t (&e)[G], const uint32_t (&base)[G],
+                               const uint32_t (&ko)[1 << NB]) {
+                               for (int si = s0; si < s1; ++si) {
+                                   const DStep u = steps[si];
+                                   apply_step<NB, G>(a, u, mats + u.mat, e, base, ko);
+                               }
+                           });
 }
 
 B200SQ_HD void exec_round_thread(double2* tile, const DRound* rd, const DStep* steps,

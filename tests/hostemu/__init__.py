@@ -12,6 +12,7 @@ SO = os.path.join(HERE, "libb200sq_hostemu.so")
 SRC = os.path.join(HERE, "hostemu.cpp")
 DEPS = [SRC, os.path.join(ROOT, "squlearn_b200", "csrc", "plan.hpp"),
         os.path.join(ROOT, "squlearn_b200", "csrc", "tile_exec.cuh"),
+        os.path.join(ROOT, "squlearn_b200", "csrc", "plan_dev.h"),
         os.path.join(ROOT, "include", "b200sq.h")]
 
 

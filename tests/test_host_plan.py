@@ -211,3 +211,25 @@ def test_config_circuit_pass_counts():
         passes = lib.b200sq_program_num_passes(h)
         lib.b200sq_program_destroy(h)
         assert 1 <= passes <= expect_max, (n, passes)
+
+
+def test_runtime_specialised_pass_kernels_compile():
+    """The straight-line pass kernels jit.cu generates for the config circuits are valid sm_100a CUDA
+    (NVRTC compiles to a cubin without a GPU)."""
+    import ctypes
+    from squlearn_b200 import _lib
+    lib = _lib.load()
+    for enc, d in ((ChebyshevPQC(13, 2), 4), (HubregtsenEncodingCircuit(10, 1), 10), (ChebyshevRx(8, 4), 2)):
+        prog = enc.get_program(d)
+        p = enc.generate_initial_parameters(d, seed=0)
+        h = ctypes.c_void_p()
+        _lib.check(lib.b200sq_program_create(prog.num_qubits, len(prog), prog.c_gates(p), 0, ctypes.byref(h)))
+        try:
+            for ip in range(lib.b200sq_program_num_passes(h)):
+                log = ctypes.create_string_buffer(4000)
+                size = lib.b200sq_program_jit_compile(h, ip, log, 4000)
+                if size == -1 and b"libnvrtc" in log.value:
+                    pytest.skip("NVRTC not available")
+                assert size > 0, log.value.decode()
+        finally:
+            lib.b200sq_program_destroy(h)
