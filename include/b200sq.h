@@ -160,6 +160,20 @@ B200SQ_API int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int 
 B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
                 double* K_dev, int64_t ldk, uint32_t flags, void* stream);
 
+/* The two halves of the B200SQ_GRAM_INT8 path, for callers that reuse or exchange the digit planes (the
+ * multi-GPU Gram sends planes, not complex128 states: 12 instead of 16 bytes per amplitude, sliced once).
+ *   planes  [12][plane_rows][2 * dim] int8: planes 0..5 = digits of (re, im), 6..11 = digits of (im, -re)
+ *   expo    [plane_rows] int32: power-of-two scale of every row
+ * b200sq_gram_slice writes rows [row0, row0 + N) of the planes from N states; b200sq_gram_from_planes
+ * computes K[i][j] = |<x_{x0+i} | y_{y0+j}>|^2 for Nx x Ny rows of the two plane sets (flags as b200sq_gram). */
+B200SQ_API size_t b200sq_gram_planes_bytes(int64_t plane_rows, int64_t dim);
+B200SQ_API int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
+                                 int64_t row0, int32_t* expo_dev, void* stream);
+B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
+                                       int64_t x0, int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev,
+                                       int64_t plane_rows_y, int64_t y0, int64_t Ny, int64_t dim, double* K_dev,
+                                       int64_t ldk, uint32_t flags, void* stream);
+
 /* Gaussian outer kernel of the projected quantum kernel: K[i][j] = exp(-gamma |F_x[i]-F_y[j]|^2)
  * (src/squlearn/kernel/lowlevel_kernel/projected_quantum_kernel.py:945-973).
  *   fx_dev [Nx][nf], fy_dev [Ny][nf] float64; K_dev [Nx][ldk] float64                          */

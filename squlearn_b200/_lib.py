@@ -56,7 +56,8 @@ EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_expvals", "b200sq_expvals",
-    "b200sq_gram", "b200sq_rbf", "b200sq_launch_count",
+    "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_rbf",
+    "b200sq_launch_count",
 ]
 
 _lib = None
@@ -104,6 +105,12 @@ def load():
                                    c.POINTER(c.c_uint32), vp, vp]
     lib.b200sq_gram.restype = c.c_int
     lib.b200sq_gram.argtypes = [vp, i64, vp, i64, i64, vp, i64, c.c_uint32, vp]
+    lib.b200sq_gram_planes_bytes.restype = c.c_size_t
+    lib.b200sq_gram_planes_bytes.argtypes = [i64, i64]
+    lib.b200sq_gram_slice.restype = c.c_int
+    lib.b200sq_gram_slice.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp]
+    lib.b200sq_gram_from_planes.restype = c.c_int
+    lib.b200sq_gram_from_planes.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, i64, vp, i64, c.c_uint32, vp]
     lib.b200sq_rbf.restype = c.c_int
     lib.b200sq_rbf.argtypes = [vp, i64, vp, i64, c.c_int, dbl, vp, i64, vp]
     if lib.b200sq_abi_version() != 1:

@@ -428,6 +428,38 @@ int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_
     return 0;
 }
 
+size_t b200sq_gram_planes_bytes(int64_t plane_rows, int64_t dim) {
+    return plane_rows > 0 && dim > 0 ? (size_t)12 * (size_t)plane_rows * (size_t)(2 * dim) : 0;
+}
+
+int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
+                      int64_t row0, int32_t* expo_dev, void* stream_) {
+    if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
+    if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
+    if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
+    int e = launch_slice_i8((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
+                            (cudaStream_t)stream_);
+    if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
+int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x, int64_t x0,
+                            int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev, int64_t plane_rows_y,
+                            int64_t y0, int64_t Ny, int64_t dim, double* K_dev, int64_t ldk, uint32_t flags,
+                            void* stream_) {
+    if (!planes_x_dev || !planes_y_dev || !expo_x_dev || !expo_y_dev || !K_dev) return fail(2, "NULL argument");
+    if (Nx < 0 || Ny < 0 || x0 < 0 || y0 < 0 || x0 + Nx > plane_rows_x || y0 + Ny > plane_rows_y || ldk < Ny)
+        return fail(2, "bad sizes");
+    if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
+    if ((flags & B200SQ_GRAM_SYMMETRIC) && (planes_x_dev != planes_y_dev || x0 != y0 || Nx != Ny))
+        return fail(2, "symmetric Gram needs identical operands");
+    int e = launch_gram_planes((const int8_t*)planes_x_dev, expo_x_dev, plane_rows_x, x0, Nx,
+                               (const int8_t*)planes_y_dev, expo_y_dev, plane_rows_y, y0, Ny, dim, K_dev, ldk, flags,
+                               (cudaStream_t)stream_);
+    if (e) return cuda_fail(e, "gram launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
 int b200sq_rbf(const double* fx_dev, int64_t Nx, const double* fy_dev, int64_t Ny, int nf, double gamma,
                double* K_dev, int64_t ldk, void* stream_) {
     if (!fx_dev || !fy_dev || !K_dev) return fail(2, "NULL argument");

@@ -30,6 +30,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace b200sq {
@@ -56,6 +58,7 @@ struct I8Schedule {
 
 struct I8Args {
     int64_t rows_a, rows_b;   // rows per digit plane of the A / B operand
+    int64_t row0_a, row0_b;   // first row of the operand inside its planes
     int kbytes;               // K' = 2 * dim bytes per row
     int n_chunks, chunk_bytes;
     int tiles_n, n_tiles, symmetric;
@@ -261,9 +264,9 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
                 for (int ci = 0; ci < S.n_classes; ++ci)
                     for (int p = 0; p < S.n_pairs[ci]; ++p) {
-                        const int row_a = (int)(S.pi[ci][p] * A.rows_a) + bm * MN + (int)cta_rank * kTile;
-                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b) + bn * MN + (int)cta_rank * kTile;
-                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b) + bn * MN + (int)cta_rank * kTile;
+                        const int row_a = (int)(S.pi[ci][p] * A.rows_a + A.row0_a) + bm * MN + (int)cta_rank * kTile;
+                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b + A.row0_b) + bn * MN + (int)cta_rank * kTile;
+                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b + A.row0_b) + bn * MN + (int)cta_rank * kTile;
                         for (int k = k0; k < k1; k += kStageK) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t dst = smem_base + stage * kStageBytes;
@@ -378,10 +381,10 @@ __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int 
     return word | (((uint32_t)d & 255u) << (8 * byte));
 }
 
-__global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t n_rows, int64_t dim,
-                                                  int8_t* __restrict__ planes, int* __restrict__ expo) {
-    const int64_t row = blockIdx.x;
-    const double2* src = psi + row * dim;
+__global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
+                                                  int64_t dim, int8_t* __restrict__ planes, int* __restrict__ expo) {
+    const int64_t row = row0 + blockIdx.x;   // row inside the planes; state blockIdx.x of psi
+    const double2* src = psi + (int64_t)blockIdx.x * dim;
     __shared__ double red[8];
     __shared__ int s_e;
     double m = 0.0;
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ ps
     }
     __syncthreads();
     const double scale = ldexp(1.0, kTopBits - s_e);
-    const size_t plane_stride = (size_t)n_rows * 2 * dim;
+    const size_t plane_stride = (size_t)plane_rows * 2 * dim;
     int8_t* dst_row = planes + (size_t)row * 2 * dim;
     // 8 complex amplitudes per thread and iteration -> 16 bytes per plane
     for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
                 // bit-exactly symmetric whatever order the atomic FP64 accumulation happened in
                 const int r2 = (diag_tile && col > row) ? col : row, c2 = (diag_tile && col > row) ? row : col;
                 const double re = wt[(size_t)c2 * MN + r2], im = wt[(size_t)(MN + c2) * MN + r2];
-                k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j] - 12));
+                k = ldexp(re * re + im * im, 2 * (ex[A.row0_a + i] + ey[A.row0_b + j] - 12));
                 if (sym && i == j) {
                     if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
                     else if (flags & B200SQ_GRAM_DIAG_ZERO) k = 0.0;
@@ -511,43 +514,64 @@ int encode_planes(CUtensorMap* map, void* base, uint64_t kbytes, uint64_t rows_t
 
 bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
 
+int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
+                    int* expo, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream) {
     if (nx <= 0 || ny <= 0) return 0;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
-    const int64_t kbytes = 2 * dim;
-    const size_t plane_bytes = (size_t)kbytes;  // per row
+    const size_t plane_bytes = (size_t)(2 * dim);  // per row
     int8_t *px = nullptr, *py = nullptr;
     int *ex = nullptr, *ey = nullptr;
-    double* W = nullptr;
     cudaError_t e;
     auto cleanup = [&]() {
         if (px) cudaFreeAsync(px, stream);
         if (py && py != px) cudaFreeAsync(py, stream);
         if (ex) cudaFreeAsync(ex, stream);
         if (ey && ey != ex) cudaFreeAsync(ey, stream);
-        if (W) cudaFreeAsync(W, stream);
     };
     if ((e = cudaMallocAsync(&py, 2 * kSlices * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
     if ((e = cudaMallocAsync(&ey, ny * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-    k_slice_i8<<<(unsigned)ny, 256, 0, stream>>>(y, ny, dim, py, ey);
-    count_launch();
+    launch_slice_i8(y, ny, dim, py, ny, 0, ey, stream);
     if (sym) {
         px = py;
         ex = ey;
     } else {
         if ((e = cudaMallocAsync(&px, 2 * kSlices * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
         if ((e = cudaMallocAsync(&ex, nx * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-        k_slice_i8<<<(unsigned)nx, 256, 0, stream>>>(x, nx, dim, px, ex);
-        count_launch();
+        launch_slice_i8(x, nx, dim, px, nx, 0, ex, stream);
     }
+    const int rc = launch_gram_planes(px, ex, nx, 0, nx, py, ey, ny, 0, ny, dim, k, ldk, flags, stream);
+    cleanup();
+    return rc;
+}
+
+// Gram of rows [x0, x0 + nx) of the planes px against rows [y0, y0 + ny) of py (see k_slice_i8 for the layout;
+// rows_x / rows_y = rows per plane).  Symmetric flag: px == py and x0 == y0.
+int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t x0, int64_t nx, const int8_t* py,
+                       const int* ey, int64_t rows_y, int64_t y0, int64_t ny, int64_t dim, double* k, int64_t ldk,
+                       uint32_t flags, cudaStream_t stream) {
+    if (nx <= 0 || ny <= 0) return 0;
+    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    const int64_t kbytes = 2 * dim;
+    double* W = nullptr;
+    cudaError_t e;
+    auto cleanup = [&]() {
+        if (W) cudaFreeAsync(W, stream);
+    };
     I8Args a;
     memset(&a, 0, sizeof(a));
-    a.rows_a = nx;
-    a.rows_b = ny;
+    a.rows_a = rows_x;
+    a.rows_b = rows_y;
+    a.row0_a = x0;
+    a.row0_b = y0;
     a.kbytes = (int)kbytes;
-    a.chunk_bytes = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
-    a.n_chunks = (int)((kbytes + a.chunk_bytes - 1) / a.chunk_bytes);
     // CTA pairs (256 x 256 tiles, cta_group::2) halve the L2 -> SMEM operand traffic per MMA; small
     // problems keep single-CTA 128 x 128 tiles so that the machine still fills
     int dev = 0, sms = 148;
@@ -558,7 +582,15 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
         const int64_t tm = (nx + mn - 1) / mn, tn = (ny + mn - 1) / mn;
         return sym ? tm * (tm + 1) / 2 : tm * tn;
     };
-    const int cg = force_cg ? force_cg : (count_tiles(256) * a.n_chunks >= sms / 2 ? 2 : 1);
+    // K is cut into chunks of at most 16 KiB (the int32 accumulators stay exact).  CTA pairs need enough
+    // 256 x 256 units to fill the machine; otherwise single CTAs with 128 x 128 tiles (TMEM double
+    // buffered) run, with shorter chunks when there are fewer than half as many units as SMs.
+    a.chunk_bytes = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
+    auto n_chunks_of = [&](int cb) { return (kbytes + cb - 1) / cb; };
+    const int cg = force_cg ? force_cg : (count_tiles(256) * n_chunks_of(std::min(a.chunk_bytes, 4096)) >= sms / 2 ? 2 : 1);
+    while (a.chunk_bytes > 4096 && count_tiles(kTile * cg) * n_chunks_of(a.chunk_bytes) * 2 <= sms / cg)
+        a.chunk_bytes /= 2;
+    a.n_chunks = (int)n_chunks_of(a.chunk_bytes);
     a.mn = kTile * cg;
     const int tiles_m = (int)((nx + a.mn - 1) / a.mn);
     a.tiles_n = (int)((ny + a.mn - 1) / a.mn);
@@ -589,8 +621,8 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     a.W = W;
     cudaMemsetAsync(W, 0, wbytes, stream);
     CUtensorMap mapA, mapB;
-    int rc = encode_planes(&mapA, px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * nx);
-    if (!rc) rc = encode_planes(&mapB, py, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * ny);
+    int rc = encode_planes(&mapA, (void*)px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_x);
+    if (!rc) rc = encode_planes(&mapB, (void*)py, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_y);
     if (rc) { cleanup(); return rc; }
     const int smem = kStages * kStageBytes + 1024 + 256;
     const int n_units = a.n_tiles * a.n_chunks;

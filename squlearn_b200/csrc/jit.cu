@@ -142,9 +142,10 @@ const void* jit_pass_kernel(const Plan& plan, int ip, int team_size) {
     nvrtcProgram prog;
     if (rt.create(&prog, src.c_str(), "b200sq_pass_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return fail("nvrtcCreateProgram");
     const std::string inc = "--include-path=" + csrc_dir();
+    static const std::string minb = std::string("-DB200SQ_TILE_MINBLOCKS=") + (getenv("B200SQ_JIT_MINBLOCKS") ? getenv("B200SQ_JIT_MINBLOCKS") : "2");
     const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(),
-                          "--include-path=/usr/local/cuda/include"};
-    const nvrtcResult cr = rt.compile(prog, 5, opts);
+                          "--include-path=/usr/local/cuda/include", minb.c_str()};
+    const nvrtcResult cr = rt.compile(prog, 6, opts);
     if (cr != NVRTC_SUCCESS) {
         size_t ls = 0;
         rt.log_size(prog, &ls);

@@ -33,6 +33,14 @@ bool gram_i8_supported(int64_t dim);
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream);
 
+// Digit planes of n states into rows [row0, row0 + n) of `planes` ([12][plane_rows][2 dim] int8) and their
+// power-of-two row scales into expo[row0 ...]; Gram from planes.
+int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
+                    int* expo, cudaStream_t stream);
+int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t x0, int64_t nx, const int8_t* py,
+                       const int* ey, int64_t rows_y, int64_t y0, int64_t ny, int64_t dim, double* k, int64_t ldk,
+                       uint32_t flags, cudaStream_t stream);
+
 int launch_rbf(const double* fx, int64_t nx, const double* fy, int64_t ny, int nf, double gamma,
                double* k, int64_t ldk, cudaStream_t stream);
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -67,7 +68,8 @@ void tile_pass_geometry(const DPass& P, TileArgs* a) {
     // one thread per two register groups of eight amplitudes (the interpreter decodes a step once for
     // both), at least a warp, at most the CTA
     int groups = T >= 3 ? (1 << (T - 3)) : 1;
-    int ts = groups / 2 < 32 ? 32 : (groups / 2 > kCtaThreads ? kCtaThreads : groups / 2);
+    static const int gpt = getenv("B200SQ_TILE_G") ? atoi(getenv("B200SQ_TILE_G")) : 2;  // groups per thread
+    int ts = groups / gpt < 32 ? 32 : (groups / gpt > kCtaThreads ? kCtaThreads : groups / gpt);
     int log2ts = 0;
     while ((1 << log2ts) < ts) ++log2ts;
     const bool plain = P.has_src && P.n_fresh == 0;

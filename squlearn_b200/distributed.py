@@ -22,6 +22,10 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 
+def _mark(name):  # phase hook for tools/dist_breakdown.py (no-op in production)
+    pass
+
+
 def row_partition(n: int, parts: int) -> List[Tuple[int, int]]:
     """Balanced contiguous row ranges [(start, stop)] of n rows over `parts` ranks."""
     base, rem = divmod(n, parts)
@@ -88,10 +92,12 @@ class ShardedFidelityKernel:
     logic, with gloo and a stand-in engine.
     """
 
-    def __init__(self, kernel, group=None, diagonal: str = "one"):
+    def __init__(self, kernel, group=None, diagonal: str = "one", precision: Optional[str] = None):
         import torch.distributed as dist
 
         self._dist = dist
+        self.precision = precision  # Gram arithmetic: None = the engine's default policy ("auto")
+        self._gram_kw = {} if precision in (None, "auto") else {"precision": precision}
         self.kernel = kernel
         self.group = group
         self.rank = dist.get_rank(group)
@@ -109,53 +115,103 @@ class ShardedFidelityKernel:
         r0, r1 = parts[self.rank]
         eng = self.kernel._executor.engine
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
+        _mark("states")
         dim = psi_local.shape[1]
         dev = psi_local.device
         f64 = torch.float64
 
         jobs = gram_jobs(parts)
         mine = [j for j in jobs[self.rank] if not j["diag"]]
-
-        # ---- exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
-        # every peer is one NVSwitch hop away, so there is no ring-order penalty).  The receive
-        # buffer holds the column states of all my jobs back to back, so that jobs sharing a row
-        # range become ONE rectangular Gram launch.
+        # every off-diagonal piece of mine: column states come from the owner of those columns
         mine.sort(key=lambda j: (j["rows"], j["owner"]))
         total_cols = sum(j["cols"][1] - j["cols"][0] for j in mine)
-        recv = torch.empty((max(total_cols, 1), dim), dtype=psi_local.dtype, device=dev)
-        ops, off = [], 0
-        for q in range(self.world):          # sends: rows of mine that other ranks' jobs need
-            if q == self.rank:
-                continue
-            for j in jobs[q]:
-                if j["owner"] == self.rank and not j["diag"]:
-                    a, b = j["cols"]
-                    ops.append(dist.P2POp(dist.isend, psi_local[a - r0:b - r0].view(f64),
-                                          self._global_rank(q), self.group))
-        for j in mine:
-            w = j["cols"][1] - j["cols"][0]
-            j["off"] = off
-            ops.append(dist.P2POp(dist.irecv, recv[off:off + w].view(f64),
-                                  self._global_rank(j["owner"]), self.group))
-            off += w
-        reqs = dist.batch_isend_irecv(ops) if ops else []
+        n_local = r1 - r0
+        rows = torch.zeros((n_local, n), dtype=f64, device=dev)
+        use_planes = (hasattr(eng, "gram_from_planes")
+                      and eng.gram_precision(n, n, dim, self.precision) == "int8")  # same decision on every rank
 
-        # ---- the diagonal block needs no remote data: it runs while the blocks are in flight
-        rows = torch.zeros((r1 - r0, n), dtype=f64, device=dev)
-        if r1 > r0:
-            rows[:, r0:r1] = eng.gram(psi_local, None, diagonal=self.diagonal)
-        for req in reqs:
-            req.wait()
+        if use_planes:
+            # ---- split-integer path: every rank slices its own states ONCE into int8 digit planes and the
+            # planes travel (12 instead of 16 bytes per amplitude, no re-slicing on the receiver).  A block of
+            # rows is one contiguous buffer [12 planes | row exponents], so the exchange is a single NCCL
+            # message per peer, all posted in one batch and overlapped with the diagonal block.
+            buf_local, planes, expo = eng.alloc_plane_block(n_local, dim)
+            eng.slice_states(psi_local, planes, expo, 0)
+            ops, keep = [], []
+            for q in range(self.world):      # sends: rows of mine that other ranks' jobs need
+                if q == self.rank:
+                    continue
+                for j in jobs[q]:
+                    if j["owner"] == self.rank and not j["diag"]:
+                        a, b = j["cols"]
+                        if (a, b) == (r0, r1):
+                            msg = buf_local
+                        else:  # a sub-range of my rows (antipodal split): stage it contiguously
+                            msg = torch.cat([planes[:, a - r0:b - r0].reshape(-1), expo[a - r0:b - r0].view(torch.int8)])
+                            keep.append(msg)
+                        ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
+            for j in mine:
+                w = j["cols"][1] - j["cols"][0]
+                j["buf"], j["planes"], j["expo"] = eng.alloc_plane_block(w, dim)
+                ops.append(dist.P2POp(dist.irecv, j["buf"], self._global_rank(j["owner"]), self.group))
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            if n_local:  # the diagonal block needs no remote data: it runs while the planes are in flight
+                rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
+            _mark("diag")
+            for req in reqs:
+                req.wait()
+            _mark("exchange")
+            for j in mine:
+                ra, rb = j["rows"]
+                w = j["cols"][1] - j["cols"][0]
+                blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, j["planes"], j["expo"], 0, w)
+                rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
+                j["blk"] = blk
+            mine_done = True
+        else:
+            # ---- exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
+            # every peer is one NVSwitch hop away, so there is no ring-order penalty).  The receive
+            # buffer holds the column states of all my jobs back to back, so that jobs sharing a row
+            # range become ONE rectangular Gram launch.
+            recv = torch.empty((max(total_cols, 1), dim), dtype=psi_local.dtype, device=dev)
+            ops, off = [], 0
+            for q in range(self.world):          # sends: rows of mine that other ranks' jobs need
+                if q == self.rank:
+                    continue
+                for j in jobs[q]:
+                    if j["owner"] == self.rank and not j["diag"]:
+                        a, b = j["cols"]
+                        ops.append(dist.P2POp(dist.isend, psi_local[a - r0:b - r0].view(f64),
+                                              self._global_rank(q), self.group))
+            for j in mine:
+                w = j["cols"][1] - j["cols"][0]
+                j["off"] = off
+                ops.append(dist.P2POp(dist.irecv, recv[off:off + w].view(f64),
+                                      self._global_rank(j["owner"]), self.group))
+                off += w
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+
+            # ---- the diagonal block needs no remote data: it runs while the blocks are in flight
+            if n_local:
+                rows[:, r0:r1] = eng.gram(psi_local, None, diagonal=self.diagonal, **self._gram_kw)
+            _mark("diag")
+            for req in reqs:
+                req.wait()
+            _mark("exchange")
+
+            def rect(ra, rb, c_lo, c_hi):
+                return eng.gram(psi_local[ra - r0:rb - r0], recv[c_lo:c_hi], **self._gram_kw)
+            mine_done = False
 
         # ---- one launch per distinct row range
-        i = 0
+        i = len(mine) if mine_done else 0
         while i < len(mine):
             k = i
             while k < len(mine) and mine[k]["rows"] == mine[i]["rows"]:
                 k += 1
             ra, rb = mine[i]["rows"]
             c_lo, c_hi = mine[i]["off"], mine[k - 1]["off"] + (mine[k - 1]["cols"][1] - mine[k - 1]["cols"][0])
-            big = eng.gram(psi_local[ra - r0:rb - r0], recv[c_lo:c_hi])
+            big = rect(ra, rb, c_lo, c_hi)
             for j in mine[i:k]:
                 w = j["cols"][1] - j["cols"][0]
                 blk = big[:, j["off"] - c_lo: j["off"] - c_lo + w]
@@ -163,6 +219,7 @@ class ShardedFidelityKernel:
                 j["blk"] = blk
             i = k
 
+        _mark("rect")
         # ---- mirror: every off-diagonal piece, transposed, belongs to the owner of its columns
         ops, placements = [], []
         for j in mine:
@@ -182,6 +239,7 @@ class ShardedFidelityKernel:
                 req.wait()
         for a, b, ra, rb, buf in placements:
             rows[a:b, ra:rb] = buf
+        _mark("mirror")
         return rows, (r0, r1)
 
     def _global_rank(self, group_rank: int) -> int:

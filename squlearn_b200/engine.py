@@ -242,6 +242,51 @@ class Engine:
                                              out.data_ptr(), out.stride(0), flags, self._stream()))
         return out
 
+    def alloc_planes(self, plane_rows: int, dim: int):
+        """Empty digit planes ([12, plane_rows, 2 * dim] int8) and row exponents ([plane_rows] int32)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            return (torch.empty((12, plane_rows, 2 * dim), dtype=torch.int8, device=self.device),
+                    torch.zeros((plane_rows,), dtype=torch.int32, device=self.device))
+
+    def alloc_plane_block(self, rows: int, dim: int):
+        """One contiguous int8 buffer holding the digit planes of ``rows`` states followed by their int32 row
+        exponents (a single message for the multi-GPU exchange).  Returns (buffer, planes view, expo view)."""
+        torch = self._torch
+        nb = 12 * rows * 2 * dim
+        with torch.cuda.device(self.device):
+            buf = torch.empty((nb + 4 * rows,), dtype=torch.int8, device=self.device)
+        return buf, buf[:nb].view(12, rows, 2 * dim), buf[nb:].view(torch.int32)
+
+    def slice_states(self, psi, planes, expo, row0: int = 0):
+        """Write the digit planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes``."""
+        torch = self._torch
+        psi = psi.contiguous()
+        if psi.dtype != torch.complex128 or psi.dim() != 2:
+            raise ValueError("states must be a (N, 2^n) complex128 array")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_gram_slice(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(),
+                                                   planes.shape[1], int(row0), expo.data_ptr(), self._stream()))
+
+    def gram_from_planes(self, planes_x, expo_x, x0: int, nx: int, planes_y=None, expo_y=None, y0: int = 0,
+                         ny: int = 0, diagonal: str = "one", out=None):
+        """Gram of rows [x0, x0 + nx) of planes_x against rows [y0, y0 + ny) of planes_y
+        (``planes_y=None``: the symmetric Gram of the x rows)."""
+        torch = self._torch
+        sym = planes_y is None
+        if sym:
+            planes_y, expo_y, y0, ny = planes_x, expo_x, x0, nx
+        dim = planes_x.shape[2] // 2
+        flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[diagonal]) if sym else 0
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
+            _lib.check(self._lib.b200sq_gram_from_planes(
+                planes_x.data_ptr(), expo_x.data_ptr(), planes_x.shape[1], int(x0), int(nx), planes_y.data_ptr(),
+                expo_y.data_ptr(), planes_y.shape[1], int(y0), int(ny), dim, out.data_ptr(), out.stride(0), flags,
+                self._stream()))
+        return out
+
     @staticmethod
     def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:
         """Resolve the Gram arithmetic: "fp64" (DMMA) or "int8" (split-integer tcgen05 path)."""

@@ -75,3 +75,46 @@ def program_to_oracle(program: Program):
         else:
             out.append(Gate(g.name, g.qubits, ()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# NumPy restatement of the split-integer Gram (csrc/gram_i8.cu): digit planes and their recombination.
+# Test infrastructure: lets the CPU suite check the plane layout / exchange logic and the error of the
+# scheme without a GPU.
+I8_SLICES = 6
+
+
+def i8_slice(psi):
+    """(planes [12, N, 2 D] int8, expo [N] int32) of complex128 states, like k_slice_i8."""
+    psi = np.asarray(psi, dtype=np.complex128)
+    n_rows, dim = psi.shape
+    nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
+    rot = np.stack([psi.imag, -psi.real], axis=2).reshape(n_rows, 2 * dim)
+    m = np.abs(nat).max(axis=1)
+    expo = np.where(m > 0, np.frexp(m)[1], 0).astype(np.int32)
+    planes = np.zeros((2 * I8_SLICES, n_rows, 2 * dim), dtype=np.int8)
+    for base, v in ((0, nat), (I8_SLICES, rot)):
+        q = np.rint(np.ldexp(v, (6 + 8 * (I8_SLICES - 1) - expo)[:, None])).astype(np.int64)
+        for s_ in range(I8_SLICES - 1, 0, -1):
+            d = ((q + 128) & 255) - 128
+            q = (q - d) >> 8
+            planes[base + s_] = d.astype(np.int8)
+        planes[base] = q.astype(np.int8)
+    return planes, expo
+
+
+def i8_gram(planes_x, expo_x, planes_y, expo_y):
+    """|<x|y>|^2 from digit planes: classes c <= 5 plus the pair (3, 3), like k_gram_i8 + k_gram_i8_final."""
+    S = I8_SLICES
+    px = planes_x.astype(np.int64)
+    py = planes_y.astype(np.int64)
+    pairs = [(6, [(3, 3)])] + [(c, [(i, c - i) for i in range(c + 1)]) for c in range(S - 1, -1, -1)]
+    re = np.zeros((px.shape[1], py.shape[1]))
+    im = np.zeros_like(re)
+    for c, lst in pairs:
+        ar = sum(px[i] @ py[j].T for i, j in lst)
+        ai = sum(px[i] @ py[S + j].T for i, j in lst)
+        re += ar * 2.0 ** (-8 * c)
+        im += ai * 2.0 ** (-8 * c)
+    scale = np.ldexp(1.0, 2 * (expo_x[:, None].astype(np.int64) + expo_y[None, :] - 12))
+    return (re * re + im * im) * scale

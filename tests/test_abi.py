@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     names = _declared_symbols()
-    assert len(names) == 15
+    assert len(names) == 18
     assert sorted(names) == sorted(_lib.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name

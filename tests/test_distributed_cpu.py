@@ -14,6 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle
+from tests.helpers import i8_gram, i8_slice
 from squlearn_b200.distributed import (ShardedFidelityKernel, gram_jobs, row_partition,
                                        sharded_parameter_shift, symmetric_block_schedule)
 
@@ -73,6 +74,43 @@ class _OracleEngine:
         return torch.from_numpy(np.abs(an.conj() @ b.numpy().T) ** 2)
 
 
+class _PlanesEngine(_OracleEngine):
+    """Stand-in with the digit-plane entry points of the INT8 path (NumPy restatement in tests/helpers.py):
+    exercises the plane exchange of ShardedFidelityKernel under gloo."""
+
+    @staticmethod
+    def gram_precision(nx, ny, dim, precision=None):
+        return "int8"
+
+    def alloc_planes(self, plane_rows, dim):
+        return (torch.zeros((12, plane_rows, 2 * dim), dtype=torch.int8), torch.zeros((plane_rows,), dtype=torch.int32))
+
+    def alloc_plane_block(self, rows, dim):
+        nb = 12 * rows * 2 * dim
+        buf = torch.zeros((nb + 4 * rows,), dtype=torch.int8)
+        return buf, buf[:nb].view(12, rows, 2 * dim), buf[nb:].view(torch.int32)
+
+    def slice_states(self, psi, planes, expo, row0=0):
+        if psi.shape[0] == 0:
+            return
+        p, e = i8_slice(psi.numpy())
+        planes[:, row0:row0 + psi.shape[0]] = torch.from_numpy(p)
+        expo[row0:row0 + psi.shape[0]] = torch.from_numpy(e)
+
+    def gram_from_planes(self, px, ex, x0, nx, py=None, ey=None, y0=0, ny=0, diagonal="one", out=None):
+        sym = py is None
+        if sym:
+            py, ey, y0, ny = px, ex, x0, nx
+        k = i8_gram(px[:, x0:x0 + nx].numpy(), ex[x0:x0 + nx].numpy(), py[:, y0:y0 + ny].numpy(), ey[y0:y0 + ny].numpy())
+        if sym:
+            k = np.tril(k) + np.tril(k, -1).T
+            if diagonal == "one":
+                np.fill_diagonal(k, 1.0)
+            elif diagonal == "zero":
+                np.fill_diagonal(k, 0.0)
+        return torch.from_numpy(k)
+
+
 class _OracleExecutor:
     engine = _OracleEngine()
 
@@ -90,7 +128,7 @@ class _OracleKernel:
         return torch.from_numpy(oracle.simulate(self.gates, self.n, x, self.p))
 
 
-def _worker(rank, world, port, n_points, out_dir):
+def _worker(rank, world, port, n_points, out_dir, planes=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -98,6 +136,8 @@ def _worker(rank, world, port, n_points, out_dir):
         rng = np.random.default_rng(0)
         X = rng.uniform(-0.95, 0.95, (n_points, 2))
         kern = _OracleKernel(4, 2, 2)
+        if planes:
+            kern._executor = type("E", (), {"engine": _PlanesEngine()})()
         full = ShardedFidelityKernel(kern).evaluate(X)
         if rank == 0:
             np.save(os.path.join(out_dir, f"k_{world}_{n_points}.npy"), full)
@@ -126,3 +166,31 @@ def test_sharded_gram_gloo(tmp_path, world, n_points):
     assert got.shape == (n_points, n_points)
     assert np.max(np.abs(got - want)) < 1e-13
     assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (4, 13)])
+def test_sharded_gram_gloo_digit_planes(tmp_path, world, n_points):
+    """The INT8 path exchanges digit planes instead of states: same result within the scheme's error."""
+    mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path), True), nprocs=world, join=True)
+    got = np.load(tmp_path / f"k_{world}_{n_points}.npy")
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.95, 0.95, (n_points, 2))
+    want = oracle.fidelity_kernel(oracle.chebyshev_pqc(4, 2, 2), 4, X, None,
+                                  oracle.chebyshev_pqc_initial_parameters(4, 2, 2, seed=0))
+    assert np.max(np.abs(got - want)) < 1e-10
+    assert np.array_equal(got, got.T)
+
+
+def test_split_integer_scheme_error_on_circuit_states():
+    """NumPy restatement of the INT8 Gram (digit planes, classes c <= 5 + (3,3)) against complex128."""
+    n = 10
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-0.95, 0.95, (40, 3))
+    p = oracle.chebyshev_pqc_initial_parameters(n, 2, 3, seed=0)
+    sv = oracle.simulate(oracle.chebyshev_pqc(n, 2, 3), n, X, p)
+    sv = np.concatenate([sv, sv[:2], np.eye(1, 2 ** n, 3, dtype=complex)])   # duplicates and a basis state
+    planes, expo = i8_slice(sv)
+    assert planes[0].min() >= -65 and planes[0].max() <= 65
+    got = i8_gram(planes, expo, planes, expo)
+    want = np.abs(sv.conj() @ sv.T) ** 2
+    assert np.max(np.abs(got - want)) < 2e-11

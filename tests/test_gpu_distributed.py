@@ -26,8 +26,10 @@ def _worker(rank, world, port, out_dir):
         ex = sq.Executor("b200", device=rank)
         fk = sq.FidelityKernel(sq.ChebyshevPQC(9, 2), ex)
         full = ShardedFidelityKernel(fk).evaluate(X)
+        planes = ShardedFidelityKernel(fk, precision="int8").evaluate(X)  # digit planes travel, not states
         if rank == 0:
             np.save(os.path.join(out_dir, "k.npy"), full)
+            np.save(os.path.join(out_dir, "k8.npy"), planes)
             np.save(os.path.join(out_dir, "k1.npy"), fk.evaluate(X))
     finally:
         dist.destroy_process_group()
@@ -55,3 +57,6 @@ def test_sharded_gram_nccl(tmp_path):
     assert np.max(np.abs(got - want)) < 1e-11
     assert np.max(np.abs(got - single)) < 1e-13
     assert np.array_equal(got, got.T)
+    got8 = np.load(tmp_path / "k8.npy")
+    assert np.max(np.abs(got8 - want)) < 1e-10
+    assert np.array_equal(got8, got8.T)
