@@ -48,7 +48,7 @@ def workload(args):
 def config_dict(args, n_gpus):
     return {
         "workload": f"FidelityKernel Gram, ChebyshevPQC({args.qubits} qubits, 2 layers), "
-                    f"N={args.points}, d=4 (BASELINE configs[2])",
+                    f"N={args.points}, d=4 (BASELINE configs[{4 if args.qubits >= 20 else 2}])",
         "n_qubits": args.qubits, "n_points": args.points, "n_gates": 6 * args.qubits,
         "sharding": "single GPU" if n_gpus == 1 else f"row blocks over {n_gpus} ranks, NCCL all-gather of statevectors, symmetric half-ring of Gram blocks",
         "l2_policy": "inputs larger than L2 (statevector batch 16*N*2^n bytes >> 126 MB)",

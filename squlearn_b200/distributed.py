@@ -17,6 +17,7 @@ extension the north star asks for, built on the same single-GPU entry points:
 Single states are never split across GPUs (a 20-qubit state is 16 MiB).
 """
 
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -96,6 +97,7 @@ class ShardedFidelityKernel:
         import torch.distributed as dist
 
         self._dist = dist
+        self._blocks = {}
         self.precision = precision  # Gram arithmetic: None = the engine's default policy ("auto")
         self._gram_kw = {} if precision in (None, "auto") else {"precision": precision}
         self.kernel = kernel
@@ -135,7 +137,7 @@ class ShardedFidelityKernel:
             # planes travel (12 instead of 16 bytes per amplitude, no re-slicing on the receiver).  A block of
             # rows is one contiguous buffer [12 planes | row exponents], so the exchange is a single NCCL
             # message per peer, all posted in one batch and overlapped with the diagonal block.
-            buf_local, planes, expo = eng.alloc_plane_block(n_local, dim)
+            buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
             eng.slice_states(psi_local, planes, expo, 0)
             ops, keep = [], []
             for q in range(self.world):      # sends: rows of mine that other ranks' jobs need
@@ -147,20 +149,29 @@ class ShardedFidelityKernel:
                         if (a, b) == (r0, r1):
                             msg = buf_local
                         else:  # a sub-range of my rows (antipodal split): stage it contiguously
-                            msg = torch.cat([planes[:, a - r0:b - r0].reshape(-1), expo[a - r0:b - r0].view(torch.int8)])
+                            msg, mp, me = self._plane_block(eng, ("stage", q), b - a, dim)
+                            mp.copy_(planes[:, a - r0:b - r0])
+                            me.copy_(expo[a - r0:b - r0])
                             keep.append(msg)
                         ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
             for j in mine:
                 w = j["cols"][1] - j["cols"][0]
-                j["buf"], j["planes"], j["expo"] = eng.alloc_plane_block(w, dim)
+                j["buf"], j["planes"], j["expo"] = self._plane_block(eng, ("recv", j["owner"]), w, dim)
                 ops.append(dist.P2POp(dist.irecv, j["buf"], self._global_rank(j["owner"]), self.group))
             reqs = dist.batch_isend_irecv(ops) if ops else []
-            if n_local:  # the diagonal block needs no remote data: it runs while the planes are in flight
+            del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+            # The diagonal block needs no remote data.  By default it runs while the planes are in flight;
+            # B200SQ_DIST_DIAG_AFTER=1 runs it after the exchange (the persistent Gram kernel then does not
+            # compete with the NCCL copy kernels for SMs).
+            diag_after = os.environ.get("B200SQ_DIST_DIAG_AFTER", "0") == "1"
+            if n_local and not diag_after:
                 rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
             _mark("diag")
             for req in reqs:
                 req.wait()
             _mark("exchange")
+            if n_local and diag_after:
+                rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
             for j in mine:
                 ra, rb = j["rows"]
                 w = j["cols"][1] - j["cols"][0]
@@ -241,6 +252,17 @@ class ShardedFidelityKernel:
             rows[a:b, ra:rb] = buf
         _mark("mirror")
         return rows, (r0, r1)
+
+    def _plane_block(self, eng, tag, rows: int, dim: int):
+        """Plane buffers are kept between calls (tens of GiB per rank at n = 20: re-allocating them every
+        evaluation fragments the caching allocator at the edge of the 180 GB)."""
+        key = (tag, rows, dim)
+        blk = self._blocks.get(key)
+        if blk is None:
+            for k in [k for k in self._blocks if k[0] == tag]:   # shape changed: drop the old buffer first
+                del self._blocks[k]
+            blk = self._blocks[key] = eng.alloc_plane_block(rows, dim)
+        return blk
 
     def _global_rank(self, group_rank: int) -> int:
         if self.group is None:
