@@ -217,7 +217,7 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         // B200SQ_JIT = 0 / 1 forces it off / on.
         const void* jit = nullptr;
         {
-            static const char* mode = getenv("B200SQ_JIT");
+            const char* mode = getenv("B200SQ_JIT");  // read per call: tests and smoke() toggle it
             const bool big = ((int64_t)n_states << P.out_bits) >= ((int64_t)1 << 25);
             const bool want = (!mode || mode[0] == 'a') ? big : (mode[0] != '0');
             if (want) {
