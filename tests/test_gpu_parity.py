@@ -419,3 +419,23 @@ def test_config_c3_full_size_properties(sq, executor):
     want = oracle.fidelity_gram_zgemm(sv, sv, True)
     got = k[torch.from_numpy(sub).cuda()][:, torch.from_numpy(sub).cuda()].cpu().numpy()
     assert np.max(np.abs(got - want)) < GRAM_TOL
+
+
+# ------------------------------------------------------------------------------ next row f1: QKRR on device
+def test_qkrr_device_solver_matches_scipy(sq, executor):
+    """kernel/qkrr.py:158-169: (K + alpha I) c = y by Cholesky, predict = K(X, X_train) c."""
+    import scipy.linalg
+
+    n, d = 6, 2
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-0.9, 0.9, (60, d))
+    Xt = rng.uniform(-0.9, 0.9, (17, d))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1]
+    model = sq.QKRR(sq.FidelityKernel(sq.ChebyshevPQC(n, 2), executor), alpha=1e-4).fit(X, y)
+    gates = oracle.chebyshev_pqc(n, 2, d)
+    p = oracle.chebyshev_pqc_initial_parameters(n, 2, d, seed=0)
+    k = oracle.fidelity_kernel(gates, n, X, None, p) + 1e-4 * np.eye(60)
+    c = scipy.linalg.cho_solve((scipy.linalg.cholesky(k, lower=True), True), y)
+    assert np.max(np.abs(model.dual_coeff_ - c)) < 1e-6 * np.max(np.abs(c))
+    want = oracle.fidelity_kernel(gates, n, Xt, X, p) @ c
+    assert np.max(np.abs(model.predict(Xt) - want)) < 1e-7
