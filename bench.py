@@ -407,6 +407,14 @@ def run_gpu_arm(args):
                 "unfused_equivalent_gbs": 2 * state_bytes * 6 * n / (gt_ms * 1e-3) / 1e9,
                 "note": "the last pass is FP64-pipe bound (ncu: profiles/), not HBM bound: it applies 16 one-qubit "
                         "gates and 2 fused phase-table layers per amplitude",
+                "fp64_pipe": (lambda ins: {
+                    "instructions": ins, "achieved_tinstr_per_s": ins / (gt_ms * 1e-3) / 1e12,
+                    "peak_tinstr_per_s": 33.2 / 2.0, "frac": ins / (gt_ms * 1e-3) / 1e12 / (33.2 / 2.0),
+                    "peak_source": "measured DFMA rate 33.2 TFLOP/s = 16.6e12 FP64 instructions/s (tools/dmma_probe.cu, "
+                                   "profiles/r1_fp64_peak_probe.txt)",
+                    "algorithmic": "FP64 instructions of the plan (4 per amplitude and one-qubit gate / phase multiply) "
+                                   "summed over the live tiles of every pass",
+                })(float(n_points) * sum(cprog.fp64_instructions_per_state())),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
                 "share_of_step": gt_ms / ms_per_step,
             }

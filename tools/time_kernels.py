@@ -23,9 +23,11 @@ for T in [int(t) for t in os.environ.get("TILES", "12").split(",")]:
     ms, psi = timeit(lambda: eng.simulate(cp, xd))
     sb = 16.0 * N * (1 << n)
     out[f"sim_T{T}"] = {"ms": ms, "passes": cp.num_passes, "GBps": sb * (2 * cp.num_passes - 1) / ms / 1e6}
-for name, mode in (("gram_4m", False), ("gram_3m_ws", True), ("gram_3m_classic", "classic")):
-    ms, k = timeit(lambda: eng.gram(psi, None, three_m=mode))
+for name, mode in (("gram_fp64_4m", False), ("gram_fp64_3m_ws", True), ("gram_fp64_3m_classic", "classic")):
+    ms, k = timeit(lambda: eng.gram(psi, None, three_m=mode, precision="fp64"))
     out[name] = {"ms": ms, "alg_TFLOPs": 8.0 * (1 << n) * N * (N + 1) / 2 / ms / 1e9}
-ms, k = timeit(lambda: eng.gram(psi[: N // 8], psi[N // 8: 5 * N // 8], three_m=True))
-out["gram_rect_eighth_3m"] = {"ms": ms, "alg_TFLOPs": 8.0 * (1 << n) * (N // 8) * (N // 2) / ms / 1e9}
+ms, k = timeit(lambda: eng.gram(psi, None, precision="int8"))
+out["gram_int8_tcgen05"] = {"ms": ms, "fp64_equiv_TFLOPs": 8.0 * (1 << n) * N * (N + 1) / 2 / ms / 1e9}
+ms, k = timeit(lambda: eng.gram(psi[: N // 8], psi[N // 8: 5 * N // 8], precision="int8"))
+out["gram_rect_eighth_int8"] = {"ms": ms, "fp64_equiv_TFLOPs": 8.0 * (1 << n) * (N // 8) * (N // 2) / ms / 1e9}
 print(json.dumps(out))
