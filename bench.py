@@ -50,7 +50,7 @@ def config_dict(args, n_gpus):
         "workload": f"FidelityKernel Gram, ChebyshevPQC({args.qubits} qubits, 2 layers), "
                     f"N={args.points}, d=4 (BASELINE configs[{4 if args.qubits >= 20 else 2}])",
         "n_qubits": args.qubits, "n_points": args.points, "n_gates": 6 * args.qubits,
-        "sharding": "single GPU" if n_gpus == 1 else f"row blocks over {n_gpus} ranks, NCCL all-gather of statevectors, symmetric half-ring of Gram blocks",
+        "sharding": "single GPU" if n_gpus == 1 else f"row blocks over {n_gpus} ranks; symmetric half-ring of Gram blocks, int8 digit planes of the needed row blocks exchanged point-to-point over NCCL/NVLink",
         "l2_policy": "inputs larger than L2 (statevector batch 16*N*2^n bytes >> 126 MB)",
     }
 
