@@ -72,8 +72,9 @@ def cpu_reference_sample(args, n_states):
     return (t1 - t0) / n_states, (t2 - t1) / max(pairs, 1)
 
 
-def cpu_extrapolate(n_points, t_state, t_pair):
-    total = n_points * t_state + n_points * (n_points - 1) / 2 * t_pair
+def cpu_extrapolate(n_points, t_state, t_pair, workers=1):
+    """States and pairs are independent units: `workers` processes split them evenly."""
+    total = (n_points * t_state + n_points * (n_points - 1) / 2 * t_pair) / max(workers, 1)
     return n_points * n_points / total, total
 
 
@@ -83,32 +84,77 @@ def cpu_sample_size(args):
     return int(max(4, min(args.points, 64, round(9.0 / per_state))))
 
 
+def cpu_workers():
+    """Host processes of the CPU arm: the reference algorithm is single-threaded Python + NumPy per state and
+    per pair, so the way to use every host core is one process per core over disjoint states / pairs."""
+    return int(max(1, min(os.cpu_count() or 1, int(os.environ.get("B200SQ_CPU_WORKERS", "64")))))
+
+
+def _cpu_worker(packed):
+    qubits, points, n_states = packed
+
+    class _A:
+        pass
+
+    a = _A()
+    a.qubits, a.points = qubits, points
+    return cpu_reference_sample(a, n_states)
+
+
+def cpu_reference_parallel(args, n_states, workers):
+    """`workers` processes run the bounded sample concurrently (same contention for memory bandwidth as a
+    full multi-process run would see); returns the mean (t_state, t_pair) and the wall time."""
+    if workers <= 1:
+        t0 = time.perf_counter()
+        ts, tp = cpu_reference_sample(args, n_states)
+        return ts, tp, time.perf_counter() - t0
+    import multiprocessing as mp
+
+    # one BLAS / OpenMP thread per process (the children inherit the environment at spawn): the processes
+    # already cover the cores, nested thread pools only thrash
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    t0 = time.perf_counter()
+    try:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            res = pool.map(_cpu_worker, [(args.qubits, args.points, n_states)] * workers)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    wall = time.perf_counter() - t0
+    return float(np.mean([r[0] for r in res])), float(np.mean([r[1] for r in res])), wall
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_states = cpu_sample_size(args)
+    workers = cpu_workers()
     for _ in range(args.warmup):
         cpu_reference_sample(args, max(4, n_states // 8))
     ts, tp, t_steps = [], [], []
     for _ in range(args.steps):
-        t0 = time.perf_counter()
-        a, b = cpu_reference_sample(args, n_states)
-        t_steps.append(time.perf_counter() - t0)
+        a, b, wall = cpu_reference_parallel(args, n_states, workers)
+        t_steps.append(wall)
         ts.append(a)
         tp.append(b)
     t_state, t_pair = float(np.mean(ts)), float(np.mean(tp))
-    value, total = cpu_extrapolate(args.points, t_state, t_pair)
-    sample = (f"per step: {n_states} states simulated with one einsum per gate on the (N,2,..,2) "
-              f"array + the j<i Python pair loop on the {n_states}x{n_states} block "
-              f"({t_state:.3f} s/state, {t_pair * 1e6:.0f} us/pair); extrapolated to N={args.points}: "
-              f"{total:.0f} s for the full Gram")
+    value, total = cpu_extrapolate(args.points, t_state, t_pair, workers)
+    sample = (f"per step: {workers} processes, each {n_states} states simulated with one einsum per gate on the "
+              f"(N,2,..,2) array + the j<i Python pair loop on its {n_states}x{n_states} block "
+              f"({t_state:.3f} s/state, {t_pair * 1e6:.0f} us/pair under that load); extrapolated to N={args.points} "
+              f"split over the {workers} processes: {total:.0f} s for the full Gram")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(t_steps)), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
         "impl": "reference", "config": config_dict(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(), "numpy": np.__version__},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -419,13 +465,14 @@ def run_gpu_arm(args):
                 "share_of_step": gt_ms / ms_per_step,
             }
             n_states = cpu_sample_size(args)
-            t_state, t_pair = cpu_reference_sample(args, n_states)
-            cpu_value, cpu_total = cpu_extrapolate(n_points, t_state, t_pair)
+            workers = cpu_workers()
+            t_state, t_pair, _ = cpu_reference_parallel(args, n_states, workers)
+            cpu_value, cpu_total = cpu_extrapolate(n_points, t_state, t_pair, workers)
             line["cpu_baseline"] = {
-                "value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"{n_states} states, one einsum per gate + Python pair loop on the "
-                          f"{n_states}x{n_states} block ({t_state:.3f} s/state, {t_pair * 1e6:.0f} us/pair), "
-                          f"extrapolated to N={n_points}: {cpu_total:.0f} s",
+                "value": cpu_value, "unit": UNIT, "cores": workers, "kind": "port",
+                "sample": f"{workers} processes, each {n_states} states with one einsum per gate + the Python pair loop "
+                          f"on its {n_states}x{n_states} block ({t_state:.3f} s/state, {t_pair * 1e6:.0f} us/pair under "
+                          f"that load), extrapolated to N={n_points} over {workers} processes: {cpu_total:.0f} s",
                 "host_cores_available": os.cpu_count(),
             }
     if multi:
