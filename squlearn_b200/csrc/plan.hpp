@@ -420,7 +420,8 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
         while (n_done < absorbed.size()) {
             if ((int)plan.rounds.size() - ps.r0 >= kMaxPassRounds - 1 ||
                 (int)plan.steps.size() - ps.s0 >= kMaxPassSteps - 40 ||
-                (int)plan.mats.size() - ps.m0 >= kMaxPassMats - 48) {
+                (int)plan.mats.size() - ps.m0 >= kMaxPassMats - 48 ||
+                mat_off >= kMaxPassMatElems - 1024) {   // matrices + tables live in shared memory
                 overflow = true;
                 break;
             }

@@ -38,6 +38,7 @@ constexpr int kMaxPassSteps = 160;
 constexpr int kMaxPassRounds = 64;
 constexpr int kMaxPassMats = 224;
 constexpr int kMaxInit = 128;
+constexpr int kMaxPassMatElems = 4096;  // double2 elements of matrix / table storage per team (64 KiB)
 constexpr int kNoBit = 255;
 
 struct GateInfo {

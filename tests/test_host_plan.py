@@ -233,3 +233,32 @@ def test_runtime_specialised_pass_kernels_compile():
                 assert size > 0, log.value.decode()
         finally:
             lib.b200sq_program_destroy(h)
+
+
+def test_long_two_qubit_circuits_split_into_passes_that_fit_shared_memory():
+    """Hundreds of 4x4 gates: the planner closes a pass before its matrix storage outgrows shared memory."""
+    import ctypes
+    from squlearn_b200 import _lib
+    rng = np.random.default_rng(42)
+    n = 7
+    prog, ogates = random_circuit(n, 700, 4, 2, rng, kinds=["swap", "iswap", "rxx", "ryy", "rzx", "ecr", "rzz", "crz", "h"])
+    X = rng.uniform(-0.9, 0.9, (2, 2))
+    p = rng.uniform(-1, 1, 4)
+    got, passes = hostemu.simulate(prog, p, X, tile_bits=7, team_size=32)
+    assert np.max(np.abs(got - oracle.simulate(ogates, n, X, p))) < 1e-11
+    assert passes >= 2
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    _lib.check(lib.b200sq_program_create(n, len(prog), prog.c_gates(p), 7, ctypes.byref(h)))
+    try:
+        cnt = ctypes.c_int(0)
+        _lib.check(lib.b200sq_program_dump(h, None, 0, ctypes.byref(cnt)))
+        buf = (ctypes.c_int32 * cnt.value)()
+        _lib.check(lib.b200sq_program_dump(h, buf, cnt.value, ctypes.byref(cnt)))
+        w = list(buf)
+        pos = 5
+        for _ in range(w[2]):
+            assert w[pos + 8] <= 4096          # mat_elems of the pass
+            pos += 11 + w[pos]
+    finally:
+        lib.b200sq_program_destroy(h)
