@@ -137,47 +137,80 @@ class ShardedFidelityKernel:
             # planes travel (12 instead of 16 bytes per amplitude, no re-slicing on the receiver).  A block of
             # rows is one contiguous buffer [12 planes | row exponents], so the exchange is a single NCCL
             # message per peer, all posted in one batch and overlapped with the diagonal block.
-            buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
-            eng.slice_states(psi_local, planes, expo, 0)
-            ops, keep = [], []
-            for q in range(self.world):      # sends: rows of mine that other ranks' jobs need
-                if q == self.rank:
-                    continue
-                for j in jobs[q]:
-                    if j["owner"] == self.rank and not j["diag"]:
-                        a, b = j["cols"]
-                        if (a, b) == (r0, r1):
-                            msg = buf_local
-                        else:  # a sub-range of my rows (antipodal split): stage it contiguously
-                            msg, mp, me = self._plane_block(eng, ("stage", q), b - a, dim)
-                            mp.copy_(planes[:, a - r0:b - r0])
-                            me.copy_(expo[a - r0:b - r0])
-                            keep.append(msg)
-                        ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
-            for j in mine:
-                w = j["cols"][1] - j["cols"][0]
-                j["buf"], j["planes"], j["expo"] = self._plane_block(eng, ("recv", j["owner"]), w, dim)
-                ops.append(dist.P2POp(dist.irecv, j["buf"], self._global_rank(j["owner"]), self.group))
-            reqs = dist.batch_isend_irecv(ops) if ops else []
-            del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
-            # The diagonal block needs no remote data.  By default it runs while the planes are in flight;
-            # B200SQ_DIST_DIAG_AFTER=1 runs it after the exchange (the persistent Gram kernel then does not
-            # compete with the NCCL copy kernels for SMs).
+            equal = all(b - a == n_local for a, b in parts)
+            block_bytes = 12 * n_local * 2 * dim + 4 * n_local
+            mode = os.environ.get("B200SQ_DIST_EXCHANGE", "auto")   # "allgather" | "p2p" | "auto"
+            use_allgather = (mode == "allgather" or (mode == "auto" and self.world > 2)) and equal and n_local > 0 \
+                and n_local % 4 == 0 and self.world * block_bytes <= (32 << 30)   # 16-byte aligned blocks, <= 32 GiB
             diag_after = os.environ.get("B200SQ_DIST_DIAG_AFTER", "0") == "1"
-            if n_local and not diag_after:
-                rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-            _mark("diag")
-            for req in reqs:
-                req.wait()
-            _mark("exchange")
-            if n_local and diag_after:
-                rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-            for j in mine:
-                ra, rb = j["rows"]
-                w = j["cols"][1] - j["cols"][0]
-                blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, j["planes"], j["expo"], 0, w)
-                rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
-                j["blk"] = blk
+            if use_allgather:
+                # ---- one NCCL all-gather of the plane blocks (NVSwitch collective bandwidth; a rank uses
+                # floor(P/2) of the P - 1 remote blocks it receives, which is still faster than P2P send/recv:
+                # measured 250 GB/s per rank for the point-to-point batch).  Block q of `gathered` is rank q's
+                # [12 planes | row exponents] buffer; my own block is sliced in place.
+                gathered = self._gather_buffer(eng, self.world * block_bytes)
+                nb = 12 * n_local * 2 * dim
+                view = lambda q: (gathered[q * block_bytes: q * block_bytes + nb].view(12, n_local, 2 * dim),
+                                  gathered[q * block_bytes + nb: (q + 1) * block_bytes].view(torch.int32))
+                planes, expo = view(self.rank)
+                eng.slice_states(psi_local, planes, expo, 0)
+                del psi_local
+                work = dist.all_gather_into_tensor(gathered, gathered[self.rank * block_bytes:(self.rank + 1) * block_bytes],
+                                                   group=self.group, async_op=True)
+                if not diag_after:
+                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
+                _mark("diag")
+                work.wait()
+                _mark("exchange")
+                if diag_after:
+                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
+                for j in mine:
+                    ra, rb = j["rows"]
+                    (a, b), c0 = j["cols"], parts[j["owner"]][0]
+                    pq, eq = view(j["owner"])
+                    blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, pq, eq, a - c0, b - a)
+                    rows[ra - r0:rb - r0, a:b] = blk
+                    j["blk"] = blk
+            else:
+                buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
+                eng.slice_states(psi_local, planes, expo, 0)
+                ops, keep = [], []
+                for q in range(self.world):      # sends: rows of mine that other ranks' jobs need
+                    if q == self.rank:
+                        continue
+                    for j in jobs[q]:
+                        if j["owner"] == self.rank and not j["diag"]:
+                            a, b = j["cols"]
+                            if (a, b) == (r0, r1):
+                                msg = buf_local
+                            else:  # a sub-range of my rows (antipodal split): stage it contiguously
+                                msg, mp, me = self._plane_block(eng, ("stage", q), b - a, dim)
+                                mp.copy_(planes[:, a - r0:b - r0])
+                                me.copy_(expo[a - r0:b - r0])
+                                keep.append(msg)
+                            ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
+                for j in mine:
+                    w = j["cols"][1] - j["cols"][0]
+                    j["buf"], j["planes"], j["expo"] = self._plane_block(eng, ("recv", j["owner"]), w, dim)
+                    ops.append(dist.P2POp(dist.irecv, j["buf"], self._global_rank(j["owner"]), self.group))
+                reqs = dist.batch_isend_irecv(ops) if ops else []
+                del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+                # The diagonal block needs no remote data.  By default it runs while the planes are in flight;
+                # B200SQ_DIST_DIAG_AFTER=1 runs it after the exchange.
+                if n_local and not diag_after:
+                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
+                _mark("diag")
+                for req in reqs:
+                    req.wait()
+                _mark("exchange")
+                if n_local and diag_after:
+                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
+                for j in mine:
+                    ra, rb = j["rows"]
+                    w = j["cols"][1] - j["cols"][0]
+                    blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, j["planes"], j["expo"], 0, w)
+                    rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
+                    j["blk"] = blk
             mine_done = True
         else:
             # ---- exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
@@ -253,13 +286,20 @@ class ShardedFidelityKernel:
         _mark("mirror")
         return rows, (r0, r1)
 
+    def _gather_buffer(self, eng, nbytes: int):
+        buf = self._blocks.get("gathered")
+        if buf is None or buf.numel() != nbytes:
+            self._blocks.pop("gathered", None)
+            buf = self._blocks["gathered"] = eng.alloc_plane_block(0, 1)[0].new_empty((nbytes,))
+        return buf
+
     def _plane_block(self, eng, tag, rows: int, dim: int):
         """Plane buffers are kept between calls (tens of GiB per rank at n = 20: re-allocating them every
         evaluation fragments the caching allocator at the edge of the 180 GB)."""
         key = (tag, rows, dim)
         blk = self._blocks.get(key)
         if blk is None:
-            for k in [k for k in self._blocks if k[0] == tag]:   # shape changed: drop the old buffer first
+            for k in [k for k in self._blocks if isinstance(k, tuple) and k[0] == tag]:   # shape changed: drop the old one
                 del self._blocks[k]
             blk = self._blocks[key] = eng.alloc_plane_block(rows, dim)
         return blk

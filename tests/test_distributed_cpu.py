@@ -168,9 +168,11 @@ def test_sharded_gram_gloo(tmp_path, world, n_points):
     assert np.array_equal(got, got.T)
 
 
-@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (4, 13)])
+@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (4, 13), (3, 12), (4, 16)])
 def test_sharded_gram_gloo_digit_planes(tmp_path, world, n_points):
-    """The INT8 path exchanges digit planes instead of states: same result within the scheme's error."""
+    """The INT8 path exchanges digit planes instead of states: same result within the scheme's error.
+    Equal blocks on more than two ranks (3 x 4, 4 x 4 rows) go through one all-gather of the plane blocks,
+    the other cases through point-to-point messages."""
     mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path), True), nprocs=world, join=True)
     got = np.load(tmp_path / f"k_{world}_{n_points}.npy")
     rng = np.random.default_rng(0)
