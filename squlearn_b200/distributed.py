@@ -140,7 +140,9 @@ class ShardedFidelityKernel:
             equal = all(b - a == n_local for a, b in parts)
             block_bytes = 12 * n_local * 2 * dim + 4 * n_local
             mode = os.environ.get("B200SQ_DIST_EXCHANGE", "auto")   # "allgather" | "p2p" | "auto"
-            use_allgather = (mode == "allgather" or (mode == "auto" and self.world > 2)) and equal and n_local > 0 \
+            # default: point-to-point (measured faster: 15.4 vs 16.7 ms per C3 step on 4 GPUs; it moves only the
+            # floor(P/2) blocks a rank needs); the all-gather is kept as an option
+            use_allgather = mode == "allgather" and equal and n_local > 0 \
                 and n_local % 4 == 0 and self.world * block_bytes <= (32 << 30)   # 16-byte aligned blocks, <= 32 GiB
             diag_after = os.environ.get("B200SQ_DIST_DIAG_AFTER", "0") == "1"
             if use_allgather:

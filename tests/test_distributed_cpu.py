@@ -128,7 +128,8 @@ class _OracleKernel:
         return torch.from_numpy(oracle.simulate(self.gates, self.n, x, self.p))
 
 
-def _worker(rank, world, port, n_points, out_dir, planes=False):
+def _worker(rank, world, port, n_points, out_dir, planes=False, exchange="auto"):
+    os.environ["B200SQ_DIST_EXCHANGE"] = exchange
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -168,12 +169,12 @@ def test_sharded_gram_gloo(tmp_path, world, n_points):
     assert np.array_equal(got, got.T)
 
 
-@pytest.mark.parametrize("world,n_points", [(2, 10), (3, 7), (4, 13), (3, 12), (4, 16)])
-def test_sharded_gram_gloo_digit_planes(tmp_path, world, n_points):
+@pytest.mark.parametrize("world,n_points,exchange", [(2, 10, "auto"), (3, 7, "auto"), (4, 13, "auto"),
+                                                     (3, 12, "allgather"), (4, 16, "allgather"), (2, 8, "allgather")])
+def test_sharded_gram_gloo_digit_planes(tmp_path, world, n_points, exchange):
     """The INT8 path exchanges digit planes instead of states: same result within the scheme's error.
-    Equal blocks on more than two ranks (3 x 4, 4 x 4 rows) go through one all-gather of the plane blocks,
-    the other cases through point-to-point messages."""
-    mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path), True), nprocs=world, join=True)
+    Point-to-point messages (default) and one all-gather of equal-sized plane blocks (B200SQ_DIST_EXCHANGE)."""
+    mp.spawn(_worker, args=(world, _free_port(), n_points, str(tmp_path), True, exchange), nprocs=world, join=True)
     got = np.load(tmp_path / f"k_{world}_{n_points}.npy")
     rng = np.random.default_rng(0)
     X = rng.uniform(-0.95, 0.95, (n_points, 2))
