@@ -62,52 +62,36 @@ class CompiledProgram:
     def fp64_instructions_per_state(self):
         """Estimated FP64 instructions (DMUL / DFMA) per state and pass, from the plan: 4 per amplitude for a
         one-qubit gate slot, a phase-table or stray diagonal multiply and each product table of the expansion,
-        8 for a controlled 2x2, 32 for a 4x4; tiles that are identically zero are not counted."""
+        8 for a general / controlled 2x2, 32 for a 4x4; only the tiles that are not identically zero count
+        (tile qubits plus the outer qubits that are already active in the pass's input layout)."""
         w = self.dump()
-        n, T, n_pass, n_rounds, n_steps = (int(v) for v in w[:5])
+        n, _, n_pass, n_rounds, n_steps = (int(v) for v in w[:5])
         pos, passes = 5, []
         for _ in range(n_pass):
             Tp, a_in, a_out, last, r0, r1, s0, s1, mat, nfresh, ntabs = (int(v) for v in w[pos:pos + 11])
-            passes.append((Tp, a_in & 0xffffffff, a_out & 0xffffffff, r0, r1, nfresh))
+            tile_mask = 0
+            for q in w[pos + 11: pos + 11 + Tp]:
+                tile_mask |= 1 << int(q)
+            passes.append((Tp, a_in & 0xffffffff, r0, r1, nfresh, tile_mask))
             pos += 11 + Tp
         rounds = [tuple(int(v) for v in w[pos + 6 * i: pos + 6 * i + 6]) for i in range(n_rounds)]
         pos += 6 * n_rounds
         steps = [tuple(int(v) for v in w[pos + 7 * i: pos + 7 * i + 7]) for i in range(n_steps)]
+        cost = {6: 4.0, 7: 4.0, 8: 8.0}   # layer steps: per active register slot
         out = []
-        for Tp, a_in, a_out, r0, r1, nfresh in passes:
+        for Tp, a_in, r0, r1, nfresh, tile_mask in passes:
             per_amp = 0.0
             if nfresh:
                 per_amp += (4.0 if a_in else 0.0) + (4.0 if nfresh > 6 else 0.0)
             for r in range(r0, r1):
-                nb, _, _, _, s0, s1 = rounds[r]
-                for kind, gate, a, b, ctrl, mat, swap in steps[s0:s1]:
-                    if kind in (6, 7):
-                        per_amp += 4.0 * bin(a).count("1")
-                    elif kind == 8:
-                        per_amp += 8.0 * bin(a).count("1")
-                    elif kind in (9, 2):
-                        per_amp += 4.0
-                    elif kind == 5:
-                        per_amp += 8.0
+                for kind, _, a, _, _, _, _ in steps[rounds[r][4]:rounds[r][5]]:
+                    if kind in cost:
+                        per_amp += cost[kind] * bin(a).count("1")
                     else:
-                        per_amp += 32.0
-            # amplitudes that are actually processed: tiles over the active qubits of the input layout
-            live_bits = Tp + bin(a_in & ~self._tile_mask(w, passes.index((Tp, a_in, a_out, r0, r1, nfresh)))).count("1")
+                        per_amp += {9: 4.0, 2: 4.0, 5: 8.0}.get(kind, 32.0)
+            live_bits = Tp + bin(a_in & ~tile_mask).count("1")
             out.append(per_amp * 2.0 ** min(live_bits, n))
         return out
-
-    @staticmethod
-    def _tile_mask(w, ip):
-        pos = 5
-        for i in range(int(w[2])):
-            Tp = int(w[pos])
-            if i == ip:
-                m = 0
-                for q in w[pos + 11: pos + 11 + Tp]:
-                    m |= 1 << int(q)
-                return m
-            pos += 11 + Tp
-        return 0
 
     def dump(self) -> np.ndarray:
         n = ctypes.c_int(0)
