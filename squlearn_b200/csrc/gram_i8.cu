@@ -1,4 +1,8 @@
 // Fidelity Gram matrix on the 5th-generation tensor cores: split-integer ("Ozaki scheme") FP64 emulation.
+// Replaces the O(N^2) Python pair loop `np.abs(np.matmul(x.conj(), y))**2` of
+// FidelityKernelStatevector.evaluate_kernel_sv (src/squlearn/kernel/lowlevel_kernel/
+// fidelity_kernel_statevector.py:303-310, 358-383) for large problems; semantics (symmetric mirror, diagonal
+// policy) as in gram_kernels.cu.
 //
 // tcgen05 has no f64 kind and B200's FP64 DMMA peaks at ~37 TFLOP/s, while the INT8 kind runs at
 // ~4.5 POP/s.  Every amplitude component v of a state row is therefore written in fixed point relative to

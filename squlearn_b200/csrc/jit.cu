@@ -1,4 +1,5 @@
-// Run-time specialisation of the pass kernel.
+// Run-time specialisation of the pass kernel (the batched counterpart of the reference's per-gate replay of
+// its gate-list IR, src/squlearn/util/pennylane/pennylane_circuit.py:541-681).
 //
 // The generic kernel k_tile_pass interprets the rounds / steps of a pass; ncu shows it bound by the
 // interpreter's own instructions (step decode, register moves at the switch joins), not by the FP64
