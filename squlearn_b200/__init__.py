@@ -24,6 +24,7 @@ from .executor import (
 from .kernel import FidelityKernel, ProjectedQuantumKernel
 from .observables import CustomObservable, SinglePauli, SummedPaulis
 from .program import Angle, GateOp, Program
+from .qgpr import QGPR
 from .qkrr import QKRR
 from .qnn import LowLevelQNN
 from .qrc import QRCRegressor, QRCClassifier, random_pauli_list
@@ -36,5 +37,5 @@ __all__ = [
     "LayeredEncodingCircuit", "EncodingCircuitBase", "SinglePauli", "SummedPaulis",
     "CustomObservable", "Program", "GateOp", "Angle", "QRCRegressor", "QRCClassifier",
     "random_pauli_list", "b200_evaluate", "b200_evaluate_statevector", "b200_gradient",
-    "b200_operator_gradient", "QKRR",
+    "b200_operator_gradient", "QKRR", "QGPR",
 ]
