@@ -22,6 +22,7 @@ from .executor import (
     b200_operator_gradient,
 )
 from .kernel import FidelityKernel, ProjectedQuantumKernel
+from .kernel_loss import NLL, KernelOptimizer, ScipyMinimize, TargetAlignment
 from .observables import CustomObservable, SinglePauli, SummedPaulis
 from .program import Angle, GateOp, Program
 from .qgpr import QGPR
@@ -37,5 +38,5 @@ __all__ = [
     "LayeredEncodingCircuit", "EncodingCircuitBase", "SinglePauli", "SummedPaulis",
     "CustomObservable", "Program", "GateOp", "Angle", "QRCRegressor", "QRCClassifier",
     "random_pauli_list", "b200_evaluate", "b200_evaluate_statevector", "b200_gradient",
-    "b200_operator_gradient", "QKRR", "QGPR",
+    "b200_operator_gradient", "QKRR", "QGPR", "TargetAlignment", "NLL", "KernelOptimizer", "ScipyMinimize",
 ]

@@ -75,3 +75,76 @@ def test_qgpr_precomputed_and_std_and_sigma_accumulation_quirk():
     mean2 = model.predict(full)
     want2, _ = _reference_qgpr(full[:n_train, :n_train], full[n_train:, :n_train], full[n_train:, n_train:], y, 2e-3, False)
     assert np.max(np.abs(mean2 - want2)) < 1e-9
+
+
+# ------------------------------------------------------------------------------ row f2: trainable kernels
+class _TrainableOracleKernel(_OracleKernel):
+    """Oracle-backed stand-in with the parameter interface the losses and the optimiser use."""
+
+    def __init__(self, n, d):
+        super().__init__(n, d)
+        self.parameters = np.array(self.p, dtype=float)
+        self.num_parameters = len(self.p)
+
+    def assign_parameters(self, parameters):
+        self.parameters = np.array(parameters, dtype=float)
+        self.p = self.parameters
+
+    def _initialize_kernel(self, num_features):
+        pass
+
+    def evaluate(self, x, y=None):
+        return self.evaluate_device(x, y).numpy()
+
+
+def test_target_alignment_and_nll_match_reference_restatements():
+    from squlearn_b200 import NLL, TargetAlignment
+
+    n, d = 3, 2
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-0.9, 0.9, (14, d))
+    labels = np.where(X[:, 0] * X[:, 1] > 0, 1, -1)
+    kern = _TrainableOracleKernel(n, d)
+    p = rng.uniform(-1, 1, kern.num_parameters)
+    k = oracle.fidelity_kernel(kern.gates, n, X, None, p)
+    for rescale in (True, False):
+        ta = TargetAlignment(rescale_class_labels=rescale)
+        ta.set_quantum_kernel(kern)
+        got = ta.compute(p, X, labels=labels)
+        # target_alignment.py:78-90
+        if rescale:
+            nplus = np.count_nonzero(labels == 1)
+            nminus = len(labels) - nplus
+            yy = np.array([v / nplus if v == 1 else v / nminus for v in labels])
+        else:
+            yy = labels.astype(float)
+        T = np.outer(yy, yy)
+        want = -np.sum(k * T) / np.sqrt(np.sum(k * k) * np.sum(T * T))
+        assert abs(got - want) < 1e-12
+    y = np.sin(X[:, 0])
+    nll = NLL(sigma=1e-3)
+    nll.set_quantum_kernel(kern)
+    got = nll.compute(p, X, labels=y)
+    # negative_log_likelihood.py:77-88
+    km = k + 1e-3 * np.eye(len(X))
+    L = scipy.linalg.cholesky(km, lower=True)
+    s2 = scipy.linalg.solve_triangular(L.T, scipy.linalg.solve_triangular(L, y, lower=True), lower=False)
+    want = np.sum(np.log(np.diagonal(L))) + 0.5 * y.T @ s2 + 0.5 * len(X) * np.log(2.0 * np.pi)
+    assert got.shape == (1,) and abs(got[0] - want) < 1e-9
+
+
+def test_kernel_optimizer_lowers_the_loss_and_assigns_the_optimum():
+    from squlearn_b200 import KernelOptimizer, ScipyMinimize, TargetAlignment
+
+    n, d = 2, 1
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-0.9, 0.9, (12, d))
+    labels = np.where(X[:, 0] > 0, 1, -1)
+    kern = _TrainableOracleKernel(n, d)
+    loss = TargetAlignment()
+    opt = KernelOptimizer(kern, loss, ScipyMinimize("Nelder-Mead", {"maxiter": 60}))
+    start = loss.compute(kern.parameters, X, labels=labels) if loss._quantum_kernel is not None else None
+    res = opt.run_optimization(X, labels)
+    assert opt.is_fitted and np.allclose(kern.parameters, res.x) and np.allclose(opt.get_optimal_parameters(), res.x)
+    assert res.fun <= start + 1e-12
+    assert opt.run_optimization(X, labels) is None          # already fitted (kernel_optimizer.py:66-67)
