@@ -217,10 +217,12 @@ def b200_operator_gradient(circuit: B200Circuit, executor: Executor, param=None,
 
 
 def b200_gradient(circuit: B200Circuit, executor: Executor, param=None, x=None, param_obs=None,
-                  squared: bool = False, variant_slice: Optional[slice] = None, **_) -> np.ndarray:
+                  squared: bool = False, variant_slice: Optional[slice] = None, wrt: str = "param", **_) -> np.ndarray:
     """(N, n_obs, P): d<O>/d param by the parameter-shift batch
     (src/squlearn/util/optree/optree_derivative.py:130-158): all shifted circuits of all data
-    points are evaluated in one engine call, variant index outermost.
+    points are evaluated in one engine call, variant index outermost.  ``wrt="x"`` gives (N, n_obs, d):
+    d<O>/d x through the same shifted circuits and the chain rule of the encoding angles (the reference's
+    "dfdx", evaluation_classes.py:105-125).
 
     ``variant_slice`` restricts the evaluation to a slice of the shifted-variant list (used to
     shard the batch over GPUs); the partial sums of all slices add up to the full gradient."""
@@ -230,11 +232,12 @@ def b200_gradient(circuit: B200Circuit, executor: Executor, param=None, x=None, 
     if x2.ndim == 1:
         x2 = x2.reshape(-1, max(prog.num_features, 1))
     strings, per_obs = circuit.observable_terms(param_obs, squared)
-    gate_idx, shift, weight, pidx = prog.shift_variants(x2)
+    gate_idx, shift, weight, pidx = prog.shift_variants(
+        x2, wrt=wrt, p=None if param is None else np.asarray(param, dtype=np.float64))
     if variant_slice is not None:
         gate_idx, shift, weight, pidx = (gate_idx[variant_slice], shift[variant_slice],
                                          weight[variant_slice], pidx[variant_slice])
-    out = np.zeros((x2.shape[0], len(per_obs), prog.num_parameters))
+    out = np.zeros((x2.shape[0], len(per_obs), prog.num_parameters if wrt == "param" else prog.num_features))
     if len(gate_idx) == 0:
         return out
     expv = eng.simulate_expvals(circuit.compiled(eng, param), x2, strings,

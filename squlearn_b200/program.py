@@ -56,6 +56,21 @@ class Angle:
             return None
         return self.scale * self.feature_factor(x)
 
+    def dtheta_dfeature(self, x: np.ndarray, p: Optional[np.ndarray]) -> Optional[np.ndarray]:
+        """d theta / d x[feature] per sample, or None when the angle does not depend on a feature
+        (theta = offset + scale * p * fn(x): linear -> 1, arccos -> -1/sqrt(1 - x^2), arctan -> 1/(1 + x^2))."""
+        if self.table is not None or self.feature is None:
+            return None
+        pv = 1.0 if self.param is None else float(p[self.param])
+        v = x[:, self.feature]
+        if self.fn == "linear":
+            d = np.ones_like(v)
+        elif self.fn == "arccos":
+            d = -1.0 / np.sqrt(1.0 - v * v)
+        else:
+            d = 1.0 / (1.0 + v * v)
+        return self.scale * pv * d
+
     def coeffs(self, p: np.ndarray) -> Tuple[float, float]:
         """(c0, c1) of the C ABI: theta = c0 + c1 * f(x[feat])."""
         pv = 1.0 if self.param is None else float(p[self.param])
@@ -153,27 +168,39 @@ class Program:
         return np.ascontiguousarray(np.stack(rows, axis=0))
 
     # ------------------------------------------------------------------ parameter shift
-    def shift_variants(self, x: np.ndarray):
+    def shift_variants(self, x: np.ndarray, wrt: str = "param", p: Optional[np.ndarray] = None):
         """The shifted-circuit batch of src/squlearn/util/optree/optree_derivative.py:130-158.
 
-        For every occurrence of parameter p_j in a gate angle theta_k (linear in p_j): circuits
-        with theta_k +- pi/2 weighted +-1/2 dtheta_k/dp_j (Pauli rotations, p, cp), or the
-        four-term rule for controlled rotations (which the reference reaches by transpiling
-        crx/cry/crz to single-qubit rotations first, :352-370).
-        Returns (gate_index[V], shift[V], weight[V, N], param_index[V]).
+        ``wrt="param"``: for every occurrence of parameter p_j in a gate angle theta_k (linear in p_j): circuits
+        with theta_k +- pi/2 weighted +-1/2 dtheta_k/dp_j (Pauli rotations, p, cp), or the four-term rule for
+        controlled rotations (which the reference reaches by transpiling crx/cry/crz to single-qubit rotations
+        first, :352-370).  ``wrt="x"``: the same shifted circuits for every gate whose angle depends on a
+        feature x_j, weighted with dtheta_k/dx_j (chain rule through the encoding, needs the parameters ``p``).
+        Returns (gate_index[V], shift[V], weight[V, N], index[V]) with index = parameter / feature index.
         """
         two_term = {"rx", "ry", "rz", "p", "cp", "rxx", "ryy", "rzz", "rzx"}
         four_term = {"crx", "cry", "crz"}
         cp_ = (np.sqrt(2.0) + 1.0) / (4.0 * np.sqrt(2.0))
         cm_ = (np.sqrt(2.0) - 1.0) / (4.0 * np.sqrt(2.0))
+        if wrt not in ("param", "x"):
+            raise ValueError("wrt must be 'param' or 'x'")
         gate_idx, shifts, weights, params = [], [], [], []
         for k, g in enumerate(self.gates):
             a = g.angle
-            if a is None or a.param is None:
+            if a is None:
                 continue
-            if a.table is not None:
-                raise NotImplementedError("parameter shift through a general angle callable")
-            fac = a.dtheta_dparam(x, a.param)
+            if wrt == "param":
+                if a.param is None:
+                    continue
+                if a.table is not None:
+                    raise NotImplementedError("parameter shift through a general angle callable")
+                fac, index = a.dtheta_dparam(x, a.param), a.param
+            else:
+                if a.table is not None:
+                    raise NotImplementedError("feature derivative through a general angle callable")
+                if a.feature is None:
+                    continue
+                fac, index = a.dtheta_dfeature(x, p), a.feature
             if g.name in two_term:
                 rule = [(0.5 * np.pi, 0.5), (-0.5 * np.pi, -0.5)]
             elif g.name in four_term:
@@ -185,7 +212,7 @@ class Program:
                 gate_idx.append(k)
                 shifts.append(s)
                 weights.append(w * fac)
-                params.append(a.param)
+                params.append(index)
         if not gate_idx:
             return (np.zeros(0, dtype=np.int32), np.zeros(0), np.zeros((0, x.shape[0])),
                     np.zeros(0, dtype=np.int64))

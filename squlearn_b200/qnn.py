@@ -31,15 +31,15 @@ from .executor import (
 )
 from .observables import ObservableBase
 
-_DIRECT = {"f", "fcc", "dfdp", "dfccdp", "dfdop", "dfccdop"}
+_DIRECT = {"f", "fcc", "dfdp", "dfccdp", "dfdop", "dfccdop", "dfdx", "dfccdx"}
 _POST = {
     "var": ("f", "fcc"), "varf": ("f", "fcc"),
     "dvardp": ("f", "dfccdp", "dfdp"), "dvarfdp": ("f", "dfccdp", "dfdp"),
     "dvardop": ("f", "dfccdop", "dfdop"), "dvarfdop": ("f", "dfccdop", "dfdop"),
 }
-_NOT_YET = {"dfdx", "dfdxdx", "laplace", "laplace_dp", "laplace_dop", "dfdpdp", "dfdopdp",
+_NOT_YET = {"dfdxdx", "laplace", "laplace_dp", "laplace_dop", "dfdpdp", "dfdopdp",
             "dfdpdop", "dfdopdop", "dfdpdx", "dfdxdp", "dfdxdxdp", "dfdxdpdx", "dfdpdxdx",
-            "dfdopdx", "dfdopdxdx", "dfccdx", "dfccdxdx", "dfccdpdp", "dfccdopdx", "dfccdopdop",
+            "dfdopdx", "dfdopdxdx", "dfccdxdx", "dfccdpdp", "dfccdopdx", "dfccdopdop",
             "dvardx", "dvarfdx", "fischer"}
 
 
@@ -104,12 +104,14 @@ class LowLevelQNN:
     def _direct(self, key, x_inp, p, pobs):
         """(N, n_obs[, D]) array for one (param, param_obs) combination."""
         ex = self._executor
-        sq = key in ("fcc", "dfccdp", "dfccdop")
+        sq = key in ("fcc", "dfccdp", "dfccdop", "dfccdx")
         kw = dict(param=p, x=x_inp, param_obs=pobs)
         if key in ("f", "fcc"):
             return ex.b200_execute(b200_evaluate, self._circuit, squared=sq, **kw)
         if key in ("dfdp", "dfccdp"):
             return ex.b200_execute(b200_gradient, self._circuit, squared=sq, **kw)
+        if key in ("dfdx", "dfccdx"):
+            return ex.b200_execute(b200_gradient, self._circuit, squared=sq, wrt="x", **kw)
         if key == "dfdop":
             return ex.b200_execute(b200_operator_gradient, self._circuit, **kw)
         if key == "dfccdop":

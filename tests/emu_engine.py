@@ -1,0 +1,48 @@
+"""TEST INFRASTRUCTURE: an engine stand-in that runs the product's plan + per-thread kernel code on the CPU
+(tests/hostemu), so that the Python host glue of the package (b200_evaluate / b200_gradient /
+LowLevelQNN.evaluate ...) can be exercised by the CPU suite exactly as it runs on the GPU engine.  Never
+imported by the package; not a fallback for anything."""
+
+import numpy as np
+import torch
+
+from squlearn_b200.engine import CompiledProgram
+from squlearn_b200.observables import pauli_masks
+from tests import hostemu
+
+
+class EmuEngine:
+    device = "cpu"
+
+    def compile(self, program, params=None, tile_bits=0):
+        return CompiledProgram(program, params, tile_bits)   # planning is host-only
+
+    def _states(self, cprog, x, variants):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        psi, _ = hostemu.simulate(cprog.program, cprog.params, x, variants=variants)
+        return psi
+
+    def simulate(self, cprog, x, variants=None):
+        return torch.from_numpy(self._states(cprog, x, variants))
+
+    def simulate_expvals(self, cprog, x, terms, variants=None):
+        n = cprog.program.num_qubits
+        psi = self._states(cprog, x, variants)
+        masks = [pauli_masks(t) for t in terms]
+        out = hostemu.expvals(psi.reshape(-1, 1 << n), n, [m[0] for m in masks], [m[1] for m in masks])
+        return torch.from_numpy(out.reshape(psi.shape[:-1] + (len(terms),)))
+
+
+class EmuExecutor:
+    """The slice of squlearn_b200.Executor the QNN / kernel glue uses."""
+    quantum_framework = "b200"
+    shots = None
+
+    def __init__(self):
+        self.engine = EmuEngine()
+
+    def set_shots(self, shots):
+        self.shots = shots
+
+    def b200_execute(self, fn, circuit, **kwargs):
+        return fn(circuit, executor=self, **kwargs)

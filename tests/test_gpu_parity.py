@@ -358,7 +358,7 @@ def test_qnn_goldens_and_gradients(sq, executor, goldens, regression_data):
     single = qnn.evaluate(Xb[0], p, pop, "f")["f"]
     assert single.shape == (2,) and np.allclose(single, w["f"][0])
     with pytest.raises(NotImplementedError):
-        qnn.evaluate(Xb[:2], p, pop, "dfdx")
+        qnn.evaluate(Xb[:2], p, pop, "dfdxdx")
 
 
 def test_optree_gradient_golden_through_the_product(sq, executor, goldens):
@@ -439,3 +439,35 @@ def test_qkrr_device_solver_matches_scipy(sq, executor):
     assert np.max(np.abs(model.dual_coeff_ - c)) < 1e-6 * np.max(np.abs(c))
     want = oracle.fidelity_kernel(gates, n, Xt, X, p) @ c
     assert np.max(np.abs(model.predict(Xt) - want)) < 1e-7
+
+
+# ------------------------------------------------------------------------------ next row f3: d/dx (first order)
+def test_input_derivative_golden_and_finite_differences(sq, executor, goldens):
+    """The reference's d/dx golden (tests/util/optree/test_optree_derivative.py:49-96) and "dfdx" of a QNN
+    against central differences; same shifted-variant batch as dfdp, chain-rule weights of the encodings."""
+    g = goldens["optree_gradient"]
+    A = sq.Angle
+    prog = sq.Program(2, [
+        sq.GateOp("rx", (0,), A(param=0, feature=0)), sq.GateOp("rx", (1,), A(param=1, feature=0)),
+        sq.GateOp("ry", (0,), A(param=2)), sq.GateOp("ry", (1,), A(param=3)),
+        sq.GateOp("rxx", (0, 1), A(param=0, feature=0))], 4, 1)
+    circ = sq.B200Circuit(prog, sq.CustomObservable(2, g["observable"]))
+    dx = executor.b200_execute(sq.b200_gradient, circ, param=np.array(g["p"]), x=np.array([[g["x"]]]), wrt="x")
+    assert np.allclose(dx[0, 0], g["reference_dx"])
+    n, d = 5, 2
+    rng = np.random.default_rng(12)
+    X = rng.uniform(-0.8, 0.8, (6, d))
+    enc = sq.ChebyshevPQC(n, 2)
+    p = rng.uniform(-1, 1, enc.num_parameters)
+    pop = rng.uniform(-1, 1, n + 1)
+    qnn = sq.LowLevelQNN(enc, sq.SummedPaulis(n), executor, d)
+    got = qnn.evaluate(X, p, pop, "dfdx")["dfdx"]
+    assert got.shape == (6, d)
+    gates = oracle.chebyshev_pqc(n, 2, d)
+    h = 1e-6
+    for j in range(d):
+        e = np.zeros(d)
+        e[j] = h
+        fp = oracle.qnn_evaluate(gates, n, X + e, p, ("summed_paulis", {}), pop, ("f",))["f"]
+        fm = oracle.qnn_evaluate(gates, n, X - e, p, ("summed_paulis", {}), pop, ("f",))["f"]
+        assert np.max(np.abs(got[:, j] - (fp - fm) / (2 * h))) < 1e-7
