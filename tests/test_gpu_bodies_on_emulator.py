@@ -1,0 +1,19 @@
+"""CPU run of the bodies of GPU parity tests whose device work is only statevector simulation + Pauli
+expectation values: the same assertions, with the emulator engine (tests/emu_engine.py) in place of the CUDA
+engine.  Covers the Python host glue (QNN value / gradient assembly, reference goldens) without a GPU."""
+
+import squlearn_b200 as sq
+from tests import test_gpu_parity as gpu_tests
+from tests.emu_engine import EmuExecutor
+
+
+def test_qnn_goldens_and_gradients_on_emulator(goldens, regression_data):
+    gpu_tests.test_qnn_goldens_and_gradients(sq, EmuExecutor(), goldens, regression_data)
+
+
+def test_optree_gradient_golden_on_emulator(goldens):
+    gpu_tests.test_optree_gradient_golden_through_the_product(sq, EmuExecutor(), goldens)
+
+
+def test_input_derivative_on_emulator(goldens):
+    gpu_tests.test_input_derivative_golden_and_finite_differences(sq, EmuExecutor(), goldens)
