@@ -33,6 +33,36 @@ class EmuEngine:
         return torch.from_numpy(out.reshape(psi.shape[:-1] + (len(terms),)))
 
 
+    # --- consumers of the states: plain NumPy stand-ins of the Gram / RBF kernels (the CUDA kernels have
+    # their own parity tests; here only the host glue around them is under test)
+    def gram(self, psi_x, psi_y=None, diagonal="one", out=None, **_):
+        a = psi_x.numpy()
+        if psi_y is None:
+            k = np.abs(a.conj() @ a.T) ** 2
+            k = np.tril(k) + np.tril(k, -1).T
+            if diagonal == "one":
+                np.fill_diagonal(k, 1.0)
+            elif diagonal == "zero":
+                np.fill_diagonal(k, 0.0)
+        else:
+            k = np.abs(a.conj() @ psi_y.numpy().T) ** 2
+        return torch.from_numpy(k)
+
+    def rbf(self, fx, fy, gamma):
+        fx, fy = np.asarray(fx, dtype=np.float64), np.asarray(fy, dtype=np.float64)
+        d2 = ((fx[:, None, :] - fy[None, :, :]) ** 2).sum(axis=2)
+        return torch.from_numpy(np.exp(-gamma * d2))
+
+    def to_host(self, t):
+        return t.numpy().copy()
+
+    def to_device(self, a, dtype=None):
+        return torch.as_tensor(np.asarray(a))
+
+    def launch_count(self):
+        return 0
+
+
 class EmuExecutor:
     """The slice of squlearn_b200.Executor the QNN / kernel glue uses."""
     quantum_framework = "b200"

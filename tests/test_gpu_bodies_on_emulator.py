@@ -17,3 +17,19 @@ def test_optree_gradient_golden_on_emulator(goldens):
 
 def test_input_derivative_on_emulator(goldens):
     gpu_tests.test_input_derivative_golden_and_finite_differences(sq, EmuExecutor(), goldens)
+
+
+def test_qrc_and_highdim_goldens_on_emulator(goldens, regression_data):
+    gpu_tests.test_qrc_and_highdim_goldens(sq, EmuExecutor(), goldens, regression_data)
+
+
+def test_closed_form_kernel_goldens_on_emulator(goldens):
+    gpu_tests.test_closed_form_goldens_through_the_product(sq, EmuExecutor(), goldens)
+
+
+def test_fidelity_kernel_c1_and_duplicate_policies_on_emulator():
+    gpu_tests.test_fidelity_kernel_config_c1_and_duplicate_policies(sq, EmuExecutor())
+
+
+def test_projected_quantum_kernel_c2_on_emulator():
+    gpu_tests.test_projected_quantum_kernel_config_c2(sq, EmuExecutor())
