@@ -28,6 +28,7 @@ from .program import Angle, GateOp, Program
 from .qgpr import QGPR
 from .qkrr import QKRR
 from .qnn import LowLevelQNN
+from .qsvc import QSVC
 from .qrc import QRCRegressor, QRCClassifier, random_pauli_list
 
 __version__ = "0.1.0"
@@ -38,5 +39,5 @@ __all__ = [
     "LayeredEncodingCircuit", "EncodingCircuitBase", "SinglePauli", "SummedPaulis",
     "CustomObservable", "Program", "GateOp", "Angle", "QRCRegressor", "QRCClassifier",
     "random_pauli_list", "b200_evaluate", "b200_evaluate_statevector", "b200_gradient",
-    "b200_operator_gradient", "QKRR", "QGPR", "TargetAlignment", "NLL", "KernelOptimizer", "ScipyMinimize",
+    "b200_operator_gradient", "QKRR", "QGPR", "QSVC", "TargetAlignment", "NLL", "KernelOptimizer", "ScipyMinimize",
 ]

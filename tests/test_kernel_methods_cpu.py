@@ -148,3 +148,29 @@ def test_kernel_optimizer_lowers_the_loss_and_assigns_the_optimum():
     assert opt.is_fitted and np.allclose(kern.parameters, res.x) and np.allclose(opt.get_optimal_parameters(), res.x)
     assert res.fun <= start + 1e-12
     assert opt.run_optimization(X, labels) is None          # already fitted (kernel_optimizer.py:66-67)
+
+
+def test_qsvc_config_c1_matches_sklearn_on_the_oracle_kernel():
+    """BASELINE configs[0]: FidelityKernel + QSVC, ChebyshevPQC(4 qubits, 2 layers), 100 synthetic points with
+    labels sign(x0 * x1) — through the real FidelityKernel glue on the emulator engine."""
+    from sklearn.svm import SVC
+
+    import squlearn_b200 as sq
+    from tests.emu_engine import EmuExecutor
+
+    n, d = 4, 2
+    X = np.random.default_rng(1).uniform(-0.95, 0.95, (100, d))
+    y = np.sign(X[:, 0] * X[:, 1]).astype(int)
+    Xt = np.random.default_rng(2).uniform(-0.95, 0.95, (30, d))
+    fk = sq.FidelityKernel(sq.ChebyshevPQC(n, 2), EmuExecutor())
+    model = sq.QSVC(fk, C=2.0).fit(X, y)
+    gates = oracle.chebyshev_pqc(n, 2, d)
+    p = oracle.chebyshev_pqc_initial_parameters(n, 2, d, seed=0)
+    ref = SVC(kernel="precomputed", C=2.0).fit(oracle.fidelity_kernel(gates, n, X, None, p), y)
+    k_test = oracle.fidelity_kernel(gates, n, Xt, X, p)
+    assert np.array_equal(model.predict(Xt), ref.predict(k_test))
+    assert np.max(np.abs(model.decision_function(Xt) - ref.decision_function(k_test))) < 1e-8
+    assert model.get_params()["C"] == 2.0 and model.get_params()["quantum_kernel"] is fk
+    pre = sq.QSVC("precomputed").fit(oracle.fidelity_kernel(gates, n, X, None, p), y)
+    assert np.array_equal(pre.predict(k_test), sq.QSVC("precomputed", C=1.0).fit(
+        oracle.fidelity_kernel(gates, n, X, None, p), y).predict(k_test))
