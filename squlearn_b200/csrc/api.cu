@@ -275,7 +275,9 @@ int b200sq_program_create(int n_qubits, int n_gates, const b200sq_gate* gates, i
             if (x.fn == B200SQ_FN_TABLE && x.slot < 0) return fail(2, "negative angle-table slot");
         }
         b200sq_program* p = new b200sq_program();
-        p->plan = make_plan(n_qubits, g, tile_bits);
+        // B200SQ_ROT_LIFT=1: rx / ry layer steps by in-place lifted rotations (experimental, default off)
+        const char* lift = getenv("B200SQ_ROT_LIFT");
+        p->plan = make_plan(n_qubits, g, tile_bits, 4, true, lift && lift[0] == '1');
         for (size_t ip = 0; ip < p->plan.passes.size(); ++ip) p->blobs.push_back(build_pass_blob(p->plan, (int)ip));
         *out = p;
         return 0;

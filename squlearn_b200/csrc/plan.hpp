@@ -124,7 +124,7 @@ inline int rank_in(uint32_t set, int q) { return popc(set & ((1u << q) - 1u)); }
 // low_bits: number of lowest qubits every tile must contain (keeps global accesses in
 // contiguous runs of 2^low_bits * 16 bytes).
 inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_bits,
-                      int low_bits = 4, bool fold_prefix = true) {
+                      int low_bits = 4, bool fold_prefix = true, bool lift_rotations = false) {
     using namespace detail;
     if (n < 1 || n > B200SQ_MAX_QUBITS) throw std::invalid_argument("n_qubits out of range");
     Plan plan;
@@ -369,14 +369,19 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                         plan.steps.push_back(st);
                         continue;
                     }
-                    const int fam = g.kind == B200SQ_RX ? ST_LRX
+                    // rotation by lifting needs a carrier for the accumulated sign: the product table of a pass
+                    // with fresh qubits (see MAT_ROT)
+                    const bool lift = lift_rotations && fresh != 0 && (g.kind == B200SQ_RX || g.kind == B200SQ_RY);
+                    const int fam = lift ? (g.kind == B200SQ_RX ? ST_LROTX : ST_LROTY)
+                                  : g.kind == B200SQ_RX ? ST_LRX
                                   : (g.kind == B200SQ_RY || g.kind == B200SQ_H || g.kind == B200SQ_X) ? ST_LREAL
                                   : ST_LGEN;
+                    const int mkind = lift ? MAT_ROT : MAT_U1;
                     if (layer_step >= 0 && plan.steps[layer_step].kind == fam &&
                         !(plan.steps[layer_step].r0 >> slot & 1)) {
                         Step& st = plan.steps[layer_step];
                         st.r0 |= 1 << slot;
-                        MatRec mr{gi, MAT_U1, 0, st.mat + 4 * slot};
+                        MatRec mr{gi, mkind, 0, st.mat + 4 * slot};
                         plan.mats.push_back(mr);
                     } else {
                         Step st;
@@ -386,7 +391,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                         st.r0 = 1 << slot;
                         st.mat = mat_off;
                         mat_off += 12;  // one 2x2 per register slot
-                        MatRec mr{gi, MAT_U1, 0, st.mat + 4 * slot};
+                        MatRec mr{gi, mkind, 0, st.mat + 4 * slot};
                         plan.mats.push_back(mr);
                         layer_step = (int)plan.steps.size();
                         plan.steps.push_back(st);

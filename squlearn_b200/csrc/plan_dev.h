@@ -29,8 +29,12 @@ enum StepKind : int32_t {
     ST_LREAL = 7,   // real 2x2 (ry, h, x)
     ST_LGEN = 8,    // general complex 2x2 (y, sx, u)
     ST_DTAB = 9,    // a[k] *= table[(local_index >> r0) & ((1 << r1) - 1)], table at mat
+    ST_LROTX = 10,  // rx as two in-place lifted 2-D rotations per amplitude pair (3 FMAs each), slot mask r0
+    ST_LROTY = 11,  // ry, idem
 };
-enum MatKind : int32_t { MAT_U1 = 0, MAT_U2 = 1, MAT_DIAG = 2 };
+// MAT_ROT: m[0] = (tan(a'/2), sin a'), m[1].x = k mod 2 for a = theta/2 = a' + k pi, |a'| <= pi/2.  The lifted
+// rotation applies R(a'); the signs (-1)^k of all MAT_ROT gates of a pass multiply into the product table.
+enum MatKind : int32_t { MAT_U1 = 0, MAT_U2 = 1, MAT_DIAG = 2, MAT_ROT = 3 };
 
 constexpr int kMaxRuns = 8;
 constexpr int kMaxTileBits = 13;

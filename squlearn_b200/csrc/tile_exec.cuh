@@ -59,6 +59,15 @@ B200SQ_HD void build_matrix(int mkind, int swap, const b200sq_gate& g, double th
     const double kInvSqrt2 = 0.70710678118654752440;
     double s, c;
     sincos(0.5 * theta, &s, &c);
+    if (mkind == MAT_ROT) {  // rx / ry by lifting: a = theta / 2 = a' + k pi with |a'| <= pi / 2
+        const double kPi = 3.14159265358979323846;
+        const double a = 0.5 * theta;
+        const double k = rint(a / kPi);
+        const double ar = fma(-k, kPi, a);
+        m[0] = double2{tan(0.5 * ar), sin(ar)};
+        m[1] = double2{fabs(fmod(k, 2.0)), 0.0};
+        return;
+    }
     if (mkind == MAT_DIAG) {
         double2 one{1.0, 0.0};
         double2 em{c, -s}, ep{c, s};  // e^{-i theta/2}, e^{+i theta/2}
@@ -282,8 +291,13 @@ B200SQ_HD void build_mats_thread(const PassView& pv, const TeamMem& tm, const It
 B200SQ_HD void build_tables_thread(const PassView& pv, const TeamMem& tm, const ItemCtx& ic, int tid, int TS,
                                    bool new_sample) {
     const DPass& P = *pv.P;
+    // sign (-1)^(sum k) of the lifted rotations of this pass (MAT_ROT), carried by the low product table
+    double rot_sign = 1.0;
+    if (new_sample && P.nlo > 0)
+        for (int i = 0; i < P.n_mats; ++i)
+            if (pv.mats[i].kind == MAT_ROT && tm.mats[pv.mats[i].mat + 1].x != 0.0) rot_sign = -rot_sign;
     for (int t = tid; t < (1 << P.nlo) && P.nlo > 0 && new_sample; t += TS) {
-        double2 r{1.0, 0.0};
+        double2 r{rot_sign, 0.0};
         for (int b = 0; b < P.nlo; ++b) r = cmul(r, tm.qv[2 * b + ((t >> b) & 1)]);
         tm.plo[t] = r;
     }
@@ -404,6 +418,43 @@ B200SQ_HD void u1_real(double2 (&a)[G][1 << NB], const double2* __restrict__ m) 
         }
 }
 
+// In-place 2-D rotation [[c, s], [-s, c]] by lifting: three FMAs, no temporaries (t = tan(a/2), S = sin a).
+B200SQ_HD void rot2(double& x, double& y, double t, double S) {
+    x = fma(t, y, x);
+    y = fma(-S, x, y);
+    x = fma(t, y, x);
+}
+
+// rx(theta) = [[c, -i s], [-i s, c]]: rotates (re0, im1) and (re1, im0)
+template <int NB, int R, int G>
+B200SQ_HD void u1_rotx(double2 (&a)[G][1 << NB], const double2* __restrict__ m) {
+    const double t = m[0].x, S = m[0].y;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+        for (int k0 = 0; k0 < (1 << NB); ++k0) {
+            if (k0 & (1 << R)) continue;
+            const int k1 = k0 | (1 << R);
+            rot2(a[gi][k0].x, a[gi][k1].y, t, S);
+            rot2(a[gi][k1].x, a[gi][k0].y, t, S);
+        }
+}
+
+// ry(theta) = [[c, -s], [s, c]]: rotates (re1, re0) and (im1, im0)
+template <int NB, int R, int G>
+B200SQ_HD void u1_roty(double2 (&a)[G][1 << NB], const double2* __restrict__ m) {
+    const double t = m[0].x, S = m[0].y;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+        for (int k0 = 0; k0 < (1 << NB); ++k0) {
+            if (k0 & (1 << R)) continue;
+            const int k1 = k0 | (1 << R);
+            rot2(a[gi][k1].x, a[gi][k0].x, t, S);
+            rot2(a[gi][k1].y, a[gi][k0].y, t, S);
+        }
+}
+
 template <int NB, int R, int G>
 B200SQ_HD void u1_ctrl(double2 (&a)[G][1 << NB], const double2* __restrict__ m, const uint32_t (&e)[G],
                        const uint32_t (&ko)[1 << NB], uint32_t cm) {
@@ -486,6 +537,8 @@ B200SQ_HD void apply_step(double2 (&a)[G][1 << NB], const DStep& u, const double
         case ST_LRX: B200SQ_LAYER(u1_rx) break;
         case ST_LREAL: B200SQ_LAYER(u1_real) break;
         case ST_LGEN: B200SQ_LAYER(u1_general) break;
+        case ST_LROTX: B200SQ_LAYER(u1_rotx) break;
+        case ST_LROTY: B200SQ_LAYER(u1_roty) break;
         case ST_DTAB: dtab_apply<NB, G>(a, u, m, base, ko); break;
         case ST_DIAG: diag_apply<NB, G>(a, u, m, e, ko); break;
         case ST_U1CTRL:

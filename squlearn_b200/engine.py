@@ -77,7 +77,7 @@ class CompiledProgram:
         rounds = [tuple(int(v) for v in w[pos + 6 * i: pos + 6 * i + 6]) for i in range(n_rounds)]
         pos += 6 * n_rounds
         steps = [tuple(int(v) for v in w[pos + 7 * i: pos + 7 * i + 7]) for i in range(n_steps)]
-        cost = {6: 4.0, 7: 4.0, 8: 8.0}   # layer steps: per active register slot
+        cost = {6: 4.0, 7: 4.0, 8: 8.0, 10: 3.0, 11: 3.0}   # layer steps: per active register slot
         out = []
         for Tp, a_in, r0, r1, nfresh, tile_mask in passes:
             per_amp = 0.0

@@ -5,6 +5,7 @@
 // the squlearn_b200 package, and is not a fallback for anything.
 #include <cstdint>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -31,7 +32,8 @@ __attribute__((visibility("default"))) int hostemu_simulate(
     double* psi_out, int team_size) {
     try {
         std::vector<b200sq_gate> g(gates, gates + n_gates);
-        Plan pl = make_plan(n, g, tile_bits);
+        const char* lift = getenv("B200SQ_ROT_LIFT");
+        Plan pl = make_plan(n, g, tile_bits, 4, true, lift && lift[0] == '1');
         double2* psi = reinterpret_cast<double2*>(psi_out);
         const int TS = team_size;
         int log2ts = 0;

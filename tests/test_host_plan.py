@@ -262,3 +262,23 @@ def test_long_two_qubit_circuits_split_into_passes_that_fit_shared_memory():
             pos += 11 + w[pos]
     finally:
         lib.b200sq_program_destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lifted_rotations_option(seed, monkeypatch):
+    """B200SQ_ROT_LIFT=1 (experimental, default off): rx / ry layer steps as in-place lifted rotations
+    (3 FMAs per 2-D rotation), the signs of the angle reduction carried by the product table.  Large angles
+    exercise the sign flips."""
+    monkeypatch.setenv("B200SQ_ROT_LIFT", "1")
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.integers(3, 10))
+    tile_bits = int(rng.integers(3, n + 1))
+    prog, ogates = random_circuit(n, 50, 5, 3, rng, kinds=["rx", "ry", "rx", "ry", "rz", "crz", "cz", "h", "cx", "rzz", "p"])
+    X = rng.uniform(-0.9, 0.9, (2, 3))
+    p = rng.uniform(-9, 9, 5)
+    got, _ = hostemu.simulate(prog, p, X, tile_bits=tile_bits, team_size=32)
+    assert np.max(np.abs(got - oracle.simulate(ogates, n, X, p))) < TOL
+    enc = ChebyshevPQC(9, 2)
+    pp = enc.generate_initial_parameters(3, seed=0)
+    got, _ = hostemu.simulate(enc.get_program(3), pp, X, tile_bits=5)
+    assert np.max(np.abs(got - oracle.simulate(oracle.chebyshev_pqc(9, 2, 3), 9, X, pp))) < TOL
