@@ -36,7 +36,7 @@ extern "C" {
 #define B200SQ_API
 #endif
 
-#define B200SQ_ABI_VERSION 1
+#define B200SQ_ABI_VERSION 2
 #define B200SQ_MAX_QUBITS 26
 
 /* Gate vocabulary = the reference's gate table
@@ -162,7 +162,9 @@ B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_
 
 /* The two halves of the B200SQ_GRAM_INT8 path, for callers that reuse or exchange the digit planes (the
  * multi-GPU Gram sends planes, not complex128 states: 12 instead of 16 bytes per amplitude, sliced once).
- *   planes  [12][plane_rows][2 * dim] int8: planes 0..5 = digits of (re, im), 6..11 = digits of (im, -re)
+ *   planes  [12][plane_rows][2 * dim] int8: planes 0..5 = digits of nat = (re, im), 6..11 = digits of
+ *           rot = (-im, re).  Re<x|y> = nat(x).nat(y), Im<x|y> = rot(x).nat(y): the ROW operand uses all 12
+ *           planes, the COLUMN operand only planes 0..5 (a column block may be a [6][rows][2 * dim] buffer).
  *   expo    [plane_rows] int32: power-of-two scale of every row
  * b200sq_gram_slice writes rows [row0, row0 + N) of the planes from N states; b200sq_gram_from_planes
  * computes K[i][j] = |<x_{x0+i} | y_{y0+j}>|^2 for Nx x Ny rows of the two plane sets (flags as b200sq_gram). */
@@ -173,6 +175,46 @@ B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* 
                                        int64_t x0, int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev,
                                        int64_t plane_rows_y, int64_t y0, int64_t Ny, int64_t dim, double* K_dev,
                                        int64_t ldk, uint32_t flags, void* stream);
+
+/* Several Gram blocks that share the row operand, in ONE persistent launch (the multi-GPU Gram: the diagonal
+ * block of a rank plus every block it owns against received column planes; there is no reference counterpart,
+ * the reference evaluates the pair loop of fidelity_kernel_statevector.py:358-383 on one host).
+ *   ready_flag_dev / ready_value   optional: the job's column planes are complete when *ready_flag_dev >=
+ *           ready_value (a uint32 in device memory written by whoever delivers the planes, e.g. a peer GPU's
+ *           copy engine after its push); the kernel starts the job's tiles when it observes the flag, so blocks
+ *           are multiplied while later ones are still in flight.  The writer must be independent of this stream.
+ *   align_*                        optional, fused into the |.|^2 epilogue (kernel target alignment,
+ *           src/squlearn/kernel/loss/target_alignment.py:75-90): with row labels yx[i] (i < nx) and column
+ *           labels yy[j] (j < ny) of THIS block, align_out[0] += w * sum_ij K_ij yx_i yy_j and
+ *           align_out[1] += w * sum_ij K_ij^2, so a training step never re-reads K.  For a symmetric block the
+ *           mirrored off-diagonal entries are counted (w = 1 on the diagonal tiles' entries, 2 elsewhere);
+ *           for a rectangular block w = align_weight (2 when the block also stands for its transpose).     */
+typedef struct b200sq_gram_job {
+    int64_t x0, nx;                 /* rows [x0, x0 + nx) of the row planes                              */
+    const void* planes_y_dev;       /* column planes ([>= 6][plane_rows_y][2 * dim] int8)                */
+    const int32_t* expo_y_dev;
+    int64_t plane_rows_y, y0, ny;
+    double* K_dev;                  /* [nx][ldk]                                                         */
+    int64_t ldk;
+    uint32_t flags;                 /* B200SQ_GRAM_SYMMETRIC | DIAG_* (symmetric: column planes == row planes, y0 == x0) */
+    uint32_t ready_value;
+    const uint32_t* ready_flag_dev; /* NULL: no wait                                                     */
+    const double* align_yx_dev;     /* NULL: no reduction                                                */
+    const double* align_yy_dev;
+    double* align_out_dev;          /* [2] float64, accumulated with atomics (zero it first)             */
+    double align_weight;
+} b200sq_gram_job;
+B200SQ_API int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
+                                int64_t dim, int n_jobs, const b200sq_gram_job* jobs, void* stream);
+
+/* Peer plumbing of the multi-GPU Gram (one process per GPU): export a device allocation to the other ranks of
+ * the box (CUDA IPC), open a peer's export, and enqueue copy-engine copies (device-to-device, local or into a
+ * peer mapping over NVLink) on a stream.  b200sq_ipc_export returns the 64-byte handle of the ALLOCATION that
+ * contains dev_ptr and the offset of dev_ptr inside it; the peer adds the offset to the base it opens.   */
+B200SQ_API int b200sq_ipc_export(const void* dev_ptr, void* handle_out_64, int64_t* offset_out);
+B200SQ_API int b200sq_ipc_open(const void* handle_64, void** base_out);
+B200SQ_API int b200sq_ipc_close(void* base);
+B200SQ_API int b200sq_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 
 /* Gaussian outer kernel of the projected quantum kernel: K[i][j] = exp(-gamma |F_x[i]-F_y[j]|^2)
  * (src/squlearn/kernel/lowlevel_kernel/projected_quantum_kernel.py:945-973).

@@ -52,11 +52,26 @@ class Gate(ctypes.Structure):
     ]
 
 
+class GramJob(ctypes.Structure):
+    """struct b200sq_gram_job (include/b200sq.h)."""
+    _fields_ = [
+        ("x0", ctypes.c_int64), ("nx", ctypes.c_int64),
+        ("planes_y_dev", ctypes.c_void_p), ("expo_y_dev", ctypes.c_void_p),
+        ("plane_rows_y", ctypes.c_int64), ("y0", ctypes.c_int64), ("ny", ctypes.c_int64),
+        ("K_dev", ctypes.c_void_p), ("ldk", ctypes.c_int64),
+        ("flags", ctypes.c_uint32), ("ready_value", ctypes.c_uint32),
+        ("ready_flag_dev", ctypes.c_void_p),
+        ("align_yx_dev", ctypes.c_void_p), ("align_yy_dev", ctypes.c_void_p),
+        ("align_out_dev", ctypes.c_void_p), ("align_weight", ctypes.c_double),
+    ]
+
+
 EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_expvals", "b200sq_expvals",
-    "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_rbf",
+    "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
+    "b200sq_copy_async", "b200sq_rbf",
     "b200sq_launch_count",
 ]
 
@@ -111,9 +126,19 @@ def load():
     lib.b200sq_gram_slice.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp]
     lib.b200sq_gram_from_planes.restype = c.c_int
     lib.b200sq_gram_from_planes.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, i64, vp, i64, c.c_uint32, vp]
+    lib.b200sq_gram_jobs.restype = c.c_int
+    lib.b200sq_gram_jobs.argtypes = [vp, vp, i64, i64, c.c_int, c.POINTER(GramJob), vp]
+    lib.b200sq_ipc_export.restype = c.c_int
+    lib.b200sq_ipc_export.argtypes = [vp, c.c_char_p, c.POINTER(i64)]
+    lib.b200sq_ipc_open.restype = c.c_int
+    lib.b200sq_ipc_open.argtypes = [c.c_char_p, c.POINTER(vp)]
+    lib.b200sq_ipc_close.restype = c.c_int
+    lib.b200sq_ipc_close.argtypes = [vp]
+    lib.b200sq_copy_async.restype = c.c_int
+    lib.b200sq_copy_async.argtypes = [vp, vp, c.c_size_t, vp]
     lib.b200sq_rbf.restype = c.c_int
     lib.b200sq_rbf.argtypes = [vp, i64, vp, i64, c.c_int, dbl, vp, i64, vp]
-    if lib.b200sq_abi_version() != 1:
+    if lib.b200sq_abi_version() != 2:
         raise RuntimeError("libb200sq.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

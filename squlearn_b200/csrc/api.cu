@@ -462,6 +462,91 @@ int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev,
     return 0;
 }
 
+int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x, int64_t dim,
+                     int n_jobs, const b200sq_gram_job* jobs, void* stream_) {
+    if (!planes_x_dev || !expo_x_dev || (n_jobs > 0 && !jobs)) return fail(2, "NULL argument");
+    if (n_jobs < 0 || plane_rows_x < 0) return fail(2, "bad sizes");
+    if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
+    for (int j = 0; j < n_jobs; ++j) {
+        const b200sq_gram_job& J = jobs[j];
+        if (!J.planes_y_dev || !J.expo_y_dev || !J.K_dev) return fail(2, "NULL pointer in a Gram job");
+        if (J.nx < 0 || J.ny < 0 || J.x0 < 0 || J.y0 < 0 || J.x0 + J.nx > plane_rows_x || J.y0 + J.ny > J.plane_rows_y ||
+            J.ldk < J.ny)
+            return fail(2, "bad sizes in a Gram job");
+        if ((J.flags & B200SQ_GRAM_SYMMETRIC) && (J.planes_y_dev != planes_x_dev || J.x0 != J.y0 || J.nx != J.ny))
+            return fail(2, "symmetric Gram job needs identical operands");
+        if (J.align_yx_dev && !J.align_out_dev) return fail(2, "align_out_dev is NULL");
+    }
+    int e = launch_gram_jobs((const int8_t*)planes_x_dev, expo_x_dev, plane_rows_x, dim, n_jobs, jobs,
+                             (cudaStream_t)stream_);
+    if (e) return cuda_fail(e, "gram launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
+int b200sq_ipc_export(const void* dev_ptr, void* handle_out_64, int64_t* offset_out) {
+    if (!dev_ptr || !handle_out_64 || !offset_out) return fail(2, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    // the handle names the whole allocation: find its base (driver API through the runtime's entry-point query)
+    typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    static GetRangeFn get_range = nullptr;
+    if (!get_range) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess || !p)
+            return fail(6, "cuMemGetAddressRange is unavailable");
+        get_range = (GetRangeFn)p;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0 || !base)
+        return fail(6, "cuMemGetAddressRange failed (not a device allocation?)");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "cudaIpcGetMemHandle (allocation not exportable: pool / expandable-segment memory?)");
+    }
+    std::memcpy(handle_out_64, &h, 64);
+    *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return 0;
+}
+
+int b200sq_ipc_open(const void* handle_64, void** base_out) {
+    if (!handle_64 || !base_out) return fail(2, "NULL argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle_64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "cudaIpcOpenMemHandle");
+    }
+    *base_out = p;
+    return 0;
+}
+
+int b200sq_ipc_close(void* base) {
+    if (!base) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(base);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "cudaIpcCloseMemHandle");
+    }
+    return 0;
+}
+
+int b200sq_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream_) {
+    if (bytes == 0) return 0;
+    if (!dst_dev || !src_dev) return fail(2, "NULL argument");
+    cudaError_t e = cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "cudaMemcpyAsync (device to device)");
+    }
+    return 0;
+}
+
 int b200sq_rbf(const double* fx_dev, int64_t Nx, const double* fy_dev, int64_t Ny, int nf, double gamma,
                double* K_dev, int64_t ldk, void* stream_) {
     if (!fx_dev || !fy_dev || !K_dev) return fail(2, "NULL argument");

@@ -16,12 +16,19 @@
 // scales (measured |K - K_fp64| ~ 1e-13 .. 1e-11, see DESIGN.md for the bound).
 //
 // Complex arithmetic without data rearrangement in the GEMM: a state row is the real vector
-// (re_0, im_0, re_1, im_1, ...), K' = 2 * dim.  With  nat(y) = (yr_k, yi_k)  and  rot(y) = (yi_k, -yr_k):
-//        Re <x|y> = x . nat(y),     Im <x|y> = x . rot(y)
-// so one A tile feeds two accumulators through two B tiles (digit planes of y and of rot(y)).
+// (re_0, im_0, re_1, im_1, ...), K' = 2 * dim.  With  nat(v) = (vr_k, vi_k)  and  rot(v) = (-vi_k, vr_k):
+//        Re <x|y> = nat(x) . nat(y),     Im <x|y> = rot(x) . nat(y)
+// so ONE B tile (digit plane of nat(y)) feeds two accumulators through two A tiles (digit planes of nat(x) and
+// rot(x)): the column operand only needs its 6 nat planes, which is what the multi-GPU exchange sends.
 //
-// Kernel k_gram_i8 (one CTA per SM, persistent over work units = (128 x 128 tile, 16 KiB K-chunk)):
-//   warp 0    TMA producer: 3 x 16 KiB boxes (A_i, Bnat_j, Brot_j; 128 rows x 128 B, SWIZZLE_128B) per stage
+// JOB TABLE.  One launch covers several Gram blocks ("jobs") that share the local row operand: job j multiplies
+// rows [x0, x0 + nx) of the local planes with rows [y0, y0 + ny) of its own column planes (the local planes for
+// the diagonal block, a received block otherwise) and writes its own K pointer.  A job may carry a READY FLAG:
+// its work units start when *flag >= value, so blocks that are still being copied in by the copy engines
+// (peer pushes over NVLink) are multiplied as they land, inside the same persistent kernel.
+//
+// Kernel k_gram_i8 (one CTA per SM, persistent over work units = (tile, K-chunk), job-major order):
+//   warp 0    TMA producer: 3 x 16 KiB boxes (Anat_i, Arot_i, Bnat_j; 128 rows x 128 B, SWIZZLE_128B) per stage
 //   warp 1    MMA issuer:   8 x tcgen05.mma.kind::i8 (M = N = 128, K = 32) per stage into TMEM (s32)
 //   warp 2    TMEM allocator (512 columns: 2 accumulator stages x (Re 128 + Im 128))
 //   warps 4-7 epilogue: tcgen05.ld -> int32 -> double * 2^(-8 c) -> red.add.f64 into the per-tile FP64
@@ -60,15 +67,41 @@ struct I8Schedule {
     uint8_t pi[kMaxClasses][kMaxPairs], pj[kMaxClasses][kMaxPairs];
 };
 
+constexpr int kMaxJobs = 12;
+
+struct I8Job {
+    int64_t row0_a;           // first row of the job's row operand inside the local planes
+    int64_t row0_b, rows_b;   // first row / rows per digit plane of the column operand
+    int64_t ldk;
+    double* K;                // [nx][ldk]
+    const int* ex;            // row exponents of the local planes, of the column planes
+    const int* ey;
+    const uint32_t* ready;    // nullptr, or: the column planes are complete when *ready >= ready_value
+    const double* align_yx;   // nullptr, or row / column labels: align_out[0] += w sum K_ij yx_i yy_j,
+    const double* align_yy;   //                                   align_out[1] += w sum K_ij^2
+    double* align_out;
+    double align_weight;
+    uint32_t ready_value;
+    uint32_t flags;           // B200SQ_GRAM_* of this block
+    int32_t nx, ny;
+    int32_t tiles_n, tile0, n_tiles, symmetric;
+    int32_t map_b;            // which tensor map holds the column planes
+    int32_t pad_;
+};
+
 struct I8Args {
-    int64_t rows_a, rows_b;   // rows per digit plane of the A / B operand
-    int64_t row0_a, row0_b;   // first row of the operand inside its planes
+    int64_t rows_a;           // rows per digit plane of the local (row) operand
     int kbytes;               // K' = 2 * dim bytes per row
     int n_chunks, chunk_bytes;
-    int tiles_n, n_tiles, symmetric;
+    int n_jobs, n_tiles;      // n_tiles: over all jobs
     int mn;                   // edge of an output tile: 128 (one CTA) or 256 (CTA pair)
     double* W;                // [n_tiles][2][mn cols][mn rows]
     I8Schedule sched;
+    I8Job jobs[kMaxJobs];
+};
+
+struct I8Maps {
+    CUtensorMap b[kMaxJobs];  // column-operand planes (deduplicated by base pointer)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -190,7 +223,7 @@ constexpr uint32_t instr_desc(uint32_t mn) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((mn >> 3) << 17) | ((mn >> 4) << 24);
 }
 
-__device__ __forceinline__ void decode_tile(const I8Args& A, int t, int& bm, int& bn) {
+__device__ __forceinline__ void decode_tile(const I8Job& A, int t, int& bm, int& bn) {
     if (A.symmetric) {
         bm = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((bm + 1) * (bm + 2) / 2 <= t) ++bm;
@@ -204,9 +237,26 @@ __device__ __forceinline__ void decode_tile(const I8Args& A, int t, int& bm, int
 
 // ---------------------------------------------------------------------------------------------
 
+// Work unit u -> (job, tile inside the job, K chunk).  Units are job-major (a job's column planes may still be
+// in flight: earlier jobs run first), chunk-major inside a job.
+__device__ __forceinline__ int decode_unit(const I8Args& A, int u, int& tile, int& chunk) {
+    int j = 0;
+    while (j + 1 < A.n_jobs && u >= (A.jobs[j].tile0 + A.jobs[j].n_tiles) * A.n_chunks) ++j;
+    const int ul = u - A.jobs[j].tile0 * A.n_chunks;
+    chunk = ul / A.jobs[j].n_tiles;
+    tile = ul - chunk * A.jobs[j].n_tiles;
+    return j;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
-k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Maps mapsB,
           const __grid_constant__ I8Args A) {
     constexpr int MN = kTile * CG;            // edge of the output tile of a CTA (pair)
     constexpr int ACC = CG == 1 ? 2 : 1;      // accumulator stages: 2 * MN columns each, 512 columns in total
@@ -256,33 +306,44 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const I8Schedule& S = A.sched;
 
     if (warp == 0) {
-        // ===== TMA producer (every CTA loads its own 128 rows of A, Bnat, Brot) =====
+        // ===== TMA producer (every CTA loads its own 128 rows of Anat, Arot and B) =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t ready_jobs = 0;   // jobs whose ready flag has been seen
             for (int u = worker; u < n_units; u += n_workers) {
-                const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
+                int tile, chunk;
+                const int ji = decode_unit(A, u, tile, chunk);
+                const I8Job& J = A.jobs[ji];
+                if (J.ready && !(ready_jobs >> ji & 1u)) {
+                    // column planes pushed by a peer's copy engine: wait for its flag, then order the TMA
+                    // (async proxy) reads behind the acquire
+                    while (ld_acquire_sys(J.ready) < J.ready_value) __nanosleep(200);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    ready_jobs |= 1u << ji;
+                }
+                const CUtensorMap* mapB = &mapsB.b[J.map_b];
                 int bm, bn;
-                decode_tile(A, tile, bm, bn);
+                decode_tile(J, tile, bm, bn);
                 const int k0 = chunk * A.chunk_bytes;
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
                 for (int ci = 0; ci < S.n_classes; ++ci)
                     for (int p = 0; p < S.n_pairs[ci]; ++p) {
-                        const int row_a = (int)(S.pi[ci][p] * A.rows_a + A.row0_a) + bm * MN + (int)cta_rank * kTile;
-                        const int row_bn = (int)(S.pj[ci][p] * A.rows_b + A.row0_b) + bn * MN + (int)cta_rank * kTile;
-                        const int row_br = (int)((kSlices + S.pj[ci][p]) * A.rows_b + A.row0_b) + bn * MN + (int)cta_rank * kTile;
+                        const int row_an = (int)(S.pi[ci][p] * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
+                        const int row_ar = (int)((kSlices + S.pi[ci][p]) * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
+                        const int row_b = (int)(S.pj[ci][p] * J.rows_b + J.row0_b) + bn * MN + (int)cta_rank * kTile;
                         for (int k = k0; k < k1; k += kStageK) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t dst = smem_base + stage * kStageBytes;
                             if (CG == 1) {
                                 mbar_expect_tx(full_bar(stage), kStageBytes);
-                                tma_load_2d(dst, &mapA, full_bar(stage), k, row_a);
-                                tma_load_2d(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
-                                tma_load_2d(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                                tma_load_2d(dst, &mapA, full_bar(stage), k, row_an);
+                                tma_load_2d(dst + kTileBytes, &mapA, full_bar(stage), k, row_ar);
+                                tma_load_2d(dst + 2 * kTileBytes, mapB, full_bar(stage), k, row_b);
                             } else {
-                                tma_load_2d_2sm(dst, &mapA, full_bar(stage), k, row_a);
-                                tma_load_2d_2sm(dst + kTileBytes, &mapB, full_bar(stage), k, row_bn);
-                                tma_load_2d_2sm(dst + 2 * kTileBytes, &mapB, full_bar(stage), k, row_br);
+                                tma_load_2d_2sm(dst, &mapA, full_bar(stage), k, row_an);
+                                tma_load_2d_2sm(dst + kTileBytes, &mapA, full_bar(stage), k, row_ar);
+                                tma_load_2d_2sm(dst + 2 * kTileBytes, mapB, full_bar(stage), k, row_b);
                                 if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
                                 else mbar_arrive_cta(full_bar(stage), 0);
                             }
@@ -298,7 +359,8 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             uint32_t phase = 0;
             uint32_t acc_it = 0;
             for (int u = worker; u < n_units; u += n_workers) {
-                const int chunk = u / A.n_tiles;
+                int tile, chunk;
+                decode_unit(A, u, tile, chunk);
                 const int k0 = chunk * A.chunk_bytes;
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
                 for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
@@ -312,14 +374,14 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             mbar_wait(full_bar(stage), phase);
                             tc_fence_after();
                             const uint32_t sa = smem_base + stage * kStageBytes;
-                            const uint64_t da = umma_smem_desc(sa);
-                            const uint64_t dbn = umma_smem_desc(sa + kTileBytes);
-                            const uint64_t dbr = umma_smem_desc(sa + 2 * kTileBytes);
+                            const uint64_t dan = umma_smem_desc(sa);
+                            const uint64_t dar = umma_smem_desc(sa + kTileBytes);
+                            const uint64_t db = umma_smem_desc(sa + 2 * kTileBytes);
 #pragma unroll
                             for (int kk = 0; kk < kStageK / 32; ++kk) {
                                 // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-                                umma_i8<CG>(d_re, da + 2u * kk, dbn + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
-                                umma_i8<CG>(d_im, da + 2u * kk, dbr + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
+                                umma_i8<CG>(d_re, dan + 2u * kk, db + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
+                                umma_i8<CG>(d_im, dar + 2u * kk, db + 2u * kk, kIdesc, accumulate | (uint32_t)kk);
                             }
                             accumulate = 1;
                             umma_commit<CG>(empty_bar(stage));  // frees the stage when these MMAs have read it
@@ -335,8 +397,9 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int row = (int)cta_rank * kTile + q * 32 + lane;
         uint32_t acc_it = 0;
         for (int u = worker; u < n_units; u += n_workers) {
-            const int chunk = u / A.n_tiles, tile = u - chunk * A.n_tiles;
-            double* wt = A.W + (size_t)tile * (2 * MN * MN) + row;
+            int tile, chunk;
+            const int ji = decode_unit(A, u, tile, chunk);
+            double* wt = A.W + (size_t)(A.jobs[ji].tile0 + tile) * (2 * MN * MN) + row;
             for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
                 const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                 const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
@@ -376,8 +439,10 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------------------------------------
-// Digit planes.  planes: [2 * kSlices][n_rows][2 * dim] int8; plane s = digits of (re, im), plane
-// kSlices + s = digits of (im, -re).  One CTA per state row.
+// Digit planes.  planes: [2 * kSlices][n_rows][2 * dim] int8; plane s = digits of nat = (re, im), plane
+// kSlices + s = digits of rot = (-im, re).  One CTA per state row.  `row_max` (optional): bit patterns of the
+// row maxima max(|re|, |im|) already reduced by the producer of the states (the last gate pass), which saves
+// this kernel's first sweep over the state.
 
 __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int byte) {
     const long long d = ((q + 128) & 255) - 128;
@@ -386,21 +451,27 @@ __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int 
 }
 
 __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
-                                                  int64_t dim, int8_t* __restrict__ planes, int* __restrict__ expo) {
+                                                  int64_t dim, int8_t* __restrict__ planes, int* __restrict__ expo,
+                                                  const unsigned long long* __restrict__ row_max) {
     const int64_t row = row0 + blockIdx.x;   // row inside the planes; state blockIdx.x of psi
     const double2* src = psi + (int64_t)blockIdx.x * dim;
     __shared__ double red[8];
     __shared__ int s_e;
     double m = 0.0;
-    for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
-        const double2 v = src[i];
-        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    if (row_max) {
+        m = __longlong_as_double((long long)row_max[blockIdx.x]);
+    } else {
+        for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+            const double2 v = src[i];
+            m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
     }
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        if (!row_max)
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
         int e = 0;
         if (m > 0.0) frexp(m, &e);  // m = f * 2^e, f in [0.5, 1): every |v| < 2^e
         s_e = e;
@@ -415,12 +486,12 @@ __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ ps
         long long qn[16], qr[16];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const double2 v = src[i0 + c];
+            const double2 v = __ldcs(src + i0 + c);
             const long long a = __double2ll_rn(v.x * scale), b = __double2ll_rn(v.y * scale);
             qn[2 * c] = a;
             qn[2 * c + 1] = b;
-            qr[2 * c] = b;
-            qr[2 * c + 1] = -a;
+            qr[2 * c] = -b;
+            qr[2 * c + 1] = a;
         }
 #pragma unroll
         for (int s = kSlices - 1; s >= 0; --s) {
@@ -439,19 +510,31 @@ __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ ps
 
 // ---------------------------------------------------------------------------------------------
 // W -> K.  One CTA per tile; 32 x 32 sub-blocks go through shared memory so that both the direct and the
-// mirrored store are coalesced.
+// mirrored store are coalesced.  Jobs with `align_y` also reduce sum K_ij y_i y_j and sum K_ij^2 here (the
+// kernel-target-alignment sums of src/squlearn/kernel/loss/target_alignment.py:75-90), so that a training step
+// never re-reads K.
 
-__global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict__ W, const int* __restrict__ ex,
-                                                       const int* __restrict__ ey, double* __restrict__ K,
-                                                       int64_t ldk, int64_t nx, int64_t ny, I8Args A, uint32_t flags) {
+__global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict__ W, const __grid_constant__ I8Args A) {
     __shared__ double sm[32][33];
+    __shared__ double s_red[2][8];
+    int ji = 0;
+    while (ji + 1 < A.n_jobs && (int)blockIdx.x >= A.jobs[ji].tile0 + A.jobs[ji].n_tiles) ++ji;
+    const I8Job& J = A.jobs[ji];
     int bm, bn;
-    decode_tile(A, blockIdx.x, bm, bn);
+    decode_tile(J, (int)blockIdx.x - J.tile0, bm, bn);
     const int MN = A.mn, nsb = MN / 32;
     const double* wt = W + (size_t)blockIdx.x * (2 * (size_t)MN * MN);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t flags = J.flags;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
     const bool diag_tile = sym && bm == bn;
+    const int64_t nx = J.nx, ny = J.ny, ldk = J.ldk;
+    double* __restrict__ K = J.K;
+    const int* __restrict__ ex = J.ex + J.row0_a;
+    const int* __restrict__ ey = J.ey + J.row0_b;
+    const double* __restrict__ ayx = J.align_yx;
+    const double* __restrict__ ayy = J.align_yy;
+    double a_ky = 0.0, a_kk = 0.0;
     for (int sb = 0; sb < nsb * nsb; ++sb) {
         const int sr = sb / nsb, sc = sb - sr * nsb;
         if ((int64_t)bm * MN + sr * 32 >= nx || (int64_t)bn * MN + sc * 32 >= ny) continue;  // CTA-uniform
@@ -465,10 +548,15 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
                 // bit-exactly symmetric whatever order the atomic FP64 accumulation happened in
                 const int r2 = (diag_tile && col > row) ? col : row, c2 = (diag_tile && col > row) ? row : col;
                 const double re = wt[(size_t)c2 * MN + r2], im = wt[(size_t)(MN + c2) * MN + r2];
-                k = ldexp(re * re + im * im, 2 * (ex[A.row0_a + i] + ey[A.row0_b + j] - 12));
+                k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j] - 12));
                 if (sym && i == j) {
                     if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
                     else if (flags & B200SQ_GRAM_DIAG_ZERO) k = 0.0;
+                }
+                if (ayx) {   // off-diagonal tiles of a symmetric block stand for their mirror image too
+                    const double wgt = sym ? (bm != bn ? 2.0 : 1.0) : J.align_weight;
+                    a_ky = fma(wgt * k, ayx[i] * ayy[j], a_ky);
+                    a_kk = fma(wgt * k, k, a_kk);
                 }
             }
             sm[ty + 8 * qd][tx] = k;  // [col][row]
@@ -488,6 +576,19 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
             }
         }
         __syncthreads();
+    }
+    if (ayx) {
+        for (int o = 16; o > 0; o >>= 1) {
+            a_ky += __shfl_xor_sync(0xffffffffu, a_ky, o);
+            a_kk += __shfl_xor_sync(0xffffffffu, a_kk, o);
+        }
+        if (tx == 0) { s_red[0][ty] = a_ky; s_red[1][ty] = a_kk; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+            atomicAdd(J.align_out + threadIdx.x, t);
+        }
     }
 }
 
@@ -519,9 +620,9 @@ int encode_planes(CUtensorMap* map, void* base, uint64_t kbytes, uint64_t rows_t
 bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
 
 int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                    int* expo, cudaStream_t stream) {
+                    int* expo, cudaStream_t stream, const unsigned long long* row_max) {
     if (n <= 0) return 0;
-    k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo);
+    k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo, row_max);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -561,8 +662,33 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
 int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t x0, int64_t nx, const int8_t* py,
                        const int* ey, int64_t rows_y, int64_t y0, int64_t ny, int64_t dim, double* k, int64_t ldk,
                        uint32_t flags, cudaStream_t stream) {
-    if (nx <= 0 || ny <= 0) return 0;
-    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    b200sq_gram_job job;
+    memset(&job, 0, sizeof(job));
+    job.x0 = x0;
+    job.nx = nx;
+    job.planes_y_dev = py;
+    job.expo_y_dev = ey;
+    job.plane_rows_y = rows_y;
+    job.y0 = y0;
+    job.ny = ny;
+    job.K_dev = k;
+    job.ldk = ldk;
+    job.flags = flags;
+    return launch_gram_jobs(px, ex, rows_x, dim, 1, &job, stream);
+}
+
+// Several Gram blocks that share the row operand px in one persistent launch (see the JOB TABLE note at the top).
+// Column planes only need their kSlices nat planes resident (a received block carries no rot planes).
+int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t dim, int n_jobs,
+                     const b200sq_gram_job* jobs, cudaStream_t stream) {
+    if (n_jobs <= 0) return 0;
+    if (n_jobs > kMaxJobs) {   // more blocks than one launch holds: split
+        for (int j0 = 0; j0 < n_jobs; j0 += kMaxJobs) {
+            const int rc = launch_gram_jobs(px, ex, rows_x, dim, std::min(kMaxJobs, n_jobs - j0), jobs + j0, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     const int64_t kbytes = 2 * dim;
     double* W = nullptr;
     cudaError_t e;
@@ -572,34 +698,45 @@ int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t 
     I8Args a;
     memset(&a, 0, sizeof(a));
     a.rows_a = rows_x;
-    a.rows_b = rows_y;
-    a.row0_a = x0;
-    a.row0_b = y0;
     a.kbytes = (int)kbytes;
-    // CTA pairs (256 x 256 tiles, cta_group::2) halve the L2 -> SMEM operand traffic per MMA; small
-    // problems keep single-CTA 128 x 128 tiles so that the machine still fills
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const int force_cg = getenv("B200SQ_I8_CG") ? atoi(getenv("B200SQ_I8_CG")) : 0;
+    static const int force_chunk = getenv("B200SQ_I8_CHUNK") ? atoi(getenv("B200SQ_I8_CHUNK")) : 0;
     auto count_tiles = [&](int mn) {
-        const int64_t tm = (nx + mn - 1) / mn, tn = (ny + mn - 1) / mn;
-        return sym ? tm * (tm + 1) / 2 : tm * tn;
+        int64_t t = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            if (jobs[j].nx <= 0 || jobs[j].ny <= 0) continue;
+            const int64_t tm = (jobs[j].nx + mn - 1) / mn, tn = (jobs[j].ny + mn - 1) / mn;
+            t += (jobs[j].flags & B200SQ_GRAM_SYMMETRIC) ? tm * (tm + 1) / 2 : tm * tn;
+        }
+        return t;
     };
-    // K is cut into chunks of at most 16 KiB (the int32 accumulators stay exact).  CTA pairs need enough
-    // 256 x 256 units to fill the machine; otherwise single CTAs with 128 x 128 tiles (TMEM double
-    // buffered) run, with shorter chunks when there are fewer than half as many units as SMs.
-    a.chunk_bytes = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
+    if (count_tiles(kTile) == 0) return 0;
+    // K is cut into chunks of at most 16 KiB (the int32 accumulators stay exact).  CTA pairs (256 x 256 tiles,
+    // cta_group::2) halve the L2 -> SMEM operand traffic per MMA but need enough units to fill the machine;
+    // otherwise single CTAs with 128 x 128 tiles (TMEM double buffered) run.  The chunk is halved (down to 4 KiB)
+    // while the last wave of the persistent workers would be less than ~85 % full.
+    int chunk_max = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
     auto n_chunks_of = [&](int cb) { return (kbytes + cb - 1) / cb; };
-    const int cg = force_cg ? force_cg : (count_tiles(256) * n_chunks_of(std::min(a.chunk_bytes, 4096)) >= sms / 2 ? 2 : 1);
-    while (a.chunk_bytes > 4096 && count_tiles(kTile * cg) * n_chunks_of(a.chunk_bytes) * 2 <= sms / cg)
-        a.chunk_bytes /= 2;
+    const int cg = force_cg ? force_cg : (count_tiles(256) * n_chunks_of(std::min(chunk_max, 4096)) >= sms / 2 ? 2 : 1);
+    const int workers_max = sms / cg;
+    a.chunk_bytes = chunk_max;
+    {
+        const int64_t tiles = count_tiles(kTile * cg);
+        auto efficiency = [&](int cb) {
+            const int64_t units = tiles * n_chunks_of(cb);
+            const int64_t waves = (units + workers_max - 1) / workers_max;
+            return (double)units / (double)(waves * workers_max);
+        };
+        while (a.chunk_bytes > 4096 && a.chunk_bytes / 2 >= kStageK && efficiency(a.chunk_bytes) < 0.85 &&
+               efficiency(a.chunk_bytes / 2) > efficiency(a.chunk_bytes) + 0.02)
+            a.chunk_bytes /= 2;
+        if (force_chunk >= kStageK && force_chunk <= kChunkK && force_chunk % kStageK == 0) a.chunk_bytes = force_chunk;
+    }
     a.n_chunks = (int)n_chunks_of(a.chunk_bytes);
     a.mn = kTile * cg;
-    const int tiles_m = (int)((nx + a.mn - 1) / a.mn);
-    a.tiles_n = (int)((ny + a.mn - 1) / a.mn);
-    a.symmetric = sym ? 1 : 0;
-    a.n_tiles = (int)count_tiles(a.mn);
     // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
     {
         I8Schedule& s = a.sched;
@@ -620,14 +757,55 @@ int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t 
         }
         s.n_classes = nc;
     }
+    CUtensorMap mapA;
+    I8Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = encode_planes(&mapA, (void*)px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_x);
+    if (rc) return rc;
+    const void* map_base[kMaxJobs];
+    int n_maps = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const b200sq_gram_job& in = jobs[j];
+        if (in.nx <= 0 || in.ny <= 0) continue;
+        I8Job& J = a.jobs[a.n_jobs];
+        const bool sym = in.flags & B200SQ_GRAM_SYMMETRIC;
+        J.row0_a = in.x0;
+        J.row0_b = in.y0;
+        J.rows_b = in.plane_rows_y;
+        J.ldk = in.ldk;
+        J.K = in.K_dev;
+        J.ex = ex;
+        J.ey = in.expo_y_dev;
+        J.ready = in.ready_flag_dev;
+        J.ready_value = in.ready_value;
+        J.align_yx = in.align_yx_dev;
+        J.align_yy = in.align_yy_dev ? in.align_yy_dev : in.align_yx_dev;
+        J.align_out = in.align_out_dev;
+        J.align_weight = in.align_weight != 0.0 ? in.align_weight : 1.0;
+        J.flags = in.flags;
+        J.nx = (int32_t)in.nx;
+        J.ny = (int32_t)in.ny;
+        const int tiles_m = (int)((in.nx + a.mn - 1) / a.mn);
+        J.tiles_n = (int)((in.ny + a.mn - 1) / a.mn);
+        J.symmetric = sym ? 1 : 0;
+        J.n_tiles = sym ? tiles_m * (tiles_m + 1) / 2 : tiles_m * J.tiles_n;
+        J.tile0 = a.n_tiles;
+        a.n_tiles += J.n_tiles;
+        int m = 0;
+        while (m < n_maps && map_base[m] != in.planes_y_dev) ++m;
+        if (m == n_maps) {
+            map_base[n_maps++] = in.planes_y_dev;
+            // only the nat planes of a column operand are read
+            rc = encode_planes(&maps.b[m], (void*)in.planes_y_dev, (uint64_t)kbytes, (uint64_t)kSlices * in.plane_rows_y);
+            if (rc) return rc;
+        }
+        J.map_b = m;
+        ++a.n_jobs;
+    }
     const size_t wbytes = (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
     if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
     a.W = W;
     cudaMemsetAsync(W, 0, wbytes, stream);
-    CUtensorMap mapA, mapB;
-    int rc = encode_planes(&mapA, (void*)px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_x);
-    if (!rc) rc = encode_planes(&mapB, (void*)py, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_y);
-    if (rc) { cleanup(); return rc; }
     const int smem = kStages * kStageBytes + 1024 + 256;
     const int n_units = a.n_tiles * a.n_chunks;
     {
@@ -636,7 +814,7 @@ int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t 
             cleanup();
             return (int)e;
         }
-        const int workers = n_units < sms / cg ? n_units : sms / cg;
+        const int workers = n_units < workers_max ? n_units : workers_max;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)(workers * cg));
@@ -650,13 +828,13 @@ int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t 
         attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, a)) != cudaSuccess) {
+        if ((e = cudaLaunchKernelEx(&cfg, kern, mapA, maps, a)) != cudaSuccess) {
             cleanup();
             return (int)e;
         }
         count_launch();
     }
-    k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, ex, ey, k, ldk, nx, ny, a, flags);
+    k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, a);
     count_launch();
     e = cudaGetLastError();
     cleanup();

@@ -84,6 +84,35 @@ def gram_jobs(parts: List[Tuple[int, int]]) -> List[List[dict]]:
     return jobs
 
 
+def ring_distance(rank: int, owner: int, world: int) -> int:
+    """Steps from ``rank`` forward to ``owner`` on the ring of ranks."""
+    return (owner - rank) % world
+
+
+def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
+    """The off-diagonal jobs of ``rank`` in the order their column planes arrive: nearest owner first (every
+    rank pushes its planes to rank-1, rank-2, ... in that order, so the block a rank needs first lands first)."""
+    mine = [j for j in jobs[rank] if not j["diag"]]
+    mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
+    return mine
+
+
+def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, align: int = 1024):
+    """Receive arena of a rank: one slot [6 nat planes | row exponents] per off-diagonal job, in arrival order.
+    Returns ([{"owner", "cols", "rows", "off", "expo_off"}], flags offset, total bytes); every rank computes
+    the layout of every other rank from the job table alone (a sender needs the receiver's slot offsets)."""
+    slots, off = [], 0
+    mine = [j for j in jobs_of_rank if not j["diag"]]
+    mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
+    for j in mine:
+        w = j["cols"][1] - j["cols"][0]
+        nb = 6 * w * 2 * dim
+        slots.append({"owner": j["owner"], "cols": j["cols"], "rows": w, "off": off, "expo_off": off + nb})
+        off = (off + nb + 4 * w + align - 1) // align * align
+    flags_off = off
+    return slots, flags_off, flags_off + 4 * world + align
+
+
 class ShardedFidelityKernel:
     """Fidelity Gram matrix of ``x`` across all ranks of a process group.
 
@@ -91,6 +120,16 @@ class ShardedFidelityKernel:
     ``states(x) -> device tensor`` and ``_executor.engine.gram``); ``group`` the process group
     (default: the world).  Works with NCCL (GPU tensors) and, for the CPU tests of the sharding
     logic, with gloo and a stand-in engine.
+
+    INT8 (digit-plane) path, exchange modes (``B200SQ_DIST_EXCHANGE``):
+
+    * ``ipc`` (default on CUDA): every rank PUSHES the 6 nat planes of its row block into the receive arenas of
+      the ranks that need them with copy-engine copies over NVLink (CUDA IPC mappings; no SM is spent on the
+      exchange) and then writes an epoch flag; the receiver's single job-table Gram launch multiplies each
+      block as soon as its flag is visible (``b200sq_gram_jobs``), so the exchange hides behind the diagonal
+      block and the earlier blocks.
+    * ``p2p``: the same blocks as one NCCL send/recv batch, waited for before the (single) Gram launch.
+    * ``allgather``: one NCCL all-gather of the equal-sized blocks (what the north star names).
     """
 
     def __init__(self, kernel, group=None, diagonal: str = "one", precision: Optional[str] = None):
@@ -98,6 +137,8 @@ class ShardedFidelityKernel:
 
         self._dist = dist
         self._blocks = {}
+        self._peer = None          # state of the ipc exchange (arena, peer mappings, epoch)
+        self._host = None          # shared pinned host buffers of evaluate()
         self.precision = precision  # Gram arithmetic: None = the engine's default policy ("auto")
         self._gram_kw = {} if precision in (None, "auto") else {"precision": precision}
         self.kernel = kernel
@@ -105,6 +146,236 @@ class ShardedFidelityKernel:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.diagonal = diagonal
+
+    # ------------------------------------------------------------------ digit-plane path
+    def _exchange_mode(self, eng, equal: bool, n_local: int, block_bytes: int) -> str:
+        mode = os.environ.get("B200SQ_DIST_EXCHANGE", "auto").lower()
+        if mode == "allgather" and not (equal and n_local > 0 and n_local % 4 == 0
+                                        and self.world * block_bytes <= (32 << 30)):
+            mode = "auto"   # the all-gather needs equal, 16-byte aligned blocks that fit 32 GiB
+        if mode in ("auto", "ipc"):
+            can_ipc = hasattr(eng, "ipc_export") and self._dist.get_backend(self.group) == "nccl"
+            mode = "ipc" if can_ipc else "p2p"
+        if mode not in ("ipc", "p2p", "allgather"):
+            raise ValueError("B200SQ_DIST_EXCHANGE must be auto, ipc, p2p or allgather")
+        return mode
+
+    def _peer_setup(self, eng, parts, jobs, dim):
+        """Arena, flags and the peer mappings of the ipc exchange (cached while the shapes stay the same)."""
+        import torch
+
+        dist = self._dist
+        key = (tuple(parts), dim)
+        if self._peer is not None and self._peer["key"] == key:
+            return self._peer
+        self._peer_close()
+        slots, flags_off, total = arena_layout(jobs[self.rank], self.rank, self.world, dim)
+        arena = eng.alloc_bytes(total)
+        arena[flags_off:flags_off + 4 * self.world].zero_()
+        handle, off = eng.ipc_export(arena)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (handle, off), group=self.group)
+        r0, r1 = parts[self.rank]
+        pushes = []   # (ring distance of me as seen from q, q, local rows a..b, slot offsets in q's arena)
+        bases = {}
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            q_slots, q_flags_off, _ = arena_layout(jobs[q], q, self.world, dim)
+            for sl in q_slots:
+                if sl["owner"] != self.rank:
+                    continue
+                if q not in bases:
+                    bases[q] = eng.ipc_open(infos[q][0])
+                base = bases[q] + infos[q][1]
+                a, b = sl["cols"]
+                pushes.append({"dist": ring_distance(q, self.rank, self.world), "q": q, "a": a - r0, "b": b - r0,
+                               "dst": base + sl["off"], "dst_expo": base + sl["expo_off"],
+                               "dst_flag": base + q_flags_off + 4 * self.rank})
+        pushes.sort(key=lambda p: (p["dist"], p["q"]))
+        torch.cuda.synchronize(eng.device)
+        dist.barrier(group=self.group)   # every arena is mapped and zeroed before the first push
+        self._peer = {"key": key, "arena": arena, "slots": slots, "flags_off": flags_off, "pushes": pushes,
+                      "bases": bases, "epoch": 0, "stream": torch.cuda.Stream(device=eng.device),
+                      "sliced": torch.cuda.Event(), "pushed": None, "eng": eng}
+        return self._peer
+
+    def _peer_close(self):
+        if self._peer is None:
+            return
+        try:
+            import torch
+
+            torch.cuda.synchronize(self._peer["eng"].device)
+            for base in self._peer["bases"].values():
+                self._peer["eng"].ipc_close(base)
+        except Exception:   # interpreter / process-group shutdown
+            pass
+        self._peer = None
+
+    def __del__(self):
+        self._peer_close()
+        self._host_close()
+
+    def _rows_planes(self, eng, x, parts, jobs, rows, dim):
+        """The digit-plane (INT8) path: slice once, exchange the nat planes, ONE job-table Gram launch."""
+        import torch
+
+        dist = self._dist
+        r0, r1 = parts[self.rank]
+        n_local = r1 - r0
+        mine = remote_jobs(jobs, self.rank, self.world)
+        equal = all(b - a == n_local for a, b in parts)
+        nat_bytes = 6 * n_local * 2 * dim
+        mode = self._exchange_mode(eng, equal, n_local, nat_bytes + 4 * n_local)
+
+        buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
+        if mode == "ipc":
+            peer = self._peer_setup(eng, parts, jobs, dim)
+            if peer["pushed"] is not None:   # my previous pushes read the local planes
+                torch.cuda.current_stream(eng.device).wait_event(peer["pushed"])
+        psi_local = self.kernel.states(x[r0:r1]).contiguous()
+        _mark("states")
+        eng.slice_states(psi_local, planes, expo, 0)
+        del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+
+        glist = []
+        if n_local:
+            glist.append({"x0": 0, "nx": n_local, "planes_y": planes, "expo_y": expo, "rows_y": n_local, "y0": 0,
+                          "ny": n_local, "out": rows[:, r0:r1], "symmetric": True, "diagonal": self.diagonal})
+        if mode == "ipc":
+            peer["epoch"] += 1
+            epoch = peer["epoch"]
+            arena, st = peer["arena"], peer["stream"]
+            epoch_t = torch.full((1,), epoch, dtype=torch.int32, device=eng.device)
+            peer["sliced"].record(torch.cuda.current_stream(eng.device))
+            st.wait_event(peer["sliced"])
+            kb = 2 * dim
+            for p in peer["pushes"]:     # nearest consumer first
+                w = p["b"] - p["a"]
+                if w == n_local:         # the whole block: its 6 nat planes are contiguous
+                    eng.copy_async(p["dst"], planes.data_ptr(), nat_bytes, st)
+                else:                    # a row range (antipodal split): one copy per plane
+                    for s_ in range(6):
+                        eng.copy_async(p["dst"] + s_ * w * kb, planes[s_, p["a"]].data_ptr(), w * kb, st)
+                eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
+                eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
+            peer["pushed"] = torch.cuda.Event()
+            peer["pushed"].record(st)
+            epoch_t.record_stream(st)
+            flags_ptr = arena.data_ptr() + peer["flags_off"]
+            for j, sl in zip(mine, peer["slots"]):
+                w = sl["rows"]
+                j["planes_y"], j["expo_y"] = arena.data_ptr() + sl["off"], arena.data_ptr() + sl["expo_off"]
+                j["rows_y"], j["y0"], j["ready"] = w, 0, (flags_ptr + 4 * j["owner"], epoch)
+            _mark("diag")
+            _mark("exchange")
+        elif mode == "allgather":
+            # one NCCL all-gather of the [6 nat planes | exponents] blocks; a job reads its owner's block in place
+            block = nat_bytes + 4 * n_local
+            gathered = self._bytes(eng, "gathered", self.world * block)
+            send = self._bytes(eng, "send", block)
+            send[:nat_bytes].copy_(buf_local[:nat_bytes])
+            send[nat_bytes:].copy_(expo.view(torch.int8))
+            dist.all_gather_into_tensor(gathered, send, group=self.group)
+            _mark("diag")
+            _mark("exchange")
+            for j in mine:
+                q, c0 = j["owner"], parts[j["owner"]][0]
+                j["planes_y"] = gathered[q * block: q * block + nat_bytes].view(6, n_local, 2 * dim)
+                j["expo_y"] = gathered[q * block + nat_bytes: (q + 1) * block].view(torch.int32)
+                j["rows_y"], j["y0"], j["ready"] = n_local, j["cols"][0] - c0, None
+        else:
+            # one NCCL batch: [6 nat planes | exponents] of exactly the rows every consumer needs
+            ops, keep = [], []
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                for j in jobs[q]:
+                    if j["owner"] == self.rank and not j["diag"]:
+                        a, b = j["cols"]
+                        msg, mp, me = self._nat_block(eng, ("stage", q), b - a, dim)
+                        mp.copy_(planes[:6, a - r0:b - r0])
+                        me.copy_(expo[a - r0:b - r0])
+                        keep.append(msg)
+                        ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
+            for j in mine:
+                w = j["cols"][1] - j["cols"][0]
+                buf, j["planes_y"], j["expo_y"] = self._nat_block(eng, ("recv", j["owner"]), w, dim)
+                j["rows_y"], j["y0"], j["ready"] = w, 0, None
+                ops.append(dist.P2POp(dist.irecv, buf, self._global_rank(j["owner"]), self.group))
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            _mark("diag")
+            for req in reqs:
+                req.wait()
+            _mark("exchange")
+        for j in mine:
+            ra, rb = j["rows"]
+            w = j["cols"][1] - j["cols"][0]
+            j["blk"] = rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]]
+            glist.append({"x0": ra - r0, "nx": rb - ra, "planes_y": j["planes_y"], "expo_y": j["expo_y"],
+                          "rows_y": j["rows_y"], "y0": j["y0"], "ny": w, "out": j["blk"], "ready": j["ready"]})
+        if glist:
+            eng.gram_jobs(planes, expo, glist)
+        return mine
+
+    def _rows_states(self, eng, x, parts, jobs, rows, dim):
+        """The FP64 path: exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
+        every peer is one NVSwitch hop away, so there is no ring-order penalty).  The receive buffer holds the
+        column states of all my jobs back to back, so that jobs sharing a row range become ONE rectangular
+        Gram launch."""
+        import torch
+
+        dist = self._dist
+        f64 = torch.float64
+        r0, r1 = parts[self.rank]
+        n_local = r1 - r0
+        psi_local = self.kernel.states(x[r0:r1]).contiguous()
+        _mark("states")
+        dev = psi_local.device
+        mine = [j for j in jobs[self.rank] if not j["diag"]]
+        mine.sort(key=lambda j: (j["rows"], j["owner"]))
+        total_cols = sum(j["cols"][1] - j["cols"][0] for j in mine)
+        recv = torch.empty((max(total_cols, 1), dim), dtype=psi_local.dtype, device=dev)
+        ops, off = [], 0
+        for q in range(self.world):          # sends: rows of mine that other ranks' jobs need
+            if q == self.rank:
+                continue
+            for j in jobs[q]:
+                if j["owner"] == self.rank and not j["diag"]:
+                    a, b = j["cols"]
+                    ops.append(dist.P2POp(dist.isend, psi_local[a - r0:b - r0].view(f64),
+                                          self._global_rank(q), self.group))
+        for j in mine:
+            w = j["cols"][1] - j["cols"][0]
+            j["off"] = off
+            ops.append(dist.P2POp(dist.irecv, recv[off:off + w].view(f64),
+                                  self._global_rank(j["owner"]), self.group))
+            off += w
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        # ---- the diagonal block needs no remote data: it runs while the blocks are in flight
+        if n_local:
+            rows[:, r0:r1] = eng.gram(psi_local, None, diagonal=self.diagonal, **self._gram_kw)
+        _mark("diag")
+        for req in reqs:
+            req.wait()
+        _mark("exchange")
+        # ---- one launch per distinct row range
+        i = 0
+        while i < len(mine):
+            k = i
+            while k < len(mine) and mine[k]["rows"] == mine[i]["rows"]:
+                k += 1
+            ra, rb = mine[i]["rows"]
+            c_lo, c_hi = mine[i]["off"], mine[k - 1]["off"] + (mine[k - 1]["cols"][1] - mine[k - 1]["cols"][0])
+            big = eng.gram(psi_local[ra - r0:rb - r0], recv[c_lo:c_hi], **self._gram_kw)
+            for j in mine[i:k]:
+                w = j["cols"][1] - j["cols"][0]
+                blk = big[:, j["off"] - c_lo: j["off"] - c_lo + w]
+                rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
+                j["blk"] = blk
+            i = k
+        return mine
 
     def evaluate_rows(self, x):
         """This rank's row block K[r0:r1, :] of the symmetric Gram matrix (device tensor)."""
@@ -116,155 +387,20 @@ class ShardedFidelityKernel:
         parts = row_partition(n, self.world)
         r0, r1 = parts[self.rank]
         eng = self.kernel._executor.engine
-        psi_local = self.kernel.states(x[r0:r1]).contiguous()
-        _mark("states")
-        dim = psi_local.shape[1]
-        dev = psi_local.device
-        f64 = torch.float64
-
+        if hasattr(self.kernel, "num_qubits"):
+            dim = 1 << int(self.kernel.num_qubits)
+        else:   # stand-in kernels: ask an (empty) batch for its width
+            dim = int(self.kernel.states(x[:0]).shape[1])
         jobs = gram_jobs(parts)
-        mine = [j for j in jobs[self.rank] if not j["diag"]]
-        # every off-diagonal piece of mine: column states come from the owner of those columns
-        mine.sort(key=lambda j: (j["rows"], j["owner"]))
-        total_cols = sum(j["cols"][1] - j["cols"][0] for j in mine)
         n_local = r1 - r0
-        rows = torch.zeros((n_local, n), dtype=f64, device=dev)
-        use_planes = (hasattr(eng, "gram_from_planes")
+        dev = getattr(eng, "device", "cpu")
+        rows = torch.zeros((n_local, n), dtype=torch.float64, device=dev)
+        use_planes = (hasattr(eng, "gram_jobs")
                       and eng.gram_precision(n, n, dim, self.precision) == "int8")  # same decision on every rank
-
         if use_planes:
-            # ---- split-integer path: every rank slices its own states ONCE into int8 digit planes and the
-            # planes travel (12 instead of 16 bytes per amplitude, no re-slicing on the receiver).  A block of
-            # rows is one contiguous buffer [12 planes | row exponents], so the exchange is a single NCCL
-            # message per peer, all posted in one batch and overlapped with the diagonal block.
-            equal = all(b - a == n_local for a, b in parts)
-            block_bytes = 12 * n_local * 2 * dim + 4 * n_local
-            mode = os.environ.get("B200SQ_DIST_EXCHANGE", "auto")   # "allgather" | "p2p" | "auto"
-            # default: point-to-point (measured faster: 15.4 vs 16.7 ms per C3 step on 4 GPUs; it moves only the
-            # floor(P/2) blocks a rank needs); the all-gather is kept as an option
-            use_allgather = mode == "allgather" and equal and n_local > 0 \
-                and n_local % 4 == 0 and self.world * block_bytes <= (32 << 30)   # 16-byte aligned blocks, <= 32 GiB
-            diag_after = os.environ.get("B200SQ_DIST_DIAG_AFTER", "0") == "1"
-            if use_allgather:
-                # ---- one NCCL all-gather of the plane blocks (NVSwitch collective bandwidth; a rank uses
-                # floor(P/2) of the P - 1 remote blocks it receives, which is still faster than P2P send/recv:
-                # measured 250 GB/s per rank for the point-to-point batch).  Block q of `gathered` is rank q's
-                # [12 planes | row exponents] buffer; my own block is sliced in place.
-                gathered = self._gather_buffer(eng, self.world * block_bytes)
-                nb = 12 * n_local * 2 * dim
-                view = lambda q: (gathered[q * block_bytes: q * block_bytes + nb].view(12, n_local, 2 * dim),
-                                  gathered[q * block_bytes + nb: (q + 1) * block_bytes].view(torch.int32))
-                planes, expo = view(self.rank)
-                eng.slice_states(psi_local, planes, expo, 0)
-                del psi_local
-                work = dist.all_gather_into_tensor(gathered, gathered[self.rank * block_bytes:(self.rank + 1) * block_bytes],
-                                                   group=self.group, async_op=True)
-                if not diag_after:
-                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-                _mark("diag")
-                work.wait()
-                _mark("exchange")
-                if diag_after:
-                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-                for j in mine:
-                    ra, rb = j["rows"]
-                    (a, b), c0 = j["cols"], parts[j["owner"]][0]
-                    pq, eq = view(j["owner"])
-                    blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, pq, eq, a - c0, b - a)
-                    rows[ra - r0:rb - r0, a:b] = blk
-                    j["blk"] = blk
-            else:
-                buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
-                eng.slice_states(psi_local, planes, expo, 0)
-                ops, keep = [], []
-                for q in range(self.world):      # sends: rows of mine that other ranks' jobs need
-                    if q == self.rank:
-                        continue
-                    for j in jobs[q]:
-                        if j["owner"] == self.rank and not j["diag"]:
-                            a, b = j["cols"]
-                            if (a, b) == (r0, r1):
-                                msg = buf_local
-                            else:  # a sub-range of my rows (antipodal split): stage it contiguously
-                                msg, mp, me = self._plane_block(eng, ("stage", q), b - a, dim)
-                                mp.copy_(planes[:, a - r0:b - r0])
-                                me.copy_(expo[a - r0:b - r0])
-                                keep.append(msg)
-                            ops.append(dist.P2POp(dist.isend, msg, self._global_rank(q), self.group))
-                for j in mine:
-                    w = j["cols"][1] - j["cols"][0]
-                    j["buf"], j["planes"], j["expo"] = self._plane_block(eng, ("recv", j["owner"]), w, dim)
-                    ops.append(dist.P2POp(dist.irecv, j["buf"], self._global_rank(j["owner"]), self.group))
-                reqs = dist.batch_isend_irecv(ops) if ops else []
-                del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
-                # The diagonal block needs no remote data.  By default it runs while the planes are in flight;
-                # B200SQ_DIST_DIAG_AFTER=1 runs it after the exchange.
-                if n_local and not diag_after:
-                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-                _mark("diag")
-                for req in reqs:
-                    req.wait()
-                _mark("exchange")
-                if n_local and diag_after:
-                    rows[:, r0:r1] = eng.gram_from_planes(planes, expo, 0, n_local, diagonal=self.diagonal)
-                for j in mine:
-                    ra, rb = j["rows"]
-                    w = j["cols"][1] - j["cols"][0]
-                    blk = eng.gram_from_planes(planes, expo, ra - r0, rb - ra, j["planes"], j["expo"], 0, w)
-                    rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
-                    j["blk"] = blk
-            mine_done = True
+            mine = self._rows_planes(eng, x, parts, jobs, rows, dim)
         else:
-            # ---- exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
-            # every peer is one NVSwitch hop away, so there is no ring-order penalty).  The receive
-            # buffer holds the column states of all my jobs back to back, so that jobs sharing a row
-            # range become ONE rectangular Gram launch.
-            recv = torch.empty((max(total_cols, 1), dim), dtype=psi_local.dtype, device=dev)
-            ops, off = [], 0
-            for q in range(self.world):          # sends: rows of mine that other ranks' jobs need
-                if q == self.rank:
-                    continue
-                for j in jobs[q]:
-                    if j["owner"] == self.rank and not j["diag"]:
-                        a, b = j["cols"]
-                        ops.append(dist.P2POp(dist.isend, psi_local[a - r0:b - r0].view(f64),
-                                              self._global_rank(q), self.group))
-            for j in mine:
-                w = j["cols"][1] - j["cols"][0]
-                j["off"] = off
-                ops.append(dist.P2POp(dist.irecv, recv[off:off + w].view(f64),
-                                      self._global_rank(j["owner"]), self.group))
-                off += w
-            reqs = dist.batch_isend_irecv(ops) if ops else []
-
-            # ---- the diagonal block needs no remote data: it runs while the blocks are in flight
-            if n_local:
-                rows[:, r0:r1] = eng.gram(psi_local, None, diagonal=self.diagonal, **self._gram_kw)
-            _mark("diag")
-            for req in reqs:
-                req.wait()
-            _mark("exchange")
-
-            def rect(ra, rb, c_lo, c_hi):
-                return eng.gram(psi_local[ra - r0:rb - r0], recv[c_lo:c_hi], **self._gram_kw)
-            mine_done = False
-
-        # ---- one launch per distinct row range
-        i = len(mine) if mine_done else 0
-        while i < len(mine):
-            k = i
-            while k < len(mine) and mine[k]["rows"] == mine[i]["rows"]:
-                k += 1
-            ra, rb = mine[i]["rows"]
-            c_lo, c_hi = mine[i]["off"], mine[k - 1]["off"] + (mine[k - 1]["cols"][1] - mine[k - 1]["cols"][0])
-            big = rect(ra, rb, c_lo, c_hi)
-            for j in mine[i:k]:
-                w = j["cols"][1] - j["cols"][0]
-                blk = big[:, j["off"] - c_lo: j["off"] - c_lo + w]
-                rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]] = blk
-                j["blk"] = blk
-            i = k
-
+            mine = self._rows_states(eng, x, parts, jobs, rows, dim)
         _mark("rect")
         # ---- mirror: every off-diagonal piece, transposed, belongs to the owner of its columns
         ops, placements = [], []
@@ -277,7 +413,7 @@ class ShardedFidelityKernel:
             for j in jobs[q]:
                 if j["owner"] == self.rank and not j["diag"]:
                     (a, b), (ra, rb) = j["cols"], j["rows"]
-                    buf = torch.empty((b - a, rb - ra), dtype=f64, device=dev)
+                    buf = torch.empty((b - a, rb - ra), dtype=torch.float64, device=dev)
                     placements.append((a - r0, b - r0, ra, rb, buf))
                     ops.append(dist.P2POp(dist.irecv, buf, self._global_rank(q), self.group))
         if ops:
@@ -288,12 +424,20 @@ class ShardedFidelityKernel:
         _mark("mirror")
         return rows, (r0, r1)
 
-    def _gather_buffer(self, eng, nbytes: int):
-        buf = self._blocks.get("gathered")
+    def _bytes(self, eng, tag, nbytes: int):
+        buf = self._blocks.get(tag)
         if buf is None or buf.numel() != nbytes:
-            self._blocks.pop("gathered", None)
-            buf = self._blocks["gathered"] = eng.alloc_plane_block(0, 1)[0].new_empty((nbytes,))
+            self._blocks.pop(tag, None)
+            buf = self._blocks[tag] = eng.alloc_bytes(nbytes)
         return buf
+
+    def _nat_block(self, eng, tag, rows: int, dim: int):
+        """[6 nat planes | row exponents] of ``rows`` states in one contiguous buffer (one message)."""
+        import torch
+
+        nb = 6 * rows * 2 * dim
+        buf = self._bytes(eng, tag, nb + 4 * rows)
+        return buf, buf[:nb].view(6, rows, 2 * dim), buf[nb:].view(torch.int32)
 
     def _plane_block(self, eng, tag, rows: int, dim: int):
         """Plane buffers are kept between calls (tens of GiB per rank at n = 20: re-allocating them every
@@ -311,14 +455,92 @@ class ShardedFidelityKernel:
             return group_rank
         return self._dist.get_global_rank(self.group, group_rank)
 
+    # ------------------------------------------------------------------ host result
+    def _host_setup(self, n: int, dev):
+        """Two (n, n) float64 buffers in shared memory (/dev/shm), page-locked in every rank, so that each rank
+        copies its row block device -> host over its own PCIe link instead of funnelling K through one GPU."""
+        import mmap
+
+        import torch
+
+        dist = self._dist
+        if self._host is not None and self._host["n"] == n:
+            return self._host
+        self._host_close()
+        nbytes = max(n * n * 8, 8)
+        ok = False
+        if getattr(dev, "type", "cpu") == "cuda" and os.environ.get("B200SQ_DIST_HOST", "shm") == "shm":
+            try:
+                st = os.statvfs("/dev/shm")
+                ok = st.f_bavail * st.f_frsize > 2 * nbytes + (64 << 20)
+            except OSError:
+                ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self._host = {"n": n, "maps": None}
+            return self._host
+        paths = [None, None]
+        if self.rank == 0:
+            paths = [f"/dev/shm/b200sq_{os.getpid()}_{id(self):x}_{k}" for k in range(2)]
+            for path in paths:
+                fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, nbytes)
+                os.close(fd)
+        dist.broadcast_object_list(paths, src=self._global_rank(0), group=self.group)
+        maps, views, regs = [], [], []
+        rt = torch.cuda.cudart()
+        for path in paths:
+            fd = os.open(path, os.O_RDWR)
+            mm = mmap.mmap(fd, nbytes)
+            os.close(fd)
+            t = torch.frombuffer(mm, dtype=torch.float64, count=n * n).view(n, n)
+            err = rt.cudaHostRegister(t.data_ptr(), nbytes, 0)
+            regs.append(t.data_ptr() if int(err) == 0 else None)
+            maps.append(mm)
+            views.append(t)
+        dist.barrier(group=self.group)
+        if self.rank == 0:   # every rank holds its mapping: the names can go (nothing to leak on a crash)
+            for path in paths:
+                os.unlink(path)
+        self._host = {"n": n, "maps": maps, "views": views, "regs": regs, "turn": 0}
+        return self._host
+
+    def _host_close(self):
+        h, self._host = self._host, None
+        if not h or not h.get("maps"):
+            return
+        try:
+            import torch
+
+            rt = torch.cuda.cudart()
+            for p in h["regs"]:
+                if p is not None:
+                    rt.cudaHostUnregister(p)
+        except Exception:   # interpreter shutdown
+            pass
+        h["views"] = None   # the mappings themselves go when the last array referencing them does
+
     def evaluate(self, x, dst: int = 0) -> Optional[np.ndarray]:
-        """Full (N, N) Gram matrix as a NumPy array on rank ``dst`` (None elsewhere)."""
+        """Full (N, N) Gram matrix as a NumPy array on rank ``dst`` (None elsewhere).
+
+        On CUDA every rank copies its row block straight into a shared page-locked host buffer (two buffers are
+        used in turn: the array returned by a call stays valid until the call after the next one)."""
         import torch
 
         dist = self._dist
         rows, (r0, r1) = self.evaluate_rows(x)
         n = rows.shape[1]
         parts = row_partition(n, self.world)
+        host = self._host_setup(n, rows.device) if dst == 0 else {"maps": None}
+        if host.get("maps"):
+            view = host["views"][host["turn"]]
+            host["turn"] ^= 1
+            if r1 > r0:
+                view[r0:r1].copy_(rows, non_blocking=True)
+            torch.cuda.current_stream(rows.device).synchronize()
+            dist.barrier(group=self.group)
+            return view.numpy() if self.rank == dst else None
         if self.rank == dst:
             full = torch.empty((n, n), dtype=torch.float64, device=rows.device)
             full[r0:r1] = rows

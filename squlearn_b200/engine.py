@@ -292,6 +292,12 @@ class Engine:
             buf = torch.empty((nb + 4 * rows,), dtype=torch.int8, device=self.device)
         return buf, buf[:nb].view(12, rows, 2 * dim), buf[nb:].view(torch.int32)
 
+    def alloc_bytes(self, nbytes: int):
+        """Uninitialised int8 device buffer (exchange arenas and staging blocks of the multi-GPU Gram)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            return torch.empty((int(nbytes),), dtype=torch.int8, device=self.device)
+
     def slice_states(self, psi, planes, expo, row0: int = 0):
         """Write the digit planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes``."""
         torch = self._torch
@@ -320,6 +326,64 @@ class Engine:
                 expo_y.data_ptr(), planes_y.shape[1], int(y0), int(ny), dim, out.data_ptr(), out.stride(0), flags,
                 self._stream()))
         return out
+
+    def gram_jobs(self, planes_x, expo_x, jobs: Sequence[dict]):
+        """Several Gram blocks sharing the row planes in ONE persistent launch (b200sq_gram_jobs).
+
+        Every job is a dict: ``x0, nx`` (rows of planes_x), ``planes_y, expo_y`` (tensors or raw device pointers of
+        the column planes: only the 6 nat planes are read), ``rows_y`` (rows per plane of planes_y), ``y0, ny``,
+        ``out`` (2-D float64 view the block is written to), optional ``symmetric`` + ``diagonal``, optional
+        ``ready=(flag_ptr, value)`` (start the block when the uint32 at flag_ptr is >= value) and optional
+        ``align=(yx, yy, out2, weight)`` (fused target-alignment sums, see include/b200sq.h)."""
+        torch = self._torch
+        ptr = lambda t: int(t) if isinstance(t, int) else t.data_ptr()
+        arr = (_lib.GramJob * max(len(jobs), 1))()
+        for k, j in enumerate(jobs):
+            out = j["out"]
+            if out.dtype != torch.float64 or out.dim() != 2 or (out.shape[1] > 1 and out.stride(1) != 1):
+                raise ValueError("job output must be a row-major float64 2-D view")
+            if tuple(out.shape) != (j["nx"], j["ny"]):
+                raise ValueError("job output shape does not match (nx, ny)")
+            g = arr[k]
+            g.x0, g.nx, g.y0, g.ny = int(j["x0"]), int(j["nx"]), int(j["y0"]), int(j["ny"])
+            g.planes_y_dev, g.expo_y_dev = ptr(j["planes_y"]), ptr(j["expo_y"])
+            g.plane_rows_y = int(j["rows_y"])
+            g.K_dev, g.ldk = out.data_ptr(), int(out.stride(0)) if out.shape[0] > 1 else max(int(out.stride(0)), out.shape[1])
+            g.flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[j.get("diagonal", "one")]) if j.get("symmetric") else 0
+            if j.get("ready") is not None:
+                g.ready_flag_dev, g.ready_value = int(j["ready"][0]), int(j["ready"][1])
+            if j.get("align") is not None:
+                yx, yy, out2, weight = j["align"]
+                g.align_yx_dev, g.align_yy_dev, g.align_out_dev = ptr(yx), ptr(yy), ptr(out2)
+                g.align_weight = float(weight)
+        dim = planes_x.shape[2] // 2
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_gram_jobs(planes_x.data_ptr(), expo_x.data_ptr(), planes_x.shape[1], dim,
+                                                  len(jobs), arr, self._stream()))
+
+    # ------------------------------------------------------------------ peer plumbing (multi-GPU Gram)
+    def ipc_export(self, tensor):
+        """(64-byte CUDA IPC handle of the allocation holding ``tensor``, offset of the tensor inside it)."""
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        _lib.check(self._lib.b200sq_ipc_export(tensor.data_ptr(), handle, ctypes.byref(off)))
+        return handle.raw, int(off.value)
+
+    def ipc_open(self, handle: bytes) -> int:
+        base = ctypes.c_void_p()
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_ipc_open(handle, ctypes.byref(base)))
+        return int(base.value)
+
+    def ipc_close(self, base: int):
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_ipc_close(ctypes.c_void_p(base)))
+
+    def copy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream=None):
+        """Copy-engine device-to-device copy (dst may be a peer mapping) on ``stream`` (default: current)."""
+        st = self._stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_copy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), int(nbytes), st))
 
     @staticmethod
     def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:

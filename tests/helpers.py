@@ -89,7 +89,7 @@ def i8_slice(psi):
     psi = np.asarray(psi, dtype=np.complex128)
     n_rows, dim = psi.shape
     nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
-    rot = np.stack([psi.imag, -psi.real], axis=2).reshape(n_rows, 2 * dim)
+    rot = np.stack([-psi.imag, psi.real], axis=2).reshape(n_rows, 2 * dim)
     m = np.abs(nat).max(axis=1)
     expo = np.where(m > 0, np.frexp(m)[1], 0).astype(np.int32)
     planes = np.zeros((2 * I8_SLICES, n_rows, 2 * dim), dtype=np.int8)
@@ -104,7 +104,8 @@ def i8_slice(psi):
 
 
 def i8_gram(planes_x, expo_x, planes_y, expo_y):
-    """|<x|y>|^2 from digit planes: classes c <= 5 plus the pair (3, 3), like k_gram_i8 + k_gram_i8_final."""
+    """|<x|y>|^2 from digit planes: classes c <= 5 plus the pair (3, 3), like k_gram_i8 + k_gram_i8_final.
+    Re = nat(x) . nat(y), Im = rot(x) . nat(y): the column operand only needs its 6 nat planes."""
     S = I8_SLICES
     px = planes_x.astype(np.int64)
     py = planes_y.astype(np.int64)
@@ -113,7 +114,7 @@ def i8_gram(planes_x, expo_x, planes_y, expo_y):
     im = np.zeros_like(re)
     for c, lst in pairs:
         ar = sum(px[i] @ py[j].T for i, j in lst)
-        ai = sum(px[i] @ py[S + j].T for i, j in lst)
+        ai = sum(px[S + i] @ py[j].T for i, j in lst)
         re += ar * 2.0 ** (-8 * c)
         im += ai * 2.0 ** (-8 * c)
     scale = np.ldexp(1.0, 2 * (expo_x[:, None].astype(np.int64) + expo_y[None, :] - 12))

@@ -21,11 +21,11 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     names = _declared_symbols()
-    assert len(names) == 18
+    assert len(names) == len(_lib.EXPORTS) >= 23
     assert sorted(names) == sorted(_lib.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.b200sq_abi_version() == 1
+    assert lib.b200sq_abi_version() == 2
 
 
 def test_gate_struct_layout_matches_header():
@@ -36,6 +36,22 @@ def test_gate_struct_layout_matches_header():
     enum = re.search(r"enum b200sq_gate_kind \{(.*?)B200SQ_NUM_GATE_KINDS", text, re.S).group(1)
     header_names = [m.lower() for m in re.findall(r"B200SQ_(\w+)", enum)]
     assert header_names == _lib.GATE_KINDS
+
+
+def test_gram_job_struct_layout_matches_header():
+    """struct b200sq_gram_job: field order and size as declared in include/b200sq.h."""
+    text = open(os.path.join(ROOT, "include", "b200sq.h")).read()
+    body = re.search(r"typedef struct b200sq_gram_job \{(.*?)\} b200sq_gram_job;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip().lstrip("*") for n in decl.split(",")]
+            names[-len(decl.split(",")):] = [re.findall(r"(\w+)$", n.strip())[0] for n in decl.split(",")]
+    assert names == [f[0] for f in _lib.GramJob._fields_]
+    assert ctypes.sizeof(_lib.GramJob) == 120
+    assert _lib.GramJob.ready_flag_dev.offset == 80 and _lib.GramJob.align_weight.offset == 112
 
 
 def test_plan_without_gpu_and_error_reporting():

@@ -90,6 +90,20 @@ class _PlanesEngine(_OracleEngine):
         buf = torch.zeros((nb + 4 * rows,), dtype=torch.int8)
         return buf, buf[:nb].view(12, rows, 2 * dim), buf[nb:].view(torch.int32)
 
+    def alloc_bytes(self, nbytes):
+        return torch.zeros((int(nbytes),), dtype=torch.int8)
+
+    def gram_jobs(self, px, ex, jobs):
+        for j in jobs:
+            py, ey = j["planes_y"], j["expo_y"]
+            assert not isinstance(py, int)          # raw pointers only appear on the CUDA ipc path
+            if j.get("symmetric"):
+                k = self.gram_from_planes(px, ex, j["x0"], j["nx"], diagonal=j.get("diagonal", "one"))
+            else:
+                assert py.shape[0] >= 6 and py.shape[1] == j["rows_y"]
+                k = self.gram_from_planes(px, ex, j["x0"], j["nx"], py, ey, j["y0"], j["ny"])
+            j["out"].copy_(k)
+
     def slice_states(self, psi, planes, expo, row0=0):
         if psi.shape[0] == 0:
             return
@@ -197,3 +211,46 @@ def test_split_integer_scheme_error_on_circuit_states():
     got = i8_gram(planes, expo, planes, expo)
     want = np.abs(sv.conj() @ sv.T) ** 2
     assert np.max(np.abs(got - want)) < 2e-11
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter shift sharded by shifted variant (north star; optree_derivative.py:130-158): every rank evaluates a
+# slice of the variant list on the full batch, the partial gradients are all-reduced.  The engine is the host
+# emulator (the product's own plan + per-thread kernel code on the CPU).
+def _shift_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import squlearn_b200 as sq
+        from tests.emu_engine import EmuExecutor
+
+        ex = EmuExecutor()
+        enc = sq.ChebyshevRx(4, 2, closed=False)
+        circ = sq.B200Circuit(enc.get_program(2), [sq.SummedPaulis(4), sq.SinglePauli(4, 1, "X")])
+        X = np.random.default_rng(4).uniform(-0.9, 0.9, (7, 2))
+        p = enc.generate_initial_parameters(2, seed=0)
+        pobs = np.linspace(0.2, 1.0, 5)
+        g = sharded_parameter_shift(circ, ex, p, X, pobs)
+        np.save(os.path.join(out_dir, f"g_{rank}.npy"), g)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "g_single.npy"),
+                    sq.b200_gradient(circ, ex, param=p, x=X, param_obs=pobs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_parameter_shift_gloo(tmp_path, world):
+    mp.spawn(_shift_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = np.load(tmp_path / "g_single.npy")
+    assert want.shape == (7, 2, 16)
+    for r in range(world):                                   # every rank holds the complete gradient
+        assert np.max(np.abs(np.load(tmp_path / f"g_{r}.npy") - want)) < 1e-13
+    # and it is the oracle's gradient (generator route, independent of the shift rule)
+    X = np.random.default_rng(4).uniform(-0.9, 0.9, (7, 2))
+    p = oracle.chebyshev_rx_initial_parameters(4, 2, 2, seed=0)
+    ref = oracle.qnn_evaluate(oracle.chebyshev_rx(4, 2, 2, closed=False), 4, X, p,
+                              [("summed_paulis", {}), ("single_pauli", {"qubit": 1, "op_str": "X"})],
+                              np.linspace(0.2, 1.0, 5), ("dfdp",))["dfdp"]
+    assert np.max(np.abs(want - ref)) < 1e-12
