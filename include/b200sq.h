@@ -207,6 +207,11 @@ typedef struct b200sq_gram_job {
 B200SQ_API int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
                                 int64_t dim, int n_jobs, const b200sq_gram_job* jobs, void* stream);
 
+/* A job whose ready flag does not arrive within 20 s is multiplied anyway (the GPU must not hang on a lost
+ * peer) and counted: this returns the count of such jobs since the library was loaded (it synchronises the
+ * device; callers that use ready flags check it after a step and treat non-zero as an error).           */
+B200SQ_API int64_t b200sq_gram_ready_timeouts(void);
+
 /* Peer plumbing of the multi-GPU Gram (one process per GPU): export a device allocation to the other ranks of
  * the box (CUDA IPC), open a peer's export, and enqueue copy-engine copies (device-to-device, local or into a
  * peer mapping over NVLink) on a stream.  b200sq_ipc_export returns the 64-byte handle of the ALLOCATION that

@@ -483,6 +483,8 @@ int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_
     return 0;
 }
 
+int64_t b200sq_gram_ready_timeouts(void) { return (int64_t)gram_ready_timeouts(); }
+
 int b200sq_ipc_export(const void* dev_ptr, void* handle_out_64, int64_t* offset_out) {
     if (!dev_ptr || !handle_out_64 || !offset_out) return fail(2, "NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");

@@ -248,6 +248,18 @@ __device__ __forceinline__ int decode_unit(const I8Args& A, int u, int& tile, in
     return j;
 }
 
+// Blocks that never arrive must not hang the GPU: a producer gives up after kReadyTimeoutNs, counts the event here
+// (b200sq_gram_ready_timeouts) and multiplies whatever the buffer holds; the host side treats a non-zero count
+// as an error.
+__device__ unsigned int g_ready_timeouts = 0;
+constexpr unsigned long long kReadyTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -318,7 +330,14 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                 if (J.ready && !(ready_jobs >> ji & 1u)) {
                     // column planes pushed by a peer's copy engine: wait for its flag, then order the TMA
                     // (async proxy) reads behind the acquire
-                    while (ld_acquire_sys(J.ready) < J.ready_value) __nanosleep(200);
+                    const unsigned long long t_start = global_timer_ns();
+                    while (ld_acquire_sys(J.ready) < J.ready_value) {
+                        __nanosleep(200);
+                        if (global_timer_ns() - t_start > kReadyTimeoutNs) {
+                            atomicAdd(&g_ready_timeouts, 1u);
+                            break;
+                        }
+                    }
                     asm volatile("fence.proxy.async;" ::: "memory");
                     ready_jobs |= 1u << ji;
                 }
@@ -616,6 +635,15 @@ int encode_planes(CUtensorMap* map, void* base, uint64_t kbytes, uint64_t rows_t
 }
 
 }  // namespace
+
+unsigned int gram_ready_timeouts() {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_ready_timeouts, sizeof(v)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return v;
+}
 
 bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
 

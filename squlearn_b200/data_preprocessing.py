@@ -21,34 +21,32 @@ def convert_to_float64(x) -> np.ndarray:
 
 
 def _adjust_input(x, x_length: int, allow_single_array: bool) -> Tuple[np.ndarray, bool]:
-    multiple_inputs = False
-    shape = np.shape(x)
-    if shape == () and x_length == 1:
-        xx = np.array([[x]])
-    elif sum(shape) == 0 and x_length > 0:
+    """Rows of width ``x_length`` from a scalar / 1-D / 2-D input, and whether the caller passed several rows.
+
+    Shape contract (and messages) of src/squlearn/util/data_preprocessing.py:37-91: a 1-D input of width-1 data
+    is a column of samples — always "several" for features, only when longer than one for parameters; a 1-D
+    input of wider data is one row; an input without any extent is rejected when a width is expected."""
+    arr = np.asarray(x)
+    ndim, width = arr.ndim, int(x_length)
+    if ndim == 0 and width == 1:
+        return convert_to_float64(arr.reshape(1, 1)), False
+    if width > 0 and not any(arr.shape):
         raise ValueError(f"Received an empty input, but expected {x_length} features.")
-    elif len(shape) == 1:
-        if x_length == 1:
-            xx = np.array([np.array([v]) for v in x])
-            multiple_inputs = (shape[0] != 1) if allow_single_array else True
-        else:
-            if len(x) == x_length:
-                xx = np.array([x])
-            else:
-                raise ValueError(f"1D input has length {len(x)}, but expected {x_length} features.")
-    elif len(shape) == 2:
-        if shape[1] == x_length:
-            xx = x
-            multiple_inputs = True
-        else:
+    if ndim == 1:
+        if width == 1:
+            return convert_to_float64(arr.reshape(-1, 1)), (arr.shape[0] != 1 or not allow_single_array)
+        if arr.shape[0] != width:
+            raise ValueError(f"1D input has length {arr.shape[0]}, but expected {x_length} features.")
+        return convert_to_float64(arr.reshape(1, width)), False
+    if ndim == 2:
+        if arr.shape[1] != width:
             raise ValueError(
-                f"2D input has shape {shape}, but second dimension must match expected feature "
+                f"2D input has shape {arr.shape}, but second dimension must match expected feature "
                 f"dimension {x_length}.")
-    else:
-        raise ValueError(
-            f"Unsupported input shape {shape}. Expected scalar, 1D array of length {x_length}, "
-            f"or 2D array with shape (n_samples, {x_length}).")
-    return convert_to_float64(xx), multiple_inputs
+        return convert_to_float64(arr), True
+    raise ValueError(
+        f"Unsupported input shape {arr.shape}. Expected scalar, 1D array of length {x_length}, "
+        f"or 2D array with shape (n_samples, {x_length}).")
 
 
 def adjust_features(x: Union[np.ndarray, float], x_length: int) -> Tuple[np.ndarray, bool]:

@@ -379,6 +379,11 @@ class Engine:
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b200sq_ipc_close(ctypes.c_void_p(base)))
 
+    def ready_timeouts(self) -> int:
+        """Gram jobs whose ready flag never arrived (synchronises; non-zero means a peer's push was lost)."""
+        with self._torch.cuda.device(self.device):
+            return int(self._lib.b200sq_gram_ready_timeouts())
+
     def copy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream=None):
         """Copy-engine device-to-device copy (dst may be a peer mapping) on ``stream`` (default: current)."""
         st = self._stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)

@@ -17,7 +17,7 @@ from typing import Optional, Union
 
 import numpy as np
 
-from .data_preprocessing import convert_to_float64, extract_num_features
+from .data_preprocessing import adjust_features, convert_to_float64, extract_num_features
 from .executor import B200Circuit, Executor, b200_evaluate_statevector
 from .observables import ObservableBase, SinglePauli
 from .qnn import LowLevelQNN
@@ -41,6 +41,21 @@ def tikhonov_regularization(gram_matrix):
     if shift < 0:
         gram_matrix -= (shift - 1e-14) * np.identity(gram_matrix.shape[0])
     return gram_matrix
+
+
+def device_kernel(kernel, x, y=None):
+    """The kernel matrix of ANY kernel object as a float64 torch tensor on the device the kernel computes on:
+    ``evaluate_device`` where the kernel has one (the matrix never leaves HBM), otherwise its host ``evaluate``
+    (every reference kernel offers that: kernel_matrix_base.py:92-105) moved to the engine's device."""
+    import torch
+
+    if hasattr(kernel, "evaluate_device"):
+        return kernel.evaluate_device(x, y).to(torch.float64)
+    k = torch.as_tensor(np.asarray(kernel.evaluate(x, y), dtype=np.float64))
+    dev = getattr(getattr(getattr(kernel, "_executor", None), "engine", None), "device", None)
+    if dev is not None and str(dev) != "cpu":
+        k = k.to(dev)
+    return k
 
 
 class KernelMatrixBase:
@@ -100,6 +115,23 @@ class KernelMatrixBase:
         raise AttributeError("Regularization technique is unknown, please use either "
                              "'thresholding' or 'tikhonov'.")
 
+    def _regularize_device(self, k):
+        """The two regularisations of regularization.py:5-46 on a device tensor.  The kernel matrix is symmetric,
+        so the eigen-decomposition is the symmetric one (device ``eigh``; the reference calls scipy's general
+        ``eig`` and keeps the real part, which agrees to rounding for a symmetric matrix)."""
+        import torch
+
+        if self._regularization == "thresholding":
+            evals, evecs = torch.linalg.eigh(0.5 * (k + k.T))
+            return (evecs * evals.clamp(min=0.0)) @ evecs.T
+        if self._regularization == "tikhonov":
+            shift = torch.linalg.eigvalsh(0.5 * (k + k.T)).min()
+            if float(shift) < 0:
+                k = k - (shift - 1e-14) * torch.eye(k.shape[0], dtype=k.dtype, device=k.device)
+            return k
+        raise AttributeError("Regularization technique is unknown, please use either "
+                             "'thresholding' or 'tikhonov'.")
+
     def evaluate(self, x, y=None):
         raise NotImplementedError
 
@@ -147,56 +179,60 @@ class FidelityKernel(KernelMatrixBase):
                                            param=self._parameters, x=x, as_tensor=as_tensor)
 
     def evaluate_device(self, x, y=None):
-        """The Gram matrix as a float64 device tensor (no device->host copy)."""
+        """The kernel matrix as a float64 device tensor (no device->host copy), with everything ``evaluate``
+        applies — the duplicates policy, depolarising-noise mitigation (fidelity_kernel.py:264-330) and the
+        regularisation (:228-231) — done on the device, so that consumers that keep K in HBM (QKRR, QGPR,
+        kernel losses) see exactly what the reference's ``quantum_kernel.evaluate`` returns."""
+        import torch
+
         num_features = extract_num_features(x)
-        if y is None:
-            y = x
-        x = convert_to_float64(x)
-        y = convert_to_float64(y)
+        x = adjust_features(convert_to_float64(x), num_features)[0]
+        y = x if y is None else adjust_features(convert_to_float64(y), num_features)[0]
         self._initialize_kernel(num_features)
-        shots = self._executor.shots
-        self._executor.set_shots(None)  # fidelity_kernel_statevector.py:299-300
         symmetric = np.array_equal(x, y)
         eng = self._executor.engine
-        x_sv = self.states(x)
-        self.last_states = x_sv
-        if symmetric:
-            # "off_diagonal"/"none": diagonal := 1.0; "all": the reference never computes the
-            # symmetric diagonal and leaves it 0.0 (fidelity_kernel_statevector.py:358-383)
-            diag = "zero" if self._evaluate_duplicates == "all" else "one"
-            k = eng.gram(x_sv, None, diagonal=diag)
-        else:
-            k = eng.gram(x_sv, self.states(y))
-        self._executor.set_shots(shots)
+        shots = self._executor.shots
+        self._executor.set_shots(None)  # fidelity_kernel_statevector.py:299-300
+        try:
+            x_sv = self.states(x)
+            self.last_states = x_sv
+            if symmetric:
+                # "off_diagonal"/"none": diagonal := 1.0; "all": the reference never computes the
+                # symmetric diagonal and leaves it 0.0 (fidelity_kernel_statevector.py:358-383)
+                diag = "zero" if self._evaluate_duplicates == "all" else "one"
+                k = eng.gram(x_sv, None, diagonal=diag)
+            else:
+                k = eng.gram(x_sv, self.states(y))
+        finally:
+            self._executor.set_shots(shots)
+        if self._evaluate_duplicates == "none":
+            # identical statevectors are short-circuited to exactly 1.0 by the reference (:365-369, 375-378);
+            # identical states <=> identical feature rows: compared on the device, in row chunks
+            xd = eng.to_device(x, torch.float64)
+            yd = xd if symmetric else eng.to_device(y, torch.float64)
+            step = max(1, (1 << 24) // max(yd.shape[0] * max(yd.shape[1], 1), 1))
+            for r0 in range(0, xd.shape[0], step):
+                eq = (xd[r0:r0 + step, None, :] == yd[None, :, :]).all(dim=2)
+                k[r0:r0 + step][eq] = 1.0
+        if self._mit_depol_noise is not None:
+            print("WARNING: Advanced option. Do not use it within an squlearn.kernel workflow")
+            if not symmetric:
+                raise ValueError("Mitigating depolarizing noise works only for square matrices "
+                                 "computed on real backend")
+            inv = 2.0 ** (-self.num_qubits)
+            surv = torch.sqrt((torch.diagonal(k) - inv) / (1.0 - inv))
+            if self._mit_depol_noise == "msplit":
+                ss = torch.outer(surv, surv)
+                k = (k - inv * (1.0 - ss)) / ss
+            else:
+                m2 = torch.mean(surv) ** 2
+                k = (k - inv * (1.0 - m2)) / m2
+        if self._regularization is not None and k.shape[0] == k.shape[1]:
+            k = self._regularize_device(k)
         return k
 
     def evaluate(self, x, y=None) -> np.ndarray:
-        x = convert_to_float64(x)
-        y_in = x if y is None else convert_to_float64(y)
-        kernel_matrix = self._executor.engine.to_host(self.evaluate_device(x, y_in))
-        if self._evaluate_duplicates == "none":
-            # identical statevectors are short-circuited to exactly 1.0 by the reference
-            # (:365-369,375-378); identical states <=> identical feature rows
-            eq = (x[:, None, :] == y_in[None, :, :]).all(axis=2) if x.shape[0] * y_in.shape[0] <= 1 << 22 \
-                else None
-            if eq is not None:
-                kernel_matrix[eq] = 1.0
-        if self._mit_depol_noise is not None:
-            print("WARNING: Advanced option. Do not use it within an squlearn.kernel workflow")
-            if not np.array_equal(x, y_in):
-                raise ValueError("Mitigating depolarizing noise works only for square matrices "
-                                 "computed on real backend")
-            nq = self.num_qubits
-            surv = np.sqrt((np.diag(kernel_matrix) - 2.0 ** (-nq)) / (1 - 2.0 ** (-nq)))
-            if self._mit_depol_noise == "msplit":
-                ss = np.outer(surv, surv)
-                kernel_matrix = (kernel_matrix - 2.0 ** (-nq) * (1 - ss)) / ss
-            else:
-                m = np.mean(surv)
-                kernel_matrix = (kernel_matrix - 2.0 ** (-nq) * (1 - m ** 2)) / m ** 2
-        if self._regularization is not None and kernel_matrix.shape[0] == kernel_matrix.shape[1]:
-            kernel_matrix = self._regularize_matrix(kernel_matrix)
-        return kernel_matrix
+        return self._executor.engine.to_host(self.evaluate_device(x, y))
 
     def get_params(self, deep: bool = True) -> dict:
         params = {"evaluate_duplicates": self._evaluate_duplicates,
@@ -215,6 +251,12 @@ class FidelityKernel(KernelMatrixBase):
                 continue
             if k not in ("evaluate_duplicates", "mit_depol_noise", "regularization", "caching"):
                 raise ValueError(f"Invalid parameter {k!r}.")
+            if k == "evaluate_duplicates":
+                v = v.lower() if v else "none"
+                if v not in ("all", "off_diagonal", "none"):
+                    raise ValueError(f"Unknown evaluate_duplicates option: {v}")
+            if k == "mit_depol_noise" and v is not None and v not in ("msplit", "mmean"):
+                raise ValueError("Only msplit or mmean mitigation is available")
             setattr(self, "_" + k, v)
         if enc_update:
             num_parameters_backup = self.num_parameters
@@ -305,16 +347,31 @@ class ProjectedQuantumKernel(KernelMatrixBase):
         param, param_op = self._parameters[:nq], self._parameters[nq:]
         return self._qnn.evaluate(x, param, param_op, "f")["f"]
 
+    def evaluate_device(self, x, y=None):
+        """The kernel matrix as a float64 device tensor (Gaussian outer kernel: computed there; other outer
+        kernels: the host result of ``evaluate`` moved to the device), regularised like ``evaluate``."""
+        import torch
+
+        eng = self._executor.engine
+        if self._outer_kernel_name is None or self._outer_kernel_name.lower() != "gaussian":
+            return eng.to_device(self.evaluate(x, y), torch.float64)
+        fx = np.atleast_2d(self.evaluate_qnn(convert_to_float64(x)))
+        fy = fx if y is None else np.atleast_2d(self.evaluate_qnn(convert_to_float64(y)))
+        k = eng.rbf(fx, fy, self.gamma)
+        if self._regularization is not None and k.shape[0] == k.shape[1]:
+            k = self._regularize_device(k)
+        return k
+
     def evaluate(self, x, y=None) -> np.ndarray:
         x = convert_to_float64(x)
+        if self._outer_kernel_name is not None and self._outer_kernel_name.lower() == "gaussian":
+            # RBF(length_scale = 1/sqrt(2 gamma)) == exp(-gamma |.|^2)  (:973), on the device
+            return self.evaluate_device(x, y).cpu().numpy()
         fx = np.atleast_2d(self.evaluate_qnn(x))
         fy = None
         if y is not None:
             fy = np.atleast_2d(self.evaluate_qnn(convert_to_float64(y)))
-        if self._outer_kernel_name is not None and self._outer_kernel_name.lower() == "gaussian":
-            # RBF(length_scale = 1/sqrt(2 gamma)) == exp(-gamma |.|^2)  (:973), on the device
-            k = self._executor.engine.rbf(fx, fx if fy is None else fy, self.gamma).cpu().numpy()
-        elif self._outer_kernel_name is not None:
+        if self._outer_kernel_name is not None:
             from sklearn.gaussian_process import kernels as skk
 
             cls = {"matern": skk.Matern, "expsinesquared": skk.ExpSineSquared,

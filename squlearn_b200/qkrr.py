@@ -14,7 +14,7 @@ from typing import Optional, Union
 import numpy as np
 
 from .data_preprocessing import convert_to_float64, extract_num_features
-from .kernel import KernelMatrixBase
+from .kernel import KernelMatrixBase, device_kernel
 
 
 class QKRR:
@@ -37,17 +37,28 @@ class QKRR:
 
         return torch
 
+    def _to_device(self, a):
+        """A precomputed kernel matrix as a device tensor (the CUDA device when there is one)."""
+        torch = self._torch()
+        t = torch.as_tensor(np.asarray(a, dtype=np.float64))
+        return t.cuda() if torch.cuda.is_available() else t
+
     def fit(self, X, y):
         torch = self._torch()
         y = np.asarray(y, dtype=np.float64)
         if isinstance(self._quantum_kernel, str):
             if self._quantum_kernel != "precomputed":
                 raise ValueError("Unknown quantum kernel: {}".format(self._quantum_kernel))
-            k = torch.as_tensor(np.asarray(X, dtype=np.float64)).cuda()
-        elif isinstance(self._quantum_kernel, KernelMatrixBase):
+            k = self._to_device(X)
+        elif hasattr(self._quantum_kernel, "evaluate") or hasattr(self._quantum_kernel, "evaluate_device"):
+            # any kernel object: FidelityKernel / ProjectedQuantumKernel keep K in HBM (evaluate_device),
+            # wrappers such as KernelOptimizer and host-only kernels go through evaluate (qkrr.py:147-156)
             X = convert_to_float64(X)
-            self._quantum_kernel._initialize_kernel(num_features=extract_num_features(X))
-            k = self._quantum_kernel.evaluate_device(X)
+            if hasattr(self._quantum_kernel, "_initialize_kernel"):
+                self._quantum_kernel._initialize_kernel(num_features=extract_num_features(X))
+            if hasattr(self._quantum_kernel, "run_optimization"):
+                self._quantum_kernel.run_optimization(X, y)
+            k = device_kernel(self._quantum_kernel, X)
         else:
             raise ValueError("Unknown type of quantum kernel: {}".format(type(self._quantum_kernel)))
         self.X_train = X
@@ -73,8 +84,8 @@ class QKRR:
             raise ValueError("The fit() method has to be called beforehand.")
         torch = self._torch()
         if isinstance(self._quantum_kernel, str):
-            kt = torch.as_tensor(np.asarray(X, dtype=np.float64)).cuda()
+            kt = self._to_device(X).to(self.k_train.device)
         else:
-            kt = self._quantum_kernel.evaluate_device(convert_to_float64(X), self.X_train)
+            kt = device_kernel(self._quantum_kernel, convert_to_float64(X), self.X_train)
         self.k_testtrain = kt
         return (kt @ self._dual_dev).cpu().numpy()

@@ -33,3 +33,7 @@ def test_fidelity_kernel_c1_and_duplicate_policies_on_emulator():
 
 def test_projected_quantum_kernel_c2_on_emulator():
     gpu_tests.test_projected_quantum_kernel_config_c2(sq, EmuExecutor())
+
+
+def test_fidelity_kernel_regularization_mitigation_and_none_policy_on_emulator():
+    gpu_tests.test_fidelity_kernel_regularization_mitigation_and_none_policy(sq, EmuExecutor())

@@ -74,6 +74,8 @@ def _worker(rank, world, port, out_dir, big):
                 psi = fk.states(X[:1024])
                 k64 = ex.engine.gram(psi, None, precision="fp64").cpu().numpy()
                 save("big_vs_fp64", np.array([float(np.max(np.abs(k[:1024, :1024] - k64)))]))
+        torch.cuda.synchronize()
+        assert ex.engine.ready_timeouts() == 0      # every pushed block arrived (no flag wait gave up)
     finally:
         dist.destroy_process_group()
 

@@ -288,6 +288,59 @@ def test_fidelity_kernel_config_c1_and_duplicate_policies(sq, executor):
         fk.evaluate(np.zeros((3, 5, 2)))
 
 
+def test_fidelity_kernel_regularization_mitigation_and_none_policy(sq, executor):
+    """fidelity_kernel.py:215-231, 264-330 and regularization.py:5-46 restated with NumPy / SciPy on the oracle's
+    kernel matrix; evaluate() and evaluate_device() (what QKRR / QGPR / the kernel losses consume) agree."""
+    import scipy.linalg
+    import torch
+
+    n, d = 4, 2
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-0.95, 0.95, (40, d))
+    X[7] = X[3]                                   # an exact duplicate pair for the "none" policy
+    gates = oracle.chebyshev_pqc(n, 2, d)
+    p = oracle.chebyshev_pqc_initial_parameters(n, 2, d, seed=0)
+    k0 = oracle.fidelity_kernel(gates, n, X, None, p)
+    inv = 2.0 ** -n
+    surv = np.sqrt((np.diag(k0) - inv) / (1 - inv))
+    want = {"msplit": (k0 - inv * (1 - np.outer(surv, surv))) / np.outer(surv, surv),
+            "mmean": (k0 - inv * (1 - surv.mean() ** 2)) / surv.mean() ** 2}
+    for mit in ("msplit", "mmean"):
+        fk = sq.FidelityKernel(sq.ChebyshevPQC(n, 2), executor, mit_depol_noise=mit)
+        assert np.max(np.abs(fk.evaluate(X) - want[mit])) < GRAM_TOL
+        with pytest.raises(ValueError):
+            fk.evaluate(X, X[:5])
+    evals, evecs = scipy.linalg.eig(k0)
+    thr = np.real(evecs @ np.diag(evals.clip(min=0)) @ evecs.T)
+    for reg, ref in (("thresholding", thr), ("tikhonov", k0)):   # K is PSD: tikhonov leaves it alone
+        fk = sq.FidelityKernel(sq.ChebyshevPQC(n, 2), executor, regularization=reg)
+        got = fk.evaluate(X)
+        assert np.max(np.abs(got - ref)) < 1e-10, reg
+        assert np.max(np.abs(fk.evaluate_device(X).cpu().numpy() - got)) == 0.0
+        # rectangular matrices are never regularised (:228-231)
+        assert np.max(np.abs(fk.evaluate(X, X[:5]) - oracle.fidelity_kernel(gates, n, X, X[:5], p))) < GRAM_TOL
+    # an indefinite symmetric matrix through the device regularisers against regularization.py:5-46
+    a = rng.normal(size=(30, 30))
+    a = 0.5 * (a + a.T)
+    fk = sq.FidelityKernel(sq.ChebyshevPQC(n, 2), executor, regularization="thresholding")
+    dev = executor.engine.to_device(a, torch.float64)
+    ev, evc = scipy.linalg.eig(a)
+    assert np.max(np.abs(fk._regularize_device(dev).cpu().numpy() - np.real(evc @ np.diag(ev.clip(min=0)) @ evc.T))) < 1e-10
+    fk.set_params(regularization="tikhonov")
+    shifted = a - (np.min(np.real(scipy.linalg.eigvals(a))) - 1e-14) * np.identity(30)
+    assert np.max(np.abs(fk._regularize_device(dev.clone()).cpu().numpy() - shifted)) < 1e-10
+    # "none": identical feature rows give exactly 1.0, also through evaluate_device and for one 1-D sample
+    fk = sq.FidelityKernel(sq.ChebyshevPQC(n, 2), executor, evaluate_duplicates="none")
+    kd = fk.evaluate_device(X).cpu().numpy()
+    assert kd[3, 7] == 1.0 and kd[7, 3] == 1.0 and np.all(np.diag(kd) == 1.0)
+    assert np.max(np.abs(kd - oracle.fidelity_kernel(gates, n, X, None, p, evaluate_duplicates="none"))) < GRAM_TOL
+    assert fk.evaluate(X[3], X[7])[0, 0] == 1.0
+    with pytest.raises(ValueError):
+        fk.set_params(evaluate_duplicates="sometimes")
+    fk.set_params(evaluate_duplicates="ALL")
+    assert fk.get_params()["evaluate_duplicates"] == "all"
+
+
 def test_closed_form_goldens_through_the_product(sq, executor, goldens):
     g = goldens["fqk_closed_form"]["multi"]
     lay = sq.LayeredEncodingCircuit(2)

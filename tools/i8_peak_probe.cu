@@ -45,9 +45,13 @@ __global__ void __launch_bounds__(128, 1) k_probe(int iters) {
     const uint32_t tmem_slot = bars + 8 * kStages;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    // operand bytes: anything non-trivial
-    for (int i = threadIdx.x; i < 3 * kTileBytes / 4; i += blockDim.x)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 4 * i), "r"(0x01020304u * (uint32_t)(i % 61 + 1)) : "memory");
+    // operand bytes: pseudo-random, like the digit planes (the switching activity of the data sets the power the
+    // MMAs draw, and the sustained figure is a power-capped one)
+    for (int i = threadIdx.x; i < 3 * kTileBytes / 4; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u + 12345u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 4 * i), "r"(h) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bars + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
