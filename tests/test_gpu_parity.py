@@ -250,6 +250,28 @@ def test_gram_int8_matches_fp64_on_circuit_states(sq, executor):
     assert torch.equal(k8, k8.T)
 
 
+def test_config_c5_size_int8_gram_on_16_points(sq, executor):
+    """BASELINE configs[4] state size (20 qubits, K' = 2^21 int8 per row): the INT8 Gram of 16 + 5 points against
+    the oracle; the measured maximum error is printed (the scheme's bound grows with K')."""
+    import torch
+
+    n, d = 20, 4
+    X = np.random.default_rng(5).uniform(-0.95, 0.95, (16, d))
+    enc = sq.ChebyshevPQC(n, 2)
+    p = enc.generate_initial_parameters(d, seed=0)
+    want_sv = oracle.simulate(oracle.chebyshev_pqc(n, 2, d), n, X, oracle.chebyshev_pqc_initial_parameters(n, 2, d, seed=0))
+    eng = executor.engine
+    psi = eng.simulate(sq.B200Circuit(enc.get_program(d)).compiled(eng, p), X)
+    err_sv = float(np.max(np.abs(psi.cpu().numpy() - want_sv)))
+    k8 = eng.gram(psi, None, diagonal="computed", precision="int8").cpu().numpy()
+    k8r = eng.gram(psi[:5], psi[3:], precision="int8").cpu().numpy()
+    want = np.abs(want_sv.conj() @ want_sv.T) ** 2
+    err, err_r = float(np.max(np.abs(k8 - want))), float(np.max(np.abs(k8r - want[:5, 3:])))
+    print(f"C5-size (n=20) INT8 Gram on 16 points: |K - oracle| = {err:.2e} (rect {err_r:.2e}), states {err_sv:.2e}")
+    assert err_sv < STATE_TOL
+    assert err < INT8_TOL and err_r < INT8_TOL
+
+
 # ------------------------------------------------------------------------------ expectation values
 def test_expvals_fused_and_from_memory(sq, executor):
     rng = np.random.default_rng(11)
