@@ -203,9 +203,17 @@ typedef struct b200sq_gram_job {
     const double* align_yy_dev;
     double* align_out_dev;          /* [2] float64, accumulated with atomics (zero it first)             */
     double align_weight;
+    double* K_mirror_dev;           /* NULL, or (rectangular jobs): also store the transpose,            */
+    int64_t ldk_mirror;             /* K_mirror[j][i] = K[i][j] — may be a peer mapping (NVLink stores)  */
 } b200sq_gram_job;
 B200SQ_API int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
                                 int64_t dim, int n_jobs, const b200sq_gram_job* jobs, void* stream);
+
+/* Enqueue a wait on `stream` until flags_dev[which[k]] >= value for every k < n (n <= 32; uint32 flags in
+ * device memory written by peers, e.g. "my mirrored blocks are stored"); gives up after 20 s like the ready
+ * flags of the Gram jobs (counted by b200sq_gram_ready_timeouts).                                        */
+B200SQ_API int b200sq_wait_flags(const uint32_t* flags_dev, const int32_t* which, int n, uint32_t value,
+                                 void* stream);
 
 /* A job whose ready flag does not arrive within 20 s is multiplied anyway (the GPU must not hang on a lost
  * peer) and counted: this returns the count of such jobs since the library was loaded (it synchronises the

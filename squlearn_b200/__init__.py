@@ -28,6 +28,8 @@ from .program import Angle, GateOp, Program
 from .qgpr import QGPR
 from .qkrr import QKRR
 from .qnn import LowLevelQNN
+from .qnn_training import (SLSQP, LBFGSB, Adam, MeanSquaredError, QNNLossBase, QNNRegressor, SquaredLoss,
+                           VarianceLoss, train)
 from .qsvc import QSVC
 from .qrc import QRCRegressor, QRCClassifier, random_pauli_list
 
@@ -39,5 +41,6 @@ __all__ = [
     "LayeredEncodingCircuit", "EncodingCircuitBase", "SinglePauli", "SummedPaulis",
     "CustomObservable", "Program", "GateOp", "Angle", "QRCRegressor", "QRCClassifier",
     "random_pauli_list", "b200_evaluate", "b200_evaluate_statevector", "b200_gradient",
-    "b200_operator_gradient", "QKRR", "QGPR", "QSVC", "TargetAlignment", "NLL", "KernelOptimizer", "ScipyMinimize",
+    "b200_operator_gradient", "QKRR", "QGPR", "QSVC", "QNNRegressor", "SquaredLoss", "MeanSquaredError", "VarianceLoss", "QNNLossBase", "train",
+    "SLSQP", "LBFGSB", "Adam", "TargetAlignment", "NLL", "KernelOptimizer", "ScipyMinimize",
 ]

@@ -63,6 +63,7 @@ class GramJob(ctypes.Structure):
         ("ready_flag_dev", ctypes.c_void_p),
         ("align_yx_dev", ctypes.c_void_p), ("align_yy_dev", ctypes.c_void_p),
         ("align_out_dev", ctypes.c_void_p), ("align_weight", ctypes.c_double),
+        ("K_mirror_dev", ctypes.c_void_p), ("ldk_mirror", ctypes.c_int64),
     ]
 
 
@@ -70,7 +71,7 @@ EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_expvals", "b200sq_expvals",
-    "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
+    "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_wait_flags", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
     "b200sq_copy_async", "b200sq_rbf",
     "b200sq_launch_count",
 ]
@@ -128,6 +129,8 @@ def load():
     lib.b200sq_gram_from_planes.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, i64, vp, i64, c.c_uint32, vp]
     lib.b200sq_gram_jobs.restype = c.c_int
     lib.b200sq_gram_jobs.argtypes = [vp, vp, i64, i64, c.c_int, c.POINTER(GramJob), vp]
+    lib.b200sq_wait_flags.restype = c.c_int
+    lib.b200sq_wait_flags.argtypes = [vp, c.POINTER(i32), c.c_int, c.c_uint32, vp]
     lib.b200sq_gram_ready_timeouts.restype = i64
     lib.b200sq_gram_ready_timeouts.argtypes = []
     lib.b200sq_ipc_export.restype = c.c_int

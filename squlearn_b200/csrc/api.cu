@@ -476,10 +476,20 @@ int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_
         if ((J.flags & B200SQ_GRAM_SYMMETRIC) && (J.planes_y_dev != planes_x_dev || J.x0 != J.y0 || J.nx != J.ny))
             return fail(2, "symmetric Gram job needs identical operands");
         if (J.align_yx_dev && !J.align_out_dev) return fail(2, "align_out_dev is NULL");
+        if (J.K_mirror_dev && J.ldk_mirror < J.nx) return fail(2, "ldk_mirror is smaller than the block height");
     }
     int e = launch_gram_jobs((const int8_t*)planes_x_dev, expo_x_dev, plane_rows_x, dim, n_jobs, jobs,
                              (cudaStream_t)stream_);
     if (e) return cuda_fail(e, "gram launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
+int b200sq_wait_flags(const uint32_t* flags_dev, const int32_t* which, int n, uint32_t value, void* stream_) {
+    if (n <= 0) return 0;
+    if (!flags_dev || !which) return fail(2, "NULL argument");
+    if (n > 32) return fail(2, "at most 32 flags per wait");
+    int e = launch_wait_flags(flags_dev, which, n, value, (cudaStream_t)stream_);
+    if (e) return cuda_fail(e, "wait-flags launch");
     return 0;
 }
 

@@ -74,6 +74,8 @@ struct I8Job {
     int64_t row0_b, rows_b;   // first row / rows per digit plane of the column operand
     int64_t ldk;
     double* K;                // [nx][ldk]
+    double* K_mirror;         // nullptr, or [ny][ldm]: the transpose of the block (rectangular jobs)
+    int64_t ldm;
     const int* ex;            // row exponents of the local planes, of the column planes
     const int* ey;
     const uint32_t* ready;    // nullptr, or: the column planes are complete when *ready >= ready_value
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
     const bool diag_tile = sym && bm == bn;
     const int64_t nx = J.nx, ny = J.ny, ldk = J.ldk;
     double* __restrict__ K = J.K;
+    double* __restrict__ Km = sym ? nullptr : J.K_mirror;
     const int* __restrict__ ex = J.ex + J.row0_a;
     const int* __restrict__ ey = J.ey + J.row0_b;
     const double* __restrict__ ayx = J.align_yx;
@@ -592,10 +595,15 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
                 const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
                 const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
                 if (i < nx && j < ny) K[j * ldk + i] = sm[ty + 8 * qd][tx];
+            } else if (Km) {        // transpose of a rectangular block for the owner of its columns
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) Km[j * J.ldm + i] = sm[ty + 8 * qd][tx];
             }
         }
         __syncthreads();
     }
+    if (Km) __threadfence_system();   // peer stores are performed before the kernel (and the flag behind it) completes
     if (ayx) {
         for (int o = 16; o > 0; o >>= 1) {
             a_ky += __shfl_xor_sync(0xffffffffu, a_ky, o);
@@ -635,6 +643,39 @@ int encode_planes(CUtensorMap* map, void* base, uint64_t kbytes, uint64_t rows_t
 }
 
 }  // namespace
+
+struct WaitArgs {
+    int32_t which[32];
+    int n;
+    uint32_t value;
+};
+
+__global__ void k_wait_flags(const uint32_t* __restrict__ flags, const WaitArgs w) {
+    if ((int)threadIdx.x < w.n) {
+        const uint32_t* f = flags + w.which[threadIdx.x];
+        const unsigned long long t_start = global_timer_ns();
+        while (ld_acquire_sys(f) < w.value) {
+            __nanosleep(500);
+            if (global_timer_ns() - t_start > kReadyTimeoutNs) {
+                atomicAdd(&g_ready_timeouts, 1u);
+                break;
+            }
+        }
+    }
+}
+
+int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    if (n > 32) return (int)cudaErrorInvalidValue;
+    WaitArgs w;
+    memset(&w, 0, sizeof(w));
+    for (int k = 0; k < n; ++k) w.which[k] = which[k];
+    w.n = n;
+    w.value = value;
+    k_wait_flags<<<1, 32, 0, stream>>>(flags, w);
+    count_launch();
+    return (int)cudaGetLastError();
+}
 
 unsigned int gram_ready_timeouts() {
     unsigned int v = 0;
@@ -802,6 +843,8 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         J.rows_b = in.plane_rows_y;
         J.ldk = in.ldk;
         J.K = in.K_dev;
+        J.K_mirror = in.K_mirror_dev;
+        J.ldm = in.ldk_mirror;
         J.ex = ex;
         J.ey = in.expo_y_dev;
         J.ready = in.ready_flag_dev;

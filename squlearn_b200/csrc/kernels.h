@@ -31,6 +31,7 @@ int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int6
 
 // Split-integer (INT8 tcgen05) Gram: see gram_i8.cu.  Falls back to nothing: callers check gram_i8_supported.
 bool gram_i8_supported(int64_t dim);
+int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream);
 unsigned int gram_ready_timeouts();   // jobs whose ready flag never arrived (synchronises the device)
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream);

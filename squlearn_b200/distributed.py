@@ -97,10 +97,13 @@ def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
     return mine
 
 
-def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, align: int = 1024):
-    """Receive arena of a rank: one slot [6 nat planes | row exponents] per off-diagonal job, in arrival order.
-    Returns ([{"owner", "cols", "rows", "off", "expo_off"}], flags offset, total bytes); every rank computes
-    the layout of every other rank from the job table alone (a sender needs the receiver's slot offsets)."""
+def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_local: int = 0, n: int = 0,
+                 align: int = 1024):
+    """Receive arena of a rank: one slot [6 nat planes | row exponents] per off-diagonal job, in arrival order,
+    then the arrival flags, the "mirrored blocks stored" flags and the rank's row block K[r0:r1, :] itself (peers
+    store the transposes of their blocks straight into it).  Returns ([{"owner", "cols", "rows", "off",
+    "expo_off"}], {"flags", "done", "rows", "total"} byte offsets); every rank computes the layout of every other
+    rank from the job table alone (a sender needs the receiver's offsets)."""
     slots, off = [], 0
     mine = [j for j in jobs_of_rank if not j["diag"]]
     mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
@@ -110,7 +113,10 @@ def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, alig
         slots.append({"owner": j["owner"], "cols": j["cols"], "rows": w, "off": off, "expo_off": off + nb})
         off = (off + nb + 4 * w + align - 1) // align * align
     flags_off = off
-    return slots, flags_off, flags_off + 4 * world + align
+    done_off = flags_off + (4 * world + 127) // 128 * 128
+    rows_off = (done_off + 4 * world + align - 1) // align * align
+    total = rows_off + 8 * n_local * n + align
+    return slots, {"flags": flags_off, "done": done_off, "rows": rows_off, "total": total}
 
 
 class ShardedFidelityKernel:
@@ -146,6 +152,7 @@ class ShardedFidelityKernel:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.diagonal = diagonal
+        self._borrow_rows = False   # evaluate() reads the shared row block in place (it copies it to the host)
 
     # ------------------------------------------------------------------ digit-plane path
     def _exchange_mode(self, eng, equal: bool, n_local: int, block_bytes: int) -> str:
@@ -161,7 +168,8 @@ class ShardedFidelityKernel:
         return mode
 
     def _peer_setup(self, eng, parts, jobs, dim):
-        """Arena, flags and the peer mappings of the ipc exchange (cached while the shapes stay the same)."""
+        """Arena, flags, the shared row block and the peer mappings of the ipc exchange (cached while the shapes
+        stay the same)."""
         import torch
 
         dist = self._dist
@@ -169,35 +177,53 @@ class ShardedFidelityKernel:
         if self._peer is not None and self._peer["key"] == key:
             return self._peer
         self._peer_close()
-        slots, flags_off, total = arena_layout(jobs[self.rank], self.rank, self.world, dim)
-        arena = eng.alloc_bytes(total)
-        arena[flags_off:flags_off + 4 * self.world].zero_()
+        n = parts[-1][1]
+        lay = lambda q: arena_layout(jobs[q], q, self.world, dim, parts[q][1] - parts[q][0], n)
+        slots, offs = lay(self.rank)
+        arena = eng.alloc_bytes(offs["total"])
+        arena[offs["flags"]:offs["rows"]].zero_()
         handle, off = eng.ipc_export(arena)
         infos = [None] * self.world
         dist.all_gather_object(infos, (handle, off), group=self.group)
         r0, r1 = parts[self.rank]
-        pushes = []   # (ring distance of me as seen from q, q, local rows a..b, slot offsets in q's arena)
-        bases = {}
+        bases, layouts = {}, {}
+
+        def base_of(q):
+            if q not in bases:
+                bases[q] = eng.ipc_open(infos[q][0])
+                layouts[q] = lay(q)
+            return bases[q] + infos[q][1]
+
+        pushes = []    # my planes -> the arenas of the ranks whose jobs read them, nearest consumer first
+        writers = []   # ranks that store mirrored blocks into my rows (they signal my "done" flags)
         for q in range(self.world):
             if q == self.rank:
                 continue
-            q_slots, q_flags_off, _ = arena_layout(jobs[q], q, self.world, dim)
+            q_slots, q_offs = lay(q)
             for sl in q_slots:
                 if sl["owner"] != self.rank:
                     continue
-                if q not in bases:
-                    bases[q] = eng.ipc_open(infos[q][0])
-                base = bases[q] + infos[q][1]
+                base = base_of(q)
                 a, b = sl["cols"]
                 pushes.append({"dist": ring_distance(q, self.rank, self.world), "q": q, "a": a - r0, "b": b - r0,
                                "dst": base + sl["off"], "dst_expo": base + sl["expo_off"],
-                               "dst_flag": base + q_flags_off + 4 * self.rank})
+                               "dst_flag": base + q_offs["flags"] + 4 * self.rank})
+                if q not in writers:
+                    writers.append(q)
         pushes.sort(key=lambda p: (p["dist"], p["q"]))
+        owners = {}    # owner of the columns of one of my jobs -> (its rows pointer, its "done" flag for me)
+        for sl in slots:
+            q = sl["owner"]
+            base = base_of(q)
+            owners[q] = (base + layouts[q][1]["rows"], base + layouts[q][1]["done"] + 4 * self.rank, parts[q][0])
         torch.cuda.synchronize(eng.device)
         dist.barrier(group=self.group)   # every arena is mapped and zeroed before the first push
-        self._peer = {"key": key, "arena": arena, "slots": slots, "flags_off": flags_off, "pushes": pushes,
-                      "bases": bases, "epoch": 0, "stream": torch.cuda.Stream(device=eng.device),
-                      "sliced": torch.cuda.Event(), "pushed": None, "eng": eng}
+        n_local = r1 - r0
+        rows = arena[offs["rows"]:offs["rows"] + 8 * n_local * n].view(torch.float64).view(n_local, n)
+        self._peer = {"key": key, "arena": arena, "slots": slots, "offs": offs, "pushes": pushes, "writers": writers,
+                      "owners": owners, "rows": rows, "bases": bases, "epoch": 0,
+                      "stream": torch.cuda.Stream(device=eng.device), "sliced": torch.cuda.Event(), "pushed": None,
+                      "eng": eng}
         return self._peer
 
     def _peer_close(self):
@@ -217,8 +243,9 @@ class ShardedFidelityKernel:
         self._peer_close()
         self._host_close()
 
-    def _rows_planes(self, eng, x, parts, jobs, rows, dim):
-        """The digit-plane (INT8) path: slice once, exchange the nat planes, ONE job-table Gram launch."""
+    def _rows_planes(self, eng, x, parts, jobs, dim):
+        """The digit-plane (INT8) path: slice once, exchange the nat planes, ONE job-table Gram launch.
+        Returns (rows, jobs left for the NCCL mirror exchange or None when the blocks were mirrored by peer stores)."""
         import torch
 
         dist = self._dist
@@ -234,6 +261,10 @@ class ShardedFidelityKernel:
             peer = self._peer_setup(eng, parts, jobs, dim)
             if peer["pushed"] is not None:   # my previous pushes read the local planes
                 torch.cuda.current_stream(eng.device).wait_event(peer["pushed"])
+            rows = peer["rows"]              # peers store their mirrored blocks into this (shared) row block
+        else:
+            rows = torch.zeros((n_local, parts[-1][1]), dtype=torch.float64, device=eng.device
+                               if hasattr(eng, "device") else "cpu")
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
         _mark("states")
         eng.slice_states(psi_local, planes, expo, 0)
@@ -263,11 +294,15 @@ class ShardedFidelityKernel:
             peer["pushed"] = torch.cuda.Event()
             peer["pushed"].record(st)
             epoch_t.record_stream(st)
-            flags_ptr = arena.data_ptr() + peer["flags_off"]
+            flags_ptr = arena.data_ptr() + peer["offs"]["flags"]
+            n = rows.shape[1]
             for j, sl in zip(mine, peer["slots"]):
                 w = sl["rows"]
                 j["planes_y"], j["expo_y"] = arena.data_ptr() + sl["off"], arena.data_ptr() + sl["expo_off"]
                 j["rows_y"], j["y0"], j["ready"] = w, 0, (flags_ptr + 4 * j["owner"], epoch)
+                # the transposed block goes straight into the owner's row block (peer stores from the epilogue)
+                o_rows, _, c0 = peer["owners"][j["owner"]]
+                j["mirror"] = (o_rows + 8 * ((j["cols"][0] - c0) * n + j["rows"][0]), n)
             _mark("diag")
             _mark("exchange")
         elif mode == "allgather":
@@ -314,10 +349,18 @@ class ShardedFidelityKernel:
             w = j["cols"][1] - j["cols"][0]
             j["blk"] = rows[ra - r0:rb - r0, j["cols"][0]:j["cols"][1]]
             glist.append({"x0": ra - r0, "nx": rb - ra, "planes_y": j["planes_y"], "expo_y": j["expo_y"],
-                          "rows_y": j["rows_y"], "y0": j["y0"], "ny": w, "out": j["blk"], "ready": j["ready"]})
+                          "rows_y": j["rows_y"], "y0": j["y0"], "ny": w, "out": j["blk"], "ready": j["ready"],
+                          "mirror": j.get("mirror")})
         if glist:
             eng.gram_jobs(planes, expo, glist)
-        return mine
+        if mode == "ipc":
+            # tell every owner that its mirrored blocks are stored; wait for the ranks that store into my rows
+            for q in sorted({j["owner"] for j in mine}):
+                eng.copy_async(peer["owners"][q][1], epoch_t.data_ptr(), 4)
+            if peer["writers"]:
+                eng.wait_flags(arena.data_ptr() + peer["offs"]["done"], peer["writers"], epoch)
+            return rows, None       # nothing left for the NCCL mirror exchange
+        return rows, mine
 
     def _rows_states(self, eng, x, parts, jobs, rows, dim):
         """The FP64 path: exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
@@ -394,14 +437,17 @@ class ShardedFidelityKernel:
         jobs = gram_jobs(parts)
         n_local = r1 - r0
         dev = getattr(eng, "device", "cpu")
-        rows = torch.zeros((n_local, n), dtype=torch.float64, device=dev)
         use_planes = (hasattr(eng, "gram_jobs")
                       and eng.gram_precision(n, n, dim, self.precision) == "int8")  # same decision on every rank
         if use_planes:
-            mine = self._rows_planes(eng, x, parts, jobs, rows, dim)
+            rows, mine = self._rows_planes(eng, x, parts, jobs, dim)
         else:
+            rows = torch.zeros((n_local, n), dtype=torch.float64, device=dev)
             mine = self._rows_states(eng, x, parts, jobs, rows, dim)
         _mark("rect")
+        if mine is None:   # ipc exchange: the row block is complete (and shared with the peers: hand out a copy)
+            _mark("mirror")
+            return (rows if self._borrow_rows else rows.clone()), (r0, r1)
         # ---- mirror: every off-diagonal piece, transposed, belongs to the owner of its columns
         ops, placements = [], []
         for j in mine:
@@ -529,7 +575,11 @@ class ShardedFidelityKernel:
         import torch
 
         dist = self._dist
-        rows, (r0, r1) = self.evaluate_rows(x)
+        self._borrow_rows = True
+        try:
+            rows, (r0, r1) = self.evaluate_rows(x)
+        finally:
+            self._borrow_rows = False
         n = rows.shape[1]
         parts = row_partition(n, self.world)
         host = self._host_setup(n, rows.device) if dst == 0 else {"maps": None}

@@ -333,8 +333,9 @@ class Engine:
         Every job is a dict: ``x0, nx`` (rows of planes_x), ``planes_y, expo_y`` (tensors or raw device pointers of
         the column planes: only the 6 nat planes are read), ``rows_y`` (rows per plane of planes_y), ``y0, ny``,
         ``out`` (2-D float64 view the block is written to), optional ``symmetric`` + ``diagonal``, optional
-        ``ready=(flag_ptr, value)`` (start the block when the uint32 at flag_ptr is >= value) and optional
-        ``align=(yx, yy, out2, weight)`` (fused target-alignment sums, see include/b200sq.h)."""
+        ``ready=(flag_ptr, value)`` (start the block when the uint32 at flag_ptr is >= value), optional
+        ``align=(yx, yy, out2, weight)`` (fused target-alignment sums, see include/b200sq.h) and optional
+        ``mirror=(ptr, ld)`` (also store the transposed block there: the owner of the columns, maybe a peer)."""
         torch = self._torch
         ptr = lambda t: int(t) if isinstance(t, int) else t.data_ptr()
         arr = (_lib.GramJob * max(len(jobs), 1))()
@@ -356,6 +357,8 @@ class Engine:
                 yx, yy, out2, weight = j["align"]
                 g.align_yx_dev, g.align_yy_dev, g.align_out_dev = ptr(yx), ptr(yy), ptr(out2)
                 g.align_weight = float(weight)
+            if j.get("mirror") is not None:      # (pointer of the transposed block, its leading dimension)
+                g.K_mirror_dev, g.ldk_mirror = int(j["mirror"][0]), int(j["mirror"][1])
         dim = planes_x.shape[2] // 2
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200sq_gram_jobs(planes_x.data_ptr(), expo_x.data_ptr(), planes_x.shape[1], dim,
@@ -378,6 +381,13 @@ class Engine:
     def ipc_close(self, base: int):
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b200sq_ipc_close(ctypes.c_void_p(base)))
+
+    def wait_flags(self, flags_ptr: int, which: Sequence[int], value: int):
+        """Enqueue a wait on the current stream until the uint32 flags flags_ptr[which[k]] are all >= value."""
+        arr = (ctypes.c_int32 * max(len(which), 1))(*[int(w) for w in which])
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_wait_flags(ctypes.c_void_p(flags_ptr), arr, len(which), int(value),
+                                                   self._stream()))
 
     def ready_timeouts(self) -> int:
         """Gram jobs whose ready flag never arrived (synchronises; non-zero means a peer's push was lost)."""

@@ -50,7 +50,7 @@ def test_gram_job_struct_layout_matches_header():
             names += [n.strip().lstrip("*") for n in decl.split(",")]
             names[-len(decl.split(",")):] = [re.findall(r"(\w+)$", n.strip())[0] for n in decl.split(",")]
     assert names == [f[0] for f in _lib.GramJob._fields_]
-    assert ctypes.sizeof(_lib.GramJob) == 120
+    assert ctypes.sizeof(_lib.GramJob) == 136
     assert _lib.GramJob.ready_flag_dev.offset == 80 and _lib.GramJob.align_weight.offset == 112
 
 

@@ -546,3 +546,69 @@ def test_input_derivative_golden_and_finite_differences(sq, executor, goldens):
         fp = oracle.qnn_evaluate(gates, n, X + e, p, ("summed_paulis", {}), pop, ("f",))["f"]
         fm = oracle.qnn_evaluate(gates, n, X - e, p, ("summed_paulis", {}), pop, ("f",))["f"]
         assert np.max(np.abs(got[:, j] - (fp - fm) / (2 * h))) < 1e-7
+
+
+# ------------------------------------------------------------------------------ QNN training (row a14)
+def test_qnn_regressor_reference_golden_and_fit(sq, executor, goldens, regression_data):
+    """tests/qnn/test_qnnr.py:20-43,179-198: the reference's predict golden through QNNRegressor; then the same
+    model is fitted with SLSQP(maxiter=2) like test_fit (:75-95) and the loss must go down; SquaredLoss gradient
+    against central differences of its value (squared_loss.py:35-61,92-143)."""
+    X, y = regression_data
+    rng = np.random.default_rng(seed=30)
+    pqc, op = sq.ChebyshevRx(2, 1), sq.SummedPaulis(2)
+    make = lambda loss, opt: sq.QNNRegressor(pqc, op, executor, loss, opt, rng.random(pqc.num_parameters),
+                                             rng.random(op.num_parameters))
+    reg = make(sq.MeanSquaredError(), sq.SLSQP(options={"maxiter": 2}))
+    with pytest.raises(RuntimeError, match="The model is not fitted."):
+        reg.predict(X)
+    reg._initialize_lowlevel_qnn(1)
+    reg._param, reg._param_op, reg._is_fitted = np.linspace(0.1, 0.4, 4), np.linspace(0.1, 0.3, 3), True
+    pred = reg.predict(X)
+    assert pred.shape == y.shape
+    assert np.allclose(pred, goldens["qnnr_predict"]["expected"], atol=1e-8)
+
+    reg = make(sq.MeanSquaredError(), sq.SLSQP(options={"maxiter": 2}))
+    reg.fit(X, y)
+    assert reg._is_fitted
+    assert not np.allclose(reg.param, reg.param_ini) and not np.allclose(reg.param_op, reg.param_op_ini)
+    qnn = reg._qnn
+    mse = lambda p, po: float(np.mean((qnn.evaluate(X, p, po, "f")["f"] - y) ** 2))
+    assert mse(reg.param, reg.param_op) < mse(reg.param_ini, reg.param_op_ini)
+
+    loss = sq.SquaredLoss()
+    loss.set_opt_param_op(True)
+    p0, po0 = np.linspace(0.3, 0.9, 4), np.array([0.2, -0.4, 0.7])
+    w = np.linspace(0.5, 1.5, len(y))
+    vals = qnn.evaluate(X, p0, po0, *loss.gradient_args_tuple)
+    g_p, g_op = loss.gradient(vals, ground_truth=y, weights=w)
+    theta0 = np.concatenate([p0, po0])
+    num = np.zeros_like(theta0)
+    for k in range(len(theta0)):
+        e = np.zeros_like(theta0)
+        e[k] = 1e-5
+        f = lambda t: loss.value(qnn.evaluate(X, t[:4], t[4:], "f"), ground_truth=y, weights=w)
+        num[k] = (f(theta0 + e) - f(theta0 - e)) / 2e-5
+    assert np.max(np.abs(np.concatenate([g_p, g_op]) - num)) < 1e-4 * max(1.0, np.max(np.abs(num)))
+
+
+def test_qnn_regressor_config_c4_shape_trains(sq, executor):
+    """BASELINE configs[3]: ChebyshevRx(8 qubits, 4 layers) + SummedPaulis(8), batch 1024, parameter-shift gradients
+    (64 circuit parameters -> 129 shifted variants x 1024 samples per gradient): a few Adam steps on a smooth
+    target lower the squared loss, and one loss gradient equals the oracle's generator-route gradient."""
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-0.95, 0.95, (1024, 2))
+    y = np.sin(2.0 * X[:, 0]) * np.cos(X[:, 1])
+    enc, op = sq.ChebyshevRx(8, 4, closed=False), sq.SummedPaulis(8)
+    reg = sq.QNNRegressor(enc, op, executor, sq.SquaredLoss(), sq.Adam({"lr": 0.05, "maxiter": 6}),
+                          param_op_ini=np.ones(9) * 0.1)
+    reg._initialize_lowlevel_qnn(2)
+    p0, po0 = reg.param.copy(), reg.param_op.copy()
+    loss0 = float(np.sum((reg._qnn.evaluate(X, p0, po0, "f")["f"] - y) ** 2))
+    reg.partial_fit(X, y)
+    loss1 = float(np.sum((reg.predict(X) - y) ** 2))
+    assert loss1 < loss0
+    vals = reg._qnn.evaluate(X[:64], p0, po0, "f", "dfdp", "dfdop")
+    want = oracle.qnn_evaluate(oracle.chebyshev_rx(8, 4, 2, closed=False), 8, X[:64], p0, ("summed_paulis", {}), po0,
+                               ("f", "dfdp", "dfdop"))
+    for key in ("f", "dfdp", "dfdop"):
+        assert np.max(np.abs(vals[key] - want[key])) < GRAM_TOL, key
