@@ -296,13 +296,16 @@ class ShardedFidelityKernel:
             epoch_t.record_stream(st)
             flags_ptr = arena.data_ptr() + peer["offs"]["flags"]
             n = rows.shape[1]
+            store_mirror = os.environ.get("B200SQ_DIST_MIRROR", "store").lower() != "nccl"
             for j, sl in zip(mine, peer["slots"]):
                 w = sl["rows"]
                 j["planes_y"], j["expo_y"] = arena.data_ptr() + sl["off"], arena.data_ptr() + sl["expo_off"]
                 j["rows_y"], j["y0"], j["ready"] = w, 0, (flags_ptr + 4 * j["owner"], epoch)
-                # the transposed block goes straight into the owner's row block (peer stores from the epilogue)
-                o_rows, _, c0 = peer["owners"][j["owner"]]
-                j["mirror"] = (o_rows + 8 * ((j["cols"][0] - c0) * n + j["rows"][0]), n)
+                # the transposed block goes straight into the owner's row block (peer stores from the epilogue);
+                # B200SQ_DIST_MIRROR=nccl keeps the NCCL send/recv mirror exchange (A/B measurements)
+                if store_mirror:
+                    o_rows, _, c0 = peer["owners"][j["owner"]]
+                    j["mirror"] = (o_rows + 8 * ((j["cols"][0] - c0) * n + j["rows"][0]), n)
             _mark("diag")
             _mark("exchange")
         elif mode == "allgather":
@@ -353,7 +356,7 @@ class ShardedFidelityKernel:
                           "mirror": j.get("mirror")})
         if glist:
             eng.gram_jobs(planes, expo, glist)
-        if mode == "ipc":
+        if mode == "ipc" and store_mirror:
             # tell every owner that its mirrored blocks are stored; wait for the ranks that store into my rows
             for q in sorted({j["owner"] for j in mine}):
                 eng.copy_async(peer["owners"][q][1], epoch_t.data_ptr(), 4)
