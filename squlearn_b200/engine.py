@@ -327,6 +327,30 @@ class Engine:
                 self._stream()))
         return out
 
+    def gram_with_alignment(self, psi, y, diagonal: str = "one", precision: Optional[str] = None):
+        """Symmetric Gram matrix of ``psi`` plus the kernel-target-alignment sums (sum_ij K_ij y_i y_j, sum_ij K_ij^2)
+        of src/squlearn/kernel/loss/target_alignment.py:75-90.  On the INT8 path the sums come out of the |.|^2
+        epilogue of the Gram kernel (K is never re-read); on the FP64 DMMA path (small problems) they are two device
+        reductions over K.  Returns (K, sums) as device tensors."""
+        torch = self._torch
+        psi = psi.contiguous()
+        n, dim = psi.shape
+        yd = self.to_device(y, torch.float64).reshape(-1)
+        if yd.shape[0] != n:
+            raise ValueError("labels and states differ in length")
+        if self.gram_precision(n, n, dim, precision) == "int8":
+            _, planes, expo = self.alloc_plane_block(n, dim)
+            self.slice_states(psi, planes, expo, 0)
+            with torch.cuda.device(self.device):
+                k = torch.empty((n, n), dtype=torch.float64, device=self.device)
+                sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self.gram_jobs(planes, expo, [{"x0": 0, "nx": n, "planes_y": planes, "expo_y": expo, "rows_y": n, "y0": 0,
+                                           "ny": n, "out": k, "symmetric": True, "diagonal": diagonal,
+                                           "align": (yd, yd, sums, 1.0)}])
+            return k, sums
+        k = self.gram(psi, None, diagonal=diagonal, precision="fp64")
+        return k, torch.stack([torch.dot(yd, k @ yd), torch.sum(k * k)])
+
     def gram_jobs(self, planes_x, expo_x, jobs: Sequence[dict]):
         """Several Gram blocks sharing the row planes in ONE persistent launch (b200sq_gram_jobs).
 

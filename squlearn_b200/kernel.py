@@ -234,6 +234,24 @@ class FidelityKernel(KernelMatrixBase):
     def evaluate(self, x, y=None) -> np.ndarray:
         return self._executor.engine.to_host(self.evaluate_device(x, y))
 
+    def evaluate_alignment(self, x, labels):
+        """(K, [sum_ij K_ij y_i y_j, sum_ij K_ij^2]) of the training kernel matrix as device tensors, with the two
+        sums of the kernel-target alignment (loss/target_alignment.py:75-90) reduced inside the Gram epilogue.
+        Returns None when the kernel is configured with post-processing the fused sums would not see
+        (regularisation, noise mitigation, the "none" duplicates policy): callers then reduce K themselves."""
+        if self._regularization is not None or self._mit_depol_noise is not None or self._evaluate_duplicates == "none":
+            return None
+        eng = self._executor.engine
+        if not hasattr(eng, "gram_with_alignment"):
+            return None
+        num_features = extract_num_features(x)
+        x = adjust_features(convert_to_float64(x), num_features)[0]
+        self._initialize_kernel(num_features)
+        x_sv = self.states(x)
+        self.last_states = x_sv
+        diag = "zero" if self._evaluate_duplicates == "all" else "one"
+        return eng.gram_with_alignment(x_sv, np.asarray(labels, dtype=np.float64), diagonal=diag)
+
     def get_params(self, deep: bool = True) -> dict:
         params = {"evaluate_duplicates": self._evaluate_duplicates,
                   "mit_depol_noise": self._mit_depol_noise, "regularization": self._regularization,

@@ -19,11 +19,9 @@ import numpy as np
 
 def _device_kernel(kernel, data):
     """The Gram matrix as a float64 torch tensor on whatever device the kernel computes on."""
-    import torch
+    from .kernel import device_kernel
 
-    if hasattr(kernel, "evaluate_device"):
-        return kernel.evaluate_device(data).to(torch.float64)
-    return torch.as_tensor(np.asarray(kernel.evaluate(data), dtype=np.float64))
+    return device_kernel(kernel, data)
 
 
 class KernelLossBase:
@@ -59,13 +57,20 @@ class TargetAlignment(KernelLossBase):
 
         labels = self._check(kwargs, "TargetAlignment")
         self._quantum_kernel.assign_parameters(parameter_values)
-        k = _device_kernel(self._quantum_kernel, data)
         if self._rescale_class_labels:
             nplus = np.count_nonzero(np.array(labels) == 1)
             nminus = len(labels) - nplus
             y = np.array([v / nplus if v == 1 else v / nminus for v in labels], dtype=np.float64)
         else:
             y = np.array(labels, dtype=np.float64)
+        fused = self._quantum_kernel.evaluate_alignment(data, y) if hasattr(self._quantum_kernel, "evaluate_alignment") \
+            else None
+        if fused is not None:
+            # sum(K * outer(y, y)) and sum(K * K) were reduced in the Gram kernel's epilogue: K is not read again
+            sums = fused[1]
+            yy = float(np.dot(y, y))
+            return float(-(sums[0] / torch.sqrt(sums[1] * yy * yy)).item())
+        k = _device_kernel(self._quantum_kernel, data)
         yd = torch.as_tensor(y, device=k.device)
         inner = torch.dot(yd, k @ yd)                              # sum(K * outer(y, y))
         norm = torch.sqrt(torch.sum(k * k) * torch.dot(yd, yd) ** 2)  # sqrt(sum(K*K) * sum(T*T))
@@ -137,7 +142,9 @@ class KernelOptimizer:
         return self._quantum_kernel.evaluate(x, y)
 
     def evaluate_device(self, x, y=None):
-        return self._quantum_kernel.evaluate_device(x, y)
+        from .kernel import device_kernel
+
+        return device_kernel(self._quantum_kernel, x, y)
 
     def get_optimal_parameters(self):
         return self._optimal_parameters
