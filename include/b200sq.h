@@ -135,6 +135,15 @@ B200SQ_API int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const dou
                     const double* angle_table_dev, int n_variants, const int32_t* var_gate,
                     const double* var_shift, void* psi_dev, void* stream);
 
+/* b200sq_simulate that also reduces, per output state, the maximum of the HIGH 32-bit words of max(|re|, |im|)
+ * into row_max_dev [n_variants][N] uint32 (zeroed here, atomicMax from the last gate pass's store epilogue): the
+ * power-of-two row scale the INT8 Gram's digit slicing needs, so that b200sq_gram_rowmax / b200sq_gram_slice_rowmax
+ * read the states once instead of twice.  The maxima describe psi as written by this call: pass them only with
+ * those very states.                                                                                  */
+B200SQ_API int b200sq_simulate_rowmax(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                                      const double* angle_table_dev, int n_variants, const int32_t* var_gate,
+                                      const double* var_shift, void* psi_dev, uint32_t* row_max_dev, void* stream);
+
 /* Simulate and reduce to Pauli expectation values without keeping the states when the state
  * fits one tile (n <= tile_bits); otherwise states go through `workspace_dev`.
  * Replaces the qml.expval stack of PennyLaneCircuit (pennylane_circuit.py:636-658) /
@@ -160,6 +169,12 @@ B200SQ_API int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int 
 B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
                 double* K_dev, int64_t ldk, uint32_t flags, void* stream);
 
+/* b200sq_gram with the row maxima b200sq_simulate_rowmax produced for psi_x / psi_y (either may be NULL; only the
+ * INT8 path uses them).                                                                                 */
+B200SQ_API int b200sq_gram_rowmax(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
+                                  double* K_dev, int64_t ldk, uint32_t flags, const uint32_t* row_max_x_dev,
+                                  const uint32_t* row_max_y_dev, void* stream);
+
 /* The two halves of the B200SQ_GRAM_INT8 path, for callers that reuse or exchange the digit planes (the
  * multi-GPU Gram sends planes, not complex128 states: 12 instead of 16 bytes per amplitude, sliced once).
  *   planes  [12][plane_rows][2 * dim] int8: planes 0..5 = digits of nat = (re, im), 6..11 = digits of
@@ -171,6 +186,9 @@ B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_
 B200SQ_API size_t b200sq_gram_planes_bytes(int64_t plane_rows, int64_t dim);
 B200SQ_API int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
                                  int64_t row0, int32_t* expo_dev, void* stream);
+B200SQ_API int b200sq_gram_slice_rowmax(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
+                                        int64_t plane_rows, int64_t row0, int32_t* expo_dev,
+                                        const uint32_t* row_max_dev, void* stream);
 B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
                                        int64_t x0, int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev,
                                        int64_t plane_rows_y, int64_t y0, int64_t Ny, int64_t dim, double* K_dev,

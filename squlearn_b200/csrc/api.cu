@@ -154,7 +154,7 @@ int upload_masks(b200sq_program* p, int n_terms, const uint32_t* xm, const uint3
 // stream-ordered scratch allocation (at most two buffers, ping-pong).
 int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v0, int nv, int d,
                const double* x, const double* table, bool have_variants, double2* psi, int64_t psi_off,
-               bool fuse_expvals, int n_terms, double* out, cudaStream_t stream) {
+               bool fuse_expvals, int n_terms, double* out, cudaStream_t stream, uint32_t* row_max = nullptr) {
     const Plan& pl = p->plan;
     const int64_t n_states = (int64_t)nv * ns;
     double2* ws[2] = {nullptr, nullptr};
@@ -211,6 +211,7 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.xmask = p->d_masks;
         a.zmask = p->d_masks ? p->d_masks + n_terms : nullptr;
         a.out = out;
+        a.row_max = (a.dst == psi && psi && P.out_bits == pl.n) ? row_max : nullptr;
         tile_pass_geometry(P, &a);
         a.total_items = n_states << P.n_obits;
         // Large batches run a kernel specialised for this pass at run time (compiled once per program);
@@ -275,9 +276,9 @@ int b200sq_program_create(int n_qubits, int n_gates, const b200sq_gate* gates, i
             if (x.fn == B200SQ_FN_TABLE && x.slot < 0) return fail(2, "negative angle-table slot");
         }
         b200sq_program* p = new b200sq_program();
-        // B200SQ_ROT_LIFT=1: rx / ry layer steps by in-place lifted rotations (experimental, default off)
+        // rx / ry layer steps as scaled rotations (one FMA per component, plan_dev.h MAT_ROT); B200SQ_ROT_LIFT=0 disables
         const char* lift = getenv("B200SQ_ROT_LIFT");
-        p->plan = make_plan(n_qubits, g, tile_bits, 4, true, lift && lift[0] == '1');
+        p->plan = make_plan(n_qubits, g, tile_bits, 4, true, !(lift && lift[0] == '0'));
         for (size_t ip = 0; ip < p->plan.passes.size(); ++ip) p->blobs.push_back(build_pass_blob(p->plan, (int)ip));
         *out = p;
         return 0;
@@ -344,6 +345,13 @@ int b200sq_program_dump(const b200sq_program* prog, int32_t* buf, int capacity, 
 int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const double* x_dev,
                     const double* angle_table_dev, int n_variants, const int32_t* var_gate,
                     const double* var_shift, void* psi_dev, void* stream_) {
+    return b200sq_simulate_rowmax(prog, N, d, x_dev, angle_table_dev, n_variants, var_gate, var_shift, psi_dev,
+                                  nullptr, stream_);
+}
+
+int b200sq_simulate_rowmax(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                           const double* angle_table_dev, int n_variants, const int32_t* var_gate,
+                           const double* var_shift, void* psi_dev, uint32_t* row_max_dev, void* stream_) {
     if (!prog || !psi_dev) return fail(2, "NULL argument");
     if (N < 0 || n_variants < 1) return fail(2, "bad batch size");
     if (N == 0) return 0;
@@ -351,8 +359,12 @@ int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const double* x_dev,
     int e;
     if ((e = ensure_device(prog, stream))) return e;
     if ((e = upload_variants(prog, n_variants, var_gate, var_shift, stream))) return e;
+    if (row_max_dev) {
+        cudaError_t ce = cudaMemsetAsync(row_max_dev, 0, (size_t)n_variants * (size_t)N * sizeof(uint32_t), stream);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemsetAsync (row maxima)");
+    }
     return run_passes(prog, N, 0, N, 0, n_variants, d, x_dev, angle_table_dev, var_gate != nullptr,
-                      (double2*)psi_dev, 0, false, 0, nullptr, stream);
+                      (double2*)psi_dev, 0, false, 0, nullptr, stream, row_max_dev);
 }
 
 int b200sq_simulate_expvals(b200sq_program* prog, int64_t N, int d, const double* x_dev,
@@ -415,6 +427,12 @@ int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int n_terms, co
 
 int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
                 double* K_dev, int64_t ldk, uint32_t flags, void* stream_) {
+    return b200sq_gram_rowmax(psi_x_dev, Nx, psi_y_dev, Ny, dim, K_dev, ldk, flags, nullptr, nullptr, stream_);
+}
+
+int b200sq_gram_rowmax(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
+                       double* K_dev, int64_t ldk, uint32_t flags, const uint32_t* row_max_x_dev,
+                       const uint32_t* row_max_y_dev, void* stream_) {
     if (!psi_x_dev || !psi_y_dev || !K_dev) return fail(2, "NULL argument");
     if (Nx < 0 || Ny < 0 || dim < 1 || ldk < Ny) return fail(2, "bad sizes");
     if ((flags & B200SQ_GRAM_SYMMETRIC) && (Nx != Ny || ldk < Nx))
@@ -422,7 +440,7 @@ int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_
     int e;
     if ((flags & B200SQ_GRAM_INT8) && gram_i8_supported(dim))
         e = launch_gram_i8((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
-                           (cudaStream_t)stream_);
+                           (cudaStream_t)stream_, row_max_x_dev, row_max_y_dev);
     else
         e = launch_gram((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
                         (cudaStream_t)stream_);
@@ -436,11 +454,16 @@ size_t b200sq_gram_planes_bytes(int64_t plane_rows, int64_t dim) {
 
 int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
                       int64_t row0, int32_t* expo_dev, void* stream_) {
+    return b200sq_gram_slice_rowmax(psi_dev, N, dim, planes_dev, plane_rows, row0, expo_dev, nullptr, stream_);
+}
+
+int b200sq_gram_slice_rowmax(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
+                             int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* stream_) {
     if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
     if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
     if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
     int e = launch_slice_i8((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
-                            (cudaStream_t)stream_);
+                            (cudaStream_t)stream_, row_max_dev);
     if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
     return 0;
 }

@@ -461,9 +461,9 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
 
 // ---------------------------------------------------------------------------------------------
 // Digit planes.  planes: [2 * kSlices][n_rows][2 * dim] int8; plane s = digits of nat = (re, im), plane
-// kSlices + s = digits of rot = (-im, re).  One CTA per state row.  `row_max` (optional): bit patterns of the
-// row maxima max(|re|, |im|) already reduced by the producer of the states (the last gate pass), which saves
-// this kernel's first sweep over the state.
+// kSlices + s = digits of rot = (-im, re).  One CTA per state row.  `row_max` (optional): high words of the row
+// maxima max(|re|, |im|) already reduced by the producer of the states (the last gate pass, see TileArgs::row_max),
+// which saves this kernel's first sweep over the state (the high word has the exponent: all the scale needs).
 
 __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int byte) {
     const long long d = ((q + 128) & 255) - 128;
@@ -473,14 +473,15 @@ __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int 
 
 __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
                                                   int64_t dim, int8_t* __restrict__ planes, int* __restrict__ expo,
-                                                  const unsigned long long* __restrict__ row_max) {
+                                                  const uint32_t* __restrict__ row_max) {
     const int64_t row = row0 + blockIdx.x;   // row inside the planes; state blockIdx.x of psi
     const double2* src = psi + (int64_t)blockIdx.x * dim;
     __shared__ double red[8];
     __shared__ int s_e;
     double m = 0.0;
     if (row_max) {
-        m = __longlong_as_double((long long)row_max[blockIdx.x]);
+        m = __hiloint2double((int)row_max[blockIdx.x], 0);
+        if (row_max[blockIdx.x] != 0u && m == 0.0) m = 4.9e-324;   // (cannot happen for a normalised state)
     } else {
         for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
             const double2 v = src[i];
@@ -689,7 +690,7 @@ unsigned int gram_ready_timeouts() {
 bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
 
 int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                    int* expo, cudaStream_t stream, const unsigned long long* row_max) {
+                    int* expo, cudaStream_t stream, const uint32_t* row_max) {
     if (n <= 0) return 0;
     k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo, row_max);
     count_launch();
@@ -697,7 +698,8 @@ int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, 
 }
 
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
-                   int64_t ldk, uint32_t flags, cudaStream_t stream) {
+                   int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x,
+                   const uint32_t* row_max_y) {
     if (nx <= 0 || ny <= 0) return 0;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
     const size_t plane_bytes = (size_t)(2 * dim);  // per row
@@ -712,14 +714,14 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     };
     if ((e = cudaMallocAsync(&py, 2 * kSlices * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
     if ((e = cudaMallocAsync(&ey, ny * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-    launch_slice_i8(y, ny, dim, py, ny, 0, ey, stream);
+    launch_slice_i8(y, ny, dim, py, ny, 0, ey, stream, row_max_y);
     if (sym) {
         px = py;
         ex = ey;
     } else {
         if ((e = cudaMallocAsync(&px, 2 * kSlices * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
         if ((e = cudaMallocAsync(&ex, nx * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-        launch_slice_i8(x, nx, dim, px, nx, 0, ex, stream);
+        launch_slice_i8(x, nx, dim, px, nx, 0, ex, stream, row_max_x);
     }
     const int rc = launch_gram_planes(px, ex, nx, 0, nx, py, ey, ny, 0, ny, dim, k, ldk, flags, stream);
     cleanup();

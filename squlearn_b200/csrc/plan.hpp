@@ -60,6 +60,9 @@ struct TabGate {     // a diagonal gate folded into a phase table
 };
 struct Tab {
     int32_t mat, lo, nbits, g0, g1;  // table offset, first local bit, width, TabGate range
+    int32_t vb[2];                   // outer ext positions the table reads (-1: none); > 2 of them: legacy = 1
+    int32_t legacy;                  // rebuilt per tile (reads more than two outer bits)
+    int32_t carrier;                 // carries the rotation scale of the pass
 };
 struct Round {
     int32_t nb;      // number of register bits (0..3)
@@ -78,6 +81,7 @@ struct Pass {
     int32_t t0, t1;          // Tab range
     int32_t i0, i1;          // folded (init) gate range in Plan::init_gates
     int32_t mat_elems;       // double2 elements of matrix + table storage per team
+    int32_t rot_carrier;     // 0 none, 1 low product table, 2 a phase table
     int32_t tile_qubits[32]; // the T tile qubits (ascending)
     uint8_t extq[32];        // ext position -> qubit
 };
@@ -308,6 +312,10 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                             tb.lo = gidx == 0 ? 0 : split;
                             tb.nbits = gidx == 0 ? std::min(split, T) : T - split;
                             tb.g0 = (int)plan.tabgates.size();
+                            tb.vb[0] = tb.vb[1] = -1;
+                            tb.legacy = 0;
+                            tb.carrier = 0;
+                            int nvb = 0;
                             for (int r : grp[gidx]) {
                                 const GateInfo ri = gate_info(gates_in[r].kind);
                                 TabGate tg;
@@ -315,10 +323,24 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                                 tg.p0 = pos[gates_in[r].q[0]];
                                 tg.p1 = ri.nq > 1 ? pos[gates_in[r].q[1]] : -1;
                                 plan.tabgates.push_back(tg);
+                                for (int pp : {tg.p0, tg.p1}) {   // outer index bits this table reads
+                                    if (pp < T) continue;
+                                    if (nvb > 0 && tb.vb[0] == pp) continue;
+                                    if (nvb > 1 && tb.vb[1] == pp) continue;
+                                    if (nvb < 2) tb.vb[nvb] = pp;
+                                    ++nvb;
+                                }
                             }
                             tb.g1 = (int)plan.tabgates.size();
                             tb.mat = mat_off;
-                            mat_off += 1 << tb.nbits;
+                            // one variant per value of the (<= 2) outer bits, all built once per state; a table that
+                            // reads more outer bits (or would not fit) is rebuilt per tile
+                            if (nvb > 2 || mat_off + ((1 << std::min(nvb, 2)) << tb.nbits) > kMaxPassMatElems - 1024) {
+                                tb.legacy = nvb > 0 ? 1 : 0;
+                                tb.vb[0] = tb.vb[1] = -1;
+                                nvb = 0;
+                            }
+                            mat_off += (1 << nvb) << tb.nbits;
                             plan.tabs.push_back(tb);
                             Step st;
                             std::memset(&st, 0, sizeof(st));
@@ -327,6 +349,7 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                             st.r0 = tb.lo;
                             st.r1 = tb.nbits;
                             st.mat = tb.mat;
+                            st.ctrl = (uint32_t)(tb.vb[0] < 0 ? kNoBit : tb.vb[0]) | ((uint32_t)(tb.vb[1] < 0 ? kNoBit : tb.vb[1]) << 8);
                             plan.steps.push_back(st);
                         }
                         std::sort(stray.begin(), stray.end());
@@ -369,14 +392,13 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
                         plan.steps.push_back(st);
                         continue;
                     }
-                    // rotation by lifting needs a carrier for the accumulated sign: the product table of a pass
-                    // with fresh qubits (see MAT_ROT)
-                    const bool lift = lift_rotations && fresh != 0 && (g.kind == B200SQ_RX || g.kind == B200SQ_RY);
-                    const int fam = lift ? (g.kind == B200SQ_RX ? ST_LROTX : ST_LROTY)
-                                  : g.kind == B200SQ_RX ? ST_LRX
-                                  : (g.kind == B200SQ_RY || g.kind == B200SQ_H || g.kind == B200SQ_X) ? ST_LREAL
+                    // rx / ry as scaled rotations (one FMA per component) need a carrier for the factored-out scale:
+                    // see the conversion after the pass has been planned (MAT_ROT)
+                    const int fam = g.kind == B200SQ_RX ? ST_LRX
+                                  : g.kind == B200SQ_RY ? ST_LROTY   // provisional family of its own: pure-ry layers
+                                  : (g.kind == B200SQ_H || g.kind == B200SQ_X) ? ST_LREAL
                                   : ST_LGEN;
-                    const int mkind = lift ? MAT_ROT : MAT_U1;
+                    const int mkind = MAT_U1;
                     if (layer_step >= 0 && plan.steps[layer_step].kind == fam &&
                         !(plan.steps[layer_step].r0 >> slot & 1)) {
                         Step& st = plan.steps[layer_step];
@@ -513,6 +535,35 @@ inline Plan make_plan(int n, const std::vector<b200sq_gate>& gates_in, int tile_
         ps.m1 = (int)plan.mats.size();
         ps.t1 = (int)plan.tabs.size();
         ps.mat_elems = mat_off;
+        // ---- scaled rotations: rx / ry layer steps become one-FMA-per-component steps when the pass has a carrier
+        // for the product of the factored-out scales (the low product table of the fresh qubits, else a phase table
+        // that is built once per state); otherwise ry layers fall back to the real-matrix family
+        {
+            int carrier = 0;
+            if (lift_rotations) {
+                if (fresh != 0) {
+                    carrier = 1;
+                } else {
+                    for (int t = ps.t0; t < ps.t1 && !carrier; ++t)
+                        if (!plan.tabs[t].legacy) { plan.tabs[t].carrier = 1; carrier = 2; }
+                }
+            }
+            ps.rot_carrier = carrier;
+            for (int si = ps.s0; si < ps.s1; ++si) {
+                Step& st = plan.steps[si];
+                if (st.kind != ST_LRX && st.kind != ST_LROTY) continue;
+                if (!carrier) {
+                    if (st.kind == ST_LROTY) st.kind = ST_LREAL;
+                    continue;
+                }
+                if (st.kind == ST_LRX) st.kind = ST_LROTX;
+                for (int m = ps.m0; m < ps.m1; ++m)
+                    if (plan.mats[m].mat >= st.mat && plan.mats[m].mat < st.mat + 12 && plan.mats[m].kind == MAT_U1 &&
+                        gate_info(gates_in[plan.mats[m].gate].kind).nq == 1 &&
+                        (gates_in[plan.mats[m].gate].kind == B200SQ_RX || gates_in[plan.mats[m].gate].kind == B200SQ_RY))
+                        plan.mats[m].kind = MAT_ROT;
+            }
+        }
         ps.last = rest.empty() ? 1 : 0;
         ps.a_out = ps.last ? full : active;
         if (ps.s1 - ps.s0 > kMaxPassSteps || ps.r1 - ps.r0 > kMaxPassRounds || ps.m1 - ps.m0 > kMaxPassMats)
@@ -542,6 +593,7 @@ inline std::vector<uint8_t> build_pass_blob(const Plan& plan, int ip) {
     h.mat_elems = ps.mat_elems;
     h.has_src = ps.a_in != 0;
     h.last = (uint8_t)ps.last;
+    h.rot_carrier = (uint8_t)ps.rot_carrier;
     h.in_bits = (uint8_t)popc(ps.a_in);
     h.out_bits = (uint8_t)popc(ps.a_out);
     std::memset(h.l_in, kNoBit, sizeof(h.l_in));
@@ -626,10 +678,13 @@ inline std::vector<uint8_t> build_pass_blob(const Plan& plan, int ip) {
         d.mat = (uint16_t)tb.mat;
         d.lo = (uint8_t)tb.lo;
         d.nbits = (uint8_t)tb.nbits;
+        if (tb.legacy) d.nbits |= 0x80;  // reads more than two outer index bits: rebuilt per tile
+        d.vb[0] = (uint8_t)(tb.vb[0] < 0 ? kNoBit : tb.vb[0]);
+        d.vb[1] = (uint8_t)(tb.vb[1] < 0 ? kNoBit : tb.vb[1]);
+        d.carrier = (uint8_t)tb.carrier;
         d.g0 = (uint16_t)tabgates.size();
         for (int g = tb.g0; g < tb.g1; ++g) {
             const TabGate& tg = plan.tabgates[g];
-            if (tg.p0 >= T || tg.p1 >= T) d.nbits |= 0x80;  // reads an outer index bit: rebuilt per tile
             tabgates.push_back(DTabGate{(uint16_t)tg.m4, (uint8_t)tg.p0, (uint8_t)(tg.p1 < 0 ? kNoBit : tg.p1)});
         }
         d.g1 = (uint16_t)tabgates.size();

@@ -28,12 +28,17 @@ enum StepKind : int32_t {
     ST_LRX = 6,     // [[c, -is], [-is, c]] on every register slot of mask r0 (matrix of slot c at mat + 4c)
     ST_LREAL = 7,   // real 2x2 (ry, h, x)
     ST_LGEN = 8,    // general complex 2x2 (y, sx, u)
-    ST_DTAB = 9,    // a[k] *= table[(local_index >> r0) & ((1 << r1) - 1)], table at mat
-    ST_LROTX = 10,  // rx as two in-place lifted 2-D rotations per amplitude pair (3 FMAs each), slot mask r0
+    ST_DTAB = 9,    // a[k] *= table[(local_index >> r0) & ((1 << r1) - 1)], table at mat (+ variant << r1, see DTab)
+    ST_LROTX = 10,  // rx as a SCALED rotation: one FMA per real component (2 per amplitude), slot mask r0
     ST_LROTY = 11,  // ry, idem
 };
-// MAT_ROT: m[0] = (tan(a'/2), sin a'), m[1].x = k mod 2 for a = theta/2 = a' + k pi, |a'| <= pi/2.  The lifted
-// rotation applies R(a'); the signs (-1)^k of all MAT_ROT gates of a pass multiply into the product table.
+// MAT_ROT (scaled rotation): with c = cos(theta/2), s = sin(theta/2) the gate is written as scale * (I + t G) with
+// the larger of |c|, |s| factored out, so that every output component is ONE fused multiply-add:
+//   |c| >= |s|:  m[0] = (s / c, 0), m[1].x = c      rx: v0' = v0 - i t v1, v1' = v1 - i t v0;  ry: v0' = v0 - t v1, v1' = v1 + t v0
+//   |s| >  |c|:  m[0] = (c / s, 1), m[1].x = s      rx: v0' = u v0 - i v1, v1' = u v1 - i v0;  ry: v0' = u v0 - v1, v1' = u v1 + v0
+// (|t|, |u| <= 1: intermediates grow by at most sqrt(2) per gate).  The product of the factored-out scales of all
+// MAT_ROT gates of a pass is one real number per state; it multiplies into the pass's carrier table (the product
+// table of the fresh qubits, or the first phase table), which is built per state anyway.
 enum MatKind : int32_t { MAT_U1 = 0, MAT_U2 = 1, MAT_DIAG = 2, MAT_ROT = 3 };
 
 constexpr int kMaxRuns = 8;
@@ -102,11 +107,14 @@ struct DTabGate {    // 4 bytes
     uint16_t m4;
     uint8_t p0, p1;  // ext positions (p1 = kNoBit for one-qubit gates)
 };
-struct DTab {        // 8 bytes
+struct DTab {        // 12 bytes
     uint16_t mat;
-    uint8_t lo, nbits;  // nbits bit 7: the table depends on outer index bits
+    uint8_t lo, nbits;  // nbits bit 7 (legacy form): the table reads > 2 outer index bits and is rebuilt per tile
     uint16_t g0, g1;
-};
+    uint8_t vb[2];      // ext positions of the (at most two) OUTER index bits the table reads, kNoBit = none:
+    uint8_t carrier;    // the table is stored in 2^(#vb) variants (variant v at mat + (v << nbits)), all built once
+    uint8_t pad;        // per state, and a tile picks its variant from its outer bits.  carrier: multiply by the
+};                      // pass's rotation scale (see MAT_ROT)
 struct DInit {       // a 1-qubit gate folded into the product start of a fresh tile qubit
     uint16_t gate;
     uint8_t qubit, pad;
@@ -120,6 +128,7 @@ struct DPass {
     uint8_t n_obits;    // outer bits of a work item = outer qubits present in the output layout
     uint8_t in_bits, out_bits;  // log2(amplitudes per state) of the input / output layout
     uint8_t last;
+    uint8_t rot_carrier;  // where the MAT_ROT scale goes: 0 none, 1 low product table, 2 a phase table (DTab::carrier)
     uint8_t l_in[16];   // local bit -> bit of the input-layout index (kNoBit: fresh)
     uint8_t l_out[16];  // local bit -> bit of the output-layout index
     uint8_t l_plo[16];  // local bit -> bit of the low product-table index (kNoBit: none)

@@ -59,13 +59,14 @@ B200SQ_HD void build_matrix(int mkind, int swap, const b200sq_gate& g, double th
     const double kInvSqrt2 = 0.70710678118654752440;
     double s, c;
     sincos(0.5 * theta, &s, &c);
-    if (mkind == MAT_ROT) {  // rx / ry by lifting: a = theta / 2 = a' + k pi with |a'| <= pi / 2
-        const double kPi = 3.14159265358979323846;
-        const double a = 0.5 * theta;
-        const double k = rint(a / kPi);
-        const double ar = fma(-k, kPi, a);
-        m[0] = double2{tan(0.5 * ar), sin(ar)};
-        m[1] = double2{fabs(fmod(k, 2.0)), 0.0};
+    if (mkind == MAT_ROT) {  // rx / ry as a scaled rotation: the larger of |c|, |s| is factored out (plan_dev.h)
+        if (fabs(c) >= fabs(s)) {
+            m[0] = double2{s / c, 0.0};
+            m[1] = double2{c, 0.0};
+        } else {
+            m[0] = double2{c / s, 1.0};
+            m[1] = double2{s, 0.0};
+        }
         return;
     }
     if (mkind == MAT_DIAG) {
@@ -291,13 +292,15 @@ B200SQ_HD void build_mats_thread(const PassView& pv, const TeamMem& tm, const It
 B200SQ_HD void build_tables_thread(const PassView& pv, const TeamMem& tm, const ItemCtx& ic, int tid, int TS,
                                    bool new_sample) {
     const DPass& P = *pv.P;
-    // sign (-1)^(sum k) of the lifted rotations of this pass (MAT_ROT), carried by the low product table
-    double rot_sign = 1.0;
-    if (new_sample && P.nlo > 0)
+    // product of the factored-out scales of the scaled rotations of this pass (MAT_ROT), carried by the low
+    // product table or by one phase table
+    double rot_scale = 1.0;
+    if (new_sample && P.rot_carrier)
         for (int i = 0; i < P.n_mats; ++i)
-            if (pv.mats[i].kind == MAT_ROT && tm.mats[pv.mats[i].mat + 1].x != 0.0) rot_sign = -rot_sign;
+            if (pv.mats[i].kind == MAT_ROT) rot_scale *= tm.mats[pv.mats[i].mat + 1].x;
+    const double plo_scale = P.rot_carrier == 1 ? rot_scale : 1.0;
     for (int t = tid; t < (1 << P.nlo) && P.nlo > 0 && new_sample; t += TS) {
-        double2 r{rot_sign, 0.0};
+        double2 r{plo_scale, 0.0};
         for (int b = 0; b < P.nlo; ++b) r = cmul(r, tm.qv[2 * b + ((t >> b) & 1)]);
         tm.plo[t] = r;
     }
@@ -308,11 +311,22 @@ B200SQ_HD void build_tables_thread(const PassView& pv, const TeamMem& tm, const 
     }
     for (int it = 0; it < P.n_tabs; ++it) {
         const DTab tb = pv.tabs[it];
-        if (!new_sample && !(tb.nbits & 0x80)) continue;
+        const bool legacy = tb.nbits & 0x80;   // reads more than two outer bits: rebuilt for every tile
+        if (!new_sample && !legacy) continue;
         const int nbits = tb.nbits & 0x7f;
-        for (int t = tid; t < (1 << nbits); t += TS) {
-            const uint32_t e = ic.ext_base | ((uint32_t)t << tb.lo);
-            double2 ph{1.0, 0.0};
+        const int nv = legacy ? 0 : (tb.vb[0] != kNoBit) + (tb.vb[1] != kNoBit);
+        const double scale = (tb.carrier && P.rot_carrier == 2) ? rot_scale : 1.0;
+        // every variant (value of the outer bits the table reads) is built here, once per state
+        for (int t = tid; t < (1 << (nbits + nv)); t += TS) {
+            const uint32_t v = (uint32_t)t >> nbits;
+            uint32_t e = ((uint32_t)(t & ((1 << nbits) - 1)) << tb.lo);
+            if (legacy) {
+                e |= ic.ext_base;
+            } else {
+                if (nv > 0) e |= (v & 1u) << tb.vb[0];
+                if (nv > 1) e |= ((v >> 1) & 1u) << tb.vb[1];
+            }
+            double2 ph{scale, 0.0};
             for (int g = tb.g0; g < tb.g1; ++g) {
                 const DTabGate tg = pv.tabgates[g];
                 uint32_t idx = (e >> tg.p0) & 1u;
@@ -418,41 +432,65 @@ B200SQ_HD void u1_real(double2 (&a)[G][1 << NB], const double2* __restrict__ m) 
         }
 }
 
-// In-place 2-D rotation [[c, s], [-s, c]] by lifting: three FMAs, no temporaries (t = tan(a/2), S = sin a).
-B200SQ_HD void rot2(double& x, double& y, double t, double S) {
-    x = fma(t, y, x);
-    y = fma(-S, x, y);
-    x = fma(t, y, x);
-}
+// Scaled rotations (MAT_ROT, plan_dev.h): one FMA per real component; the factored-out scale lives in the
+// pass's carrier table.  The form (which of |c|, |s| was factored out) is uniform over the team.
 
-// rx(theta) = [[c, -i s], [-i s, c]]: rotates (re0, im1) and (re1, im0)
+// rx(theta) / scale:  form 0: v0' = v0 - i t v1, v1' = v1 - i t v0;   form 1: v0' = u v0 - i v1, v1' = u v1 - i v0
 template <int NB, int R, int G>
 B200SQ_HD void u1_rotx(double2 (&a)[G][1 << NB], const double2* __restrict__ m) {
-    const double t = m[0].x, S = m[0].y;
+    const double t = m[0].x;
+    if (m[0].y == 0.0) {
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi)
+        for (int gi = 0; gi < G; ++gi)
 #pragma unroll
-        for (int k0 = 0; k0 < (1 << NB); ++k0) {
-            if (k0 & (1 << R)) continue;
-            const int k1 = k0 | (1 << R);
-            rot2(a[gi][k0].x, a[gi][k1].y, t, S);
-            rot2(a[gi][k1].x, a[gi][k0].y, t, S);
-        }
+            for (int k0 = 0; k0 < (1 << NB); ++k0) {
+                if (k0 & (1 << R)) continue;
+                const int k1 = k0 | (1 << R);
+                const double2 v0 = a[gi][k0], v1 = a[gi][k1];
+                a[gi][k0] = double2{fma(t, v1.y, v0.x), fma(-t, v1.x, v0.y)};
+                a[gi][k1] = double2{fma(t, v0.y, v1.x), fma(-t, v0.x, v1.y)};
+            }
+    } else {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int k0 = 0; k0 < (1 << NB); ++k0) {
+                if (k0 & (1 << R)) continue;
+                const int k1 = k0 | (1 << R);
+                const double2 v0 = a[gi][k0], v1 = a[gi][k1];
+                a[gi][k0] = double2{fma(t, v0.x, v1.y), fma(t, v0.y, -v1.x)};
+                a[gi][k1] = double2{fma(t, v1.x, v0.y), fma(t, v1.y, -v0.x)};
+            }
+    }
 }
 
-// ry(theta) = [[c, -s], [s, c]]: rotates (re1, re0) and (im1, im0)
+// ry(theta) / scale:  form 0: v0' = v0 - t v1, v1' = v1 + t v0;   form 1: v0' = u v0 - v1, v1' = u v1 + v0
 template <int NB, int R, int G>
 B200SQ_HD void u1_roty(double2 (&a)[G][1 << NB], const double2* __restrict__ m) {
-    const double t = m[0].x, S = m[0].y;
+    const double t = m[0].x;
+    if (m[0].y == 0.0) {
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi)
+        for (int gi = 0; gi < G; ++gi)
 #pragma unroll
-        for (int k0 = 0; k0 < (1 << NB); ++k0) {
-            if (k0 & (1 << R)) continue;
-            const int k1 = k0 | (1 << R);
-            rot2(a[gi][k1].x, a[gi][k0].x, t, S);
-            rot2(a[gi][k1].y, a[gi][k0].y, t, S);
-        }
+            for (int k0 = 0; k0 < (1 << NB); ++k0) {
+                if (k0 & (1 << R)) continue;
+                const int k1 = k0 | (1 << R);
+                const double2 v0 = a[gi][k0], v1 = a[gi][k1];
+                a[gi][k0] = double2{fma(-t, v1.x, v0.x), fma(-t, v1.y, v0.y)};
+                a[gi][k1] = double2{fma(t, v0.x, v1.x), fma(t, v0.y, v1.y)};
+            }
+    } else {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int k0 = 0; k0 < (1 << NB); ++k0) {
+                if (k0 & (1 << R)) continue;
+                const int k1 = k0 | (1 << R);
+                const double2 v0 = a[gi][k0], v1 = a[gi][k1];
+                a[gi][k0] = double2{fma(t, v0.x, -v1.x), fma(t, v0.y, -v1.y)};
+                a[gi][k1] = double2{fma(t, v1.x, v0.x), fma(t, v1.y, v0.y)};
+            }
+    }
 }
 
 template <int NB, int R, int G>
@@ -513,8 +551,15 @@ B200SQ_HD void diag_apply(double2 (&a)[G][1 << NB], const DStep& u, const double
 // Phase table: one complex multiply per amplitude for a whole run of diagonal gates.
 template <int NB, int G>
 B200SQ_HD void dtab_apply(double2 (&a)[G][1 << NB], const DStep& u, const double2* __restrict__ tab,
-                          const uint32_t (&base)[G], const uint32_t (&ko)[1 << NB]) {
+                          const uint32_t (&e)[G], const uint32_t (&base)[G], const uint32_t (&ko)[1 << NB]) {
     const uint32_t mask = (1u << u.r1) - 1u;
+    // variant of the table for this tile's value of the outer bits it reads (u.ctrl = vb0 | vb1 << 8)
+    const uint32_t vb0 = u.ctrl & 0xffu, vb1 = (u.ctrl >> 8) & 0xffu;
+    if (vb0 != (uint32_t)kNoBit) {
+        uint32_t v = (e[0] >> vb0) & 1u;
+        if (vb1 != (uint32_t)kNoBit) v |= ((e[0] >> vb1) & 1u) << 1;
+        tab += v << u.r1;
+    }
     uint32_t kp[1 << NB];
 #pragma unroll
     for (int k = 0; k < (1 << NB); ++k) kp[k] = (ko[k] >> u.r0) & mask;
@@ -539,7 +584,7 @@ B200SQ_HD void apply_step(double2 (&a)[G][1 << NB], const DStep& u, const double
         case ST_LGEN: B200SQ_LAYER(u1_general) break;
         case ST_LROTX: B200SQ_LAYER(u1_rotx) break;
         case ST_LROTY: B200SQ_LAYER(u1_roty) break;
-        case ST_DTAB: dtab_apply<NB, G>(a, u, m, base, ko); break;
+        case ST_DTAB: dtab_apply<NB, G>(a, u, m, e, base, ko); break;
         case ST_DIAG: diag_apply<NB, G>(a, u, m, e, ko); break;
         case ST_U1CTRL:
             switch (u.r0) {

@@ -30,6 +30,9 @@ struct TileArgs {
     const uint32_t* xmask;     // device
     const uint32_t* zmask;
     double* out;               // [n_variants_total][n_total][n_terms]
+    uint32_t* row_max;         // nullptr, or per output state (indexed like dst): running maximum of the high words of
+                               // max(|re|, |im|) over the stored amplitudes (atomicMax; zeroed by the launcher) — the
+                               // row scale the INT8 Gram's digit slicing needs, without a sweep of its own
     int32_t team_size, log2ts, teams_per_cta, team_elems;
     int64_t total_items;
 };
@@ -221,7 +224,21 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
         // ---- epilogue
         if (A.store && in_range) {
             double2* dp = dstate + (obase_out | map.out_lo);
-            for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], tm.tile[smem_idx(j)]);
+            if (A.row_max) {
+                uint32_t hi = 0;
+                for (int j = 0; j < J; ++j) {
+                    const double2 v = tm.tile[smem_idx(j)];
+                    __stcs(dp + tm.jt[J + j], v);
+                    const uint32_t hx = (uint32_t)__double2hiint(v.x) & 0x7fffffffu;
+                    const uint32_t hy = (uint32_t)__double2hiint(v.y) & 0x7fffffffu;
+                    hi = max(hi, max(hx, hy));
+                }
+                hi = __reduce_max_sync(__activemask(), hi);
+                if ((tid & 31) == 0)
+                    atomicMax(A.row_max + ((int64_t)variant * A.dst_vstride + ic.sample - A.dst_off), hi);
+            } else {
+                for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], tm.tile[smem_idx(j)]);
+            }
         }
         if (A.n_terms > 0) {
             // T == n here: the tile is the state and local index == amplitude index.

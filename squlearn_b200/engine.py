@@ -15,6 +15,11 @@ from . import _lib
 from .observables import pauli_masks
 from .program import Program, as_uint32_array
 
+def gram_i8_ok(dim: int) -> bool:
+    """The INT8 Gram's constraint on the state dimension (csrc/gram_i8.cu: gram_i8_supported)."""
+    return dim >= 64 and dim % 8 == 0
+
+
 _DIAG_FLAGS = {"one": _lib.GRAM_DIAG_ONE, "zero": _lib.GRAM_DIAG_ZERO, "computed": 0}
 
 
@@ -77,7 +82,7 @@ class CompiledProgram:
         rounds = [tuple(int(v) for v in w[pos + 6 * i: pos + 6 * i + 6]) for i in range(n_rounds)]
         pos += 6 * n_rounds
         steps = [tuple(int(v) for v in w[pos + 7 * i: pos + 7 * i + 7]) for i in range(n_steps)]
-        cost = {6: 4.0, 7: 4.0, 8: 8.0, 10: 3.0, 11: 3.0}   # layer steps: per active register slot
+        cost = {6: 4.0, 7: 4.0, 8: 8.0, 10: 2.0, 11: 2.0}   # layer steps: per active register slot
         out = []
         for Tp, a_in, r0, r1, nfresh, tile_mask in passes:
             per_amp = 0.0
@@ -200,11 +205,28 @@ class Engine:
         with torch.cuda.device(self.device):
             psi = torch.empty((nv, n_samples, 1 << prog.num_qubits), dtype=torch.complex128,
                               device=self.device)
-            _lib.check(self._lib.b200sq_simulate(
+            # the last gate pass also reduces the row maxima the INT8 Gram's digit slicing needs (one int per
+            # state): a later gram() / slice_states() of exactly this tensor then reads the states once, not twice
+            row_max = torch.empty((nv, n_samples), dtype=torch.int32, device=self.device) \
+                if gram_i8_ok(1 << prog.num_qubits) else None
+            _lib.check(self._lib.b200sq_simulate_rowmax(
                 cprog.handle, n_samples, xd.shape[1], xd.data_ptr(),
                 table.data_ptr() if table is not None else None, nv, vg, vs, psi.data_ptr(),
-                self._stream()))
-        return psi if variants is not None else psi[0]
+                row_max.data_ptr() if row_max is not None else None, self._stream()))
+        if variants is not None:
+            return psi
+        out = psi[0]
+        if row_max is not None:
+            out._b200sq_row_max = (row_max[0], out._version)
+        return out
+
+    @staticmethod
+    def _row_max_of(psi):
+        """The row maxima simulate() attached to this very tensor, if it has not been written to since."""
+        tag = getattr(psi, "_b200sq_row_max", None)
+        if tag is not None and tag[1] == psi._version and tag[0].shape[0] == psi.shape[0]:
+            return tag[0]
+        return None
 
     def simulate_expvals(self, cprog: CompiledProgram, x, terms: Sequence, variants=None):
         """Pauli expectation values <P_t> of every data point: float64 (N, n_terms) or (V, N, n_terms)."""
@@ -252,6 +274,8 @@ class Engine:
         cores, |dK| ~ 1e-12, north-star bound 1e-10) or "auto" (int8 where it is faster: 2^n >= 4096 and at
         least 1024 x 512 entries); default from B200SQ_GRAM_PRECISION, else "auto"."""
         torch = self._torch
+        rm_x = self._row_max_of(psi_x) if psi_x.is_contiguous() else None
+        rm_y = rm_x if psi_y is None else (self._row_max_of(psi_y) if psi_y.is_contiguous() else None)
         psi_x = psi_x.contiguous()
         sym = psi_y is None
         psi_y = psi_x if sym else psi_y.contiguous()
@@ -272,8 +296,10 @@ class Engine:
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
-            _lib.check(self._lib.b200sq_gram(psi_x.data_ptr(), nx, psi_y.data_ptr(), ny, dim,
-                                             out.data_ptr(), out.stride(0), flags, self._stream()))
+            _lib.check(self._lib.b200sq_gram_rowmax(psi_x.data_ptr(), nx, psi_y.data_ptr(), ny, dim,
+                                                    out.data_ptr(), out.stride(0), flags,
+                                                    rm_x.data_ptr() if rm_x is not None else None,
+                                                    rm_y.data_ptr() if rm_y is not None else None, self._stream()))
         return out
 
     def alloc_planes(self, plane_rows: int, dim: int):
@@ -301,12 +327,14 @@ class Engine:
     def slice_states(self, psi, planes, expo, row0: int = 0):
         """Write the digit planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes``."""
         torch = self._torch
+        rm = self._row_max_of(psi) if psi.is_contiguous() else None
         psi = psi.contiguous()
         if psi.dtype != torch.complex128 or psi.dim() != 2:
             raise ValueError("states must be a (N, 2^n) complex128 array")
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.b200sq_gram_slice(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(),
-                                                   planes.shape[1], int(row0), expo.data_ptr(), self._stream()))
+            _lib.check(self._lib.b200sq_gram_slice_rowmax(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(),
+                                                          planes.shape[1], int(row0), expo.data_ptr(),
+                                                          rm.data_ptr() if rm is not None else None, self._stream()))
 
     def gram_from_planes(self, planes_x, expo_x, x0: int, nx: int, planes_y=None, expo_y=None, y0: int = 0,
                          ny: int = 0, diagonal: str = "one", out=None):

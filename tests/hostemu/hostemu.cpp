@@ -33,7 +33,7 @@ __attribute__((visibility("default"))) int hostemu_simulate(
     try {
         std::vector<b200sq_gate> g(gates, gates + n_gates);
         const char* lift = getenv("B200SQ_ROT_LIFT");
-        Plan pl = make_plan(n, g, tile_bits, 4, true, lift && lift[0] == '1');
+        Plan pl = make_plan(n, g, tile_bits, 4, true, !(lift && lift[0] == '0'));
         double2* psi = reinterpret_cast<double2*>(psi_out);
         const int TS = team_size;
         int log2ts = 0;

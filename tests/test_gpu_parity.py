@@ -250,6 +250,37 @@ def test_gram_int8_matches_fp64_on_circuit_states(sq, executor):
     assert torch.equal(k8, k8.T)
 
 
+def test_row_maxima_from_the_gate_pass_feed_the_digit_slicing(sq, executor):
+    """simulate() tags its output with the per-state maxima the last gate pass reduced (b200sq_simulate_rowmax);
+    gram() / slice_states() of that very tensor then skip their own max sweep.  Same digits, same exponents as the
+    two-sweep slicing of an untagged copy; an in-place write invalidates the tag."""
+    import torch
+
+    n, d, N = 12, 3, 300
+    X = np.random.default_rng(12).uniform(-0.95, 0.95, (N, d))
+    enc = sq.ChebyshevPQC(n, 2)
+    eng = executor.engine
+    for tile_bits in (0, 7):                                         # one pass / several passes
+        cp = sq.B200Circuit(enc.get_program(d), tile_bits=tile_bits).compiled(eng, enc.generate_initial_parameters(d, seed=0))
+        psi = eng.simulate(cp, X)
+        rm = eng._row_max_of(psi)
+        assert rm is not None
+        want_hi = (psi.view(torch.float64).abs().amax(dim=1).view(torch.int64) >> 32).to(torch.int32)
+        assert torch.equal(rm, want_hi)
+        _, p1, e1 = eng.alloc_plane_block(N, 1 << n)
+        _, p2, e2 = eng.alloc_plane_block(N, 1 << n)
+        eng.slice_states(psi, p1, e1)
+        eng.slice_states(psi.clone(), p2, e2)                        # untagged: two sweeps
+        assert torch.equal(e1, e2) and torch.equal(p1, p2)
+        k_tag = eng.gram(psi, None, precision="int8")
+        k_ref = eng.gram(psi.clone(), None, precision="int8")
+        assert float((k_tag - k_ref).abs().max()) < 1e-14
+    psi.mul_(0.5)                                                    # in-place write: the tag is stale
+    assert eng._row_max_of(psi) is None
+    k_half = eng.gram(psi, None, diagonal="computed", precision="int8")
+    assert abs(float(k_half[3, 3]) - 1.0 / 16.0) < 1e-12
+
+
 def test_config_c5_size_int8_gram_on_16_points(sq, executor):
     """BASELINE configs[4] state size (20 qubits, K' = 2^21 int8 per row): the INT8 Gram of 16 + 5 points against
     the oracle; the measured maximum error is printed (the scheme's bound grows with K')."""

@@ -21,7 +21,7 @@ def stats(enc, d, tile_bits=0, params=None):
     steps = [tuple(w[pos + 7 * i: pos + 7 * i + 7]) for i in range(nu)]; pos += 7 * nu
     ninit = w[pos]
     print(f"n={n} T={T} gates={len(prog)} passes={npass} rounds={nr} steps={nu} folded={ninit}")
-    names = {1: "U2", 2: "DIAG", 5: "CTRL", 6: "L_RX", 7: "L_REAL", 8: "L_GEN", 9: "DTAB"}
+    names = {1: "U2", 2: "DIAG", 5: "CTRL", 6: "L_RX", 7: "L_REAL", 8: "L_GEN", 9: "DTAB", 10: "S_RX", 11: "S_RY"}
     qs = lambda m: [q for q in range(n) if m >> q & 1]
     for i, (Tp, a_in, a_out, last, r0, r1, s0, s1, mat, nfresh, ntabs, tq) in enumerate(passes):
         print(f" pass {i}: tile={tq} in={len(qs(a_in))}q out={len(qs(a_out))}q fresh={nfresh} last={last} "
@@ -31,7 +31,7 @@ def stats(enc, d, tile_bits=0, params=None):
             desc = []
             for u in range(rs0, rs1):
                 kind, gate, a, b, ctrl, m, sw = steps[u]
-                if kind in (6, 7, 8):
+                if kind in (6, 7, 8, 10, 11):
                     desc.append(f"{names[kind]}[slots {[c for c in range(3) if a >> c & 1]}]")
                 elif kind == 9:
                     desc.append(f"DTAB[bits {a}..{a + b - 1}]")
