@@ -158,6 +158,16 @@ B200SQ_API int b200sq_simulate_expvals(b200sq_program* prog, int64_t N, int d, c
                             const uint32_t* x_mask, const uint32_t* z_mask, double* out_dev,
                             void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* b200sq_simulate_expvals with a SECOND shift per variant (var_gate2 / var_shift2: HOST arrays, may be NULL):
+ * variant v also adds var_shift2[v] to the angle of gate var_gate2[v] (the same gate as var_gate[v]: the shifts
+ * add).  Two-gate shifted circuits are what second-order derivatives ("dfdxdx", "dfdpdx", "dfdpdp", the Laplacian:
+ * src/squlearn/qnn/lowlevel_qnn/evaluation_classes.py:105-164) are assembled from.                        */
+B200SQ_API int b200sq_simulate_expvals2(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                                        const double* angle_table_dev, int n_variants, const int32_t* var_gate,
+                                        const double* var_shift, const int32_t* var_gate2, const double* var_shift2,
+                                        int n_terms, const uint32_t* x_mask, const uint32_t* z_mask,
+                                        double* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Pauli expectation values of states already in device memory: out[i][t] = <psi_i|P_t|psi_i>. */
 B200SQ_API int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int n_terms,
                    const uint32_t* x_mask, const uint32_t* z_mask, double* out_dev, void* stream);

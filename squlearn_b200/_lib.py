@@ -71,7 +71,7 @@ EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_rowmax",
-    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals", "b200sq_expvals",
+    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_simulate_expvals", "b200sq_expvals",
     "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_wait_flags", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
     "b200sq_copy_async", "b200sq_rbf",
     "b200sq_launch_count",
@@ -124,6 +124,10 @@ def load():
     lib.b200sq_simulate_expvals.argtypes = [vp, i64, c.c_int, vp, vp, c.c_int, c.POINTER(i32),
                                             c.POINTER(dbl), c.c_int, c.POINTER(c.c_uint32),
                                             c.POINTER(c.c_uint32), vp, vp, c.c_size_t, vp]
+    lib.b200sq_simulate_expvals2.restype = c.c_int
+    lib.b200sq_simulate_expvals2.argtypes = [vp, i64, c.c_int, vp, vp, c.c_int, c.POINTER(i32), c.POINTER(dbl),
+                                             c.POINTER(i32), c.POINTER(dbl), c.c_int, c.POINTER(c.c_uint32),
+                                             c.POINTER(c.c_uint32), vp, vp, c.c_size_t, vp]
     lib.b200sq_expvals.restype = c.c_int
     lib.b200sq_expvals.argtypes = [vp, i64, c.c_int, c.c_int, c.POINTER(c.c_uint32),
                                    c.POINTER(c.c_uint32), vp, vp]

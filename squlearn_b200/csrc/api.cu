@@ -44,9 +44,10 @@ struct b200sq_program {
     std::vector<size_t> blob_off;
     std::vector<const void*> jit_kernels;  // per pass: run-time specialised kernel (jit.cu), or nullptr
     std::vector<char> jit_tried;
-    int32_t* d_var_gate = nullptr;
+    int32_t* d_var_gate = nullptr;   // [2][var_cap]: first / second shifted gate of every variant
     double* d_var_shift = nullptr;
     int var_cap = 0;
+    bool have_var2 = false;
     uint32_t* d_masks = nullptr;
     int mask_cap = 0;
 
@@ -109,23 +110,32 @@ int ensure_device(b200sq_program* p, cudaStream_t stream) {
 }
 
 int upload_variants(b200sq_program* p, int n_variants, const int32_t* var_gate, const double* var_shift,
-                    cudaStream_t stream) {
-    if (!var_gate) return 0;
+                    cudaStream_t stream, const int32_t* var_gate2 = nullptr, const double* var_shift2 = nullptr) {
+    p->have_var2 = false;
+    if (!var_gate) return var_gate2 ? fail(2, "a second shift needs a first one") : 0;
     if (!var_shift) return fail(2, "var_shift is NULL but var_gate is not");
+    if (var_gate2 && !var_shift2) return fail(2, "var_shift2 is NULL but var_gate2 is not");
     for (int v = 0; v < n_variants; ++v)
-        if (var_gate[v] >= (int)p->plan.gates.size()) return fail(2, "variant gate index out of range");
+        if (var_gate[v] >= (int)p->plan.gates.size() || (var_gate2 && var_gate2[v] >= (int)p->plan.gates.size()))
+            return fail(2, "variant gate index out of range");
     if (n_variants > p->var_cap) {
         cudaFree(p->d_var_gate);
         cudaFree(p->d_var_shift);
         p->var_cap = 0;
         cudaError_t e;
-        if ((e = cudaMalloc(&p->d_var_gate, n_variants * sizeof(int32_t))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&p->d_var_shift, n_variants * sizeof(double))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&p->d_var_gate, 2 * (size_t)n_variants * sizeof(int32_t))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&p->d_var_shift, 2 * (size_t)n_variants * sizeof(double))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
         p->var_cap = n_variants;
     }
     cudaMemcpyAsync(p->d_var_gate, var_gate, n_variants * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
     cudaError_t e = cudaMemcpyAsync(p->d_var_shift, var_shift, n_variants * sizeof(double),
                                     cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && var_gate2) {
+        cudaMemcpyAsync(p->d_var_gate + p->var_cap, var_gate2, n_variants * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        e = cudaMemcpyAsync(p->d_var_shift + p->var_cap, var_shift2, n_variants * sizeof(double),
+                            cudaMemcpyHostToDevice, stream);
+        p->have_var2 = true;
+    }
     if (e != cudaSuccess) return cuda_fail(e, "upload variants");
     return 0;
 }
@@ -206,6 +216,8 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.variant0 = v0;
         a.var_gate = have_variants ? p->d_var_gate : nullptr;
         a.var_shift = have_variants ? p->d_var_shift : nullptr;
+        a.var_gate2 = (have_variants && p->have_var2) ? p->d_var_gate + p->var_cap : nullptr;
+        a.var_shift2 = (have_variants && p->have_var2) ? p->d_var_shift + p->var_cap : nullptr;
         a.store = to_out ? 0 : 1;
         a.n_terms = to_out ? n_terms : 0;
         a.xmask = p->d_masks;
@@ -372,13 +384,22 @@ int b200sq_simulate_expvals(b200sq_program* prog, int64_t N, int d, const double
                             const double* var_shift, int n_terms, const uint32_t* x_mask,
                             const uint32_t* z_mask, double* out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream_) {
+    return b200sq_simulate_expvals2(prog, N, d, x_dev, angle_table_dev, n_variants, var_gate, var_shift, nullptr,
+                                    nullptr, n_terms, x_mask, z_mask, out_dev, workspace_dev, workspace_bytes, stream_);
+}
+
+int b200sq_simulate_expvals2(b200sq_program* prog, int64_t N, int d, const double* x_dev,
+                             const double* angle_table_dev, int n_variants, const int32_t* var_gate,
+                             const double* var_shift, const int32_t* var_gate2, const double* var_shift2,
+                             int n_terms, const uint32_t* x_mask, const uint32_t* z_mask, double* out_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream_) {
     if (!prog || !out_dev || !x_mask || !z_mask) return fail(2, "NULL argument");
     if (N < 0 || n_variants < 1 || n_terms < 1) return fail(2, "bad sizes");
     if (N == 0) return 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     int e;
     if ((e = ensure_device(prog, stream))) return e;
-    if ((e = upload_variants(prog, n_variants, var_gate, var_shift, stream))) return e;
+    if ((e = upload_variants(prog, n_variants, var_gate, var_shift, stream, var_gate2, var_shift2))) return e;
     if ((e = upload_masks(prog, n_terms, x_mask, z_mask, prog->plan.n, stream))) return e;
     const Plan& pl = prog->plan;
     const bool have_var = var_gate != nullptr;

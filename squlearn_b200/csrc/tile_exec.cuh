@@ -205,8 +205,8 @@ struct ItemCtx {
     const double* xrow;
     const double* table;
     int64_t n_total, sample;
-    int vgate;
-    double vshift;
+    int vgate, vgate2;       // gates whose angle is shifted in this variant (-1: none); a second shift serves the
+    double vshift, vshift2;  // second-order derivatives (two gates, or twice the same gate: the shifts add)
     uint32_t ext_base;
 };
 
@@ -256,6 +256,7 @@ B200SQ_HD void fold_qubit_vector(int qubit, const DInit* inits, int n_init, cons
         const b200sq_gate g = ic.gates[inits[i].gate];
         double theta = gate_angle(g, ic.xrow, ic.table, ic.n_total, ic.sample);
         if ((int)inits[i].gate == ic.vgate) theta += ic.vshift;
+        if ((int)inits[i].gate == ic.vgate2) theta += ic.vshift2;
         double2 m[4];
         if (gate_info(g.kind).diag) {
             build_matrix(MAT_DIAG, 0, g, theta, m);  // m[0], m[1] = phases of |0>, |1>
@@ -280,6 +281,7 @@ B200SQ_HD void build_mats_thread(const PassView& pv, const TeamMem& tm, const It
         const b200sq_gate g = ic.gates[r.gate];
         double theta = gate_angle(g, ic.xrow, ic.table, ic.n_total, ic.sample);
         if ((int)r.gate == ic.vgate) theta += ic.vshift;
+        if ((int)r.gate == ic.vgate2) theta += ic.vshift2;
         build_matrix(r.kind, r.swap, g, theta, tm.mats + r.mat);
     }
     for (int f = tid; f < P.n_fresh; f += TS)

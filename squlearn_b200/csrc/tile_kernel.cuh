@@ -25,6 +25,8 @@ struct TileArgs {
     int32_t variant0;          // first variant of this launch
     const int32_t* var_gate;   // device, indexed by absolute variant; nullptr = unshifted
     const double* var_shift;
+    const int32_t* var_gate2;  // optional second shift per variant (second-order derivatives); nullptr = none
+    const double* var_shift2;
     int32_t store;             // write the tile to dst
     int32_t n_terms;           // > 0: reduce the tile to expectation values (requires T == n)
     const uint32_t* xmask;     // device
@@ -194,6 +196,8 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
         ic.n_total = A.n_total;
         ic.vgate = A.var_gate ? A.var_gate[variant] : -1;
         ic.vshift = A.var_gate ? A.var_shift[variant] : 0.0;
+        ic.vgate2 = A.var_gate2 ? A.var_gate2[variant] : -1;
+        ic.vshift2 = A.var_gate2 ? A.var_shift2[variant] : 0.0;
 
         // ---- phase A: per-sample gate matrices + start vectors of the fresh qubits.  Consecutive items
         // of a team are tiles of the same state, so this runs once per state, not once per tile.

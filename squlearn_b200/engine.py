@@ -167,14 +167,16 @@ class Engine:
 
     @staticmethod
     def _variants(variants):
+        """(n, gate ptr, shift ptr, keep-alive[, second gate ptr, second shift ptr]) of a variant spec
+        ``(gate_idx, shift)`` or ``(gate_idx, shift, gate_idx2, shift2)`` (two shifts per variant)."""
         if variants is None:
             return 1, None, None, None
-        gate_idx, shift = variants
-        gate_idx = np.ascontiguousarray(gate_idx, dtype=np.int32)
-        shift = np.ascontiguousarray(shift, dtype=np.float64)
-        keep = (gate_idx, shift)
-        return (len(gate_idx), gate_idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                shift.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), keep)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32 if k % 2 == 0 else np.float64) for k, a in enumerate(variants)]
+        if len(arrs) not in (2, 4) or any(len(a) != len(arrs[0]) for a in arrs):
+            raise ValueError("variants must be (gate_idx, shift) or (gate_idx, shift, gate_idx2, shift2)")
+        ptrs = [a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32 if k % 2 == 0 else ctypes.c_double))
+                for k, a in enumerate(arrs)]
+        return (len(arrs[0]), ptrs[0], ptrs[1], arrs) + tuple(ptrs[2:])
 
     @staticmethod
     def _masks(terms, n_qubits):
@@ -200,7 +202,9 @@ class Engine:
         prog = cprog.program
         xd = self._features(prog, x)
         n_samples = xd.shape[0]
-        nv, vg, vs, keep = self._variants(variants)
+        nv, vg, vs, keep = self._variants(variants)[:4]
+        if variants is not None and len(variants) > 2:
+            raise ValueError("states of doubly shifted circuits are not offered; use simulate_expvals")
         table = self._table(cprog, x)
         with torch.cuda.device(self.device):
             psi = torch.empty((nv, n_samples, 1 << prog.num_qubits), dtype=torch.complex128,
@@ -234,7 +238,8 @@ class Engine:
         prog = cprog.program
         xd = self._features(prog, x)
         n_samples = xd.shape[0]
-        nv, vg, vs, keep = self._variants(variants)
+        nv, vg, vs, keep, *second = self._variants(variants)
+        vg2, vs2 = second if second else (None, None)
         xm, zm = self._masks(terms, prog.num_qubits)
         table = self._table(cprog, x)
         with torch.cuda.device(self.device):
@@ -247,9 +252,9 @@ class Engine:
                     self._workspace = None
                     self._workspace = torch.empty(want, dtype=torch.uint8, device=self.device)
                 ws_ptr, ws_bytes = self._workspace.data_ptr(), self._workspace.numel()
-            _lib.check(self._lib.b200sq_simulate_expvals(
+            _lib.check(self._lib.b200sq_simulate_expvals2(
                 cprog.handle, n_samples, xd.shape[1], xd.data_ptr(),
-                table.data_ptr() if table is not None else None, nv, vg, vs, len(terms), xm, zm,
+                table.data_ptr() if table is not None else None, nv, vg, vs, vg2, vs2, len(terms), xm, zm,
                 out.data_ptr(), ws_ptr, ws_bytes, self._stream()))
         return out if variants is not None else out[0]
 

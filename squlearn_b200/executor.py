@@ -25,7 +25,7 @@ import numpy as np
 
 from .engine import Engine
 from .observables import ObservableBase, pauli_sum_squared
-from .program import Program
+from .program import Program, second_order_variants
 
 
 class Executor:
@@ -244,4 +244,68 @@ def b200_gradient(circuit: B200Circuit, executor: Executor, param=None, x=None, 
                                 variants=(gate_idx, shift)).cpu().numpy()  # (V, N, n_terms)
     for v in range(len(gate_idx)):
         out[:, :, pidx[v]] += weight[v][:, None] * _combine(expv[v], per_obs)
+    return out
+
+
+def _term_values(expv: np.ndarray, per_obs, n_param_obs: int, per_term: bool) -> np.ndarray:
+    """(N, n_terms) term expectation values -> (N, n_obs) observable values, or with ``per_term`` the derivative
+    with respect to every observable parameter (N, n_obs, P_op) (the expectation of the term it multiplies)."""
+    if not per_term:
+        return _combine(expv, per_obs)
+    out = np.zeros((expv.shape[0], len(per_obs), n_param_obs))
+    for o, entries in enumerate(per_obs):
+        for t, _, j in entries:
+            if j >= 0:
+                out[:, o, j] += expv[:, t]
+    return out
+
+
+def b200_hessian(circuit: B200Circuit, executor: Executor, param=None, x=None, param_obs=None, wrt=("x", "x"),
+                 squared: bool = False, per_term: bool = False, chunk: int = 4096, **_) -> np.ndarray:
+    """Second derivatives of the expectation values: (N, n_obs, D1, D2) with ``wrt = (a, b)``, a, b in {"param", "x"}
+    (axes in that order), from doubly shifted circuits (program.second_order_variants) evaluated ``chunk`` variants
+    per engine call.  ``per_term``: (N, n_obs, P_op, D1, D2), the same derivative of d<O>/d param_obs.
+    Reference: "dfdxdx", "dfdpdx", "dfdxdp", "dfdpdp", "dfdopdxdx" of evaluation_classes.py:105-164."""
+    eng = executor.engine
+    prog = circuit.program
+    x2 = np.asarray(np.zeros((1, 0)) if x is None else x, dtype=np.float64)
+    if x2.ndim == 1:
+        x2 = x2.reshape(-1, max(prog.num_features, 1))
+    pv = None if param is None else np.asarray(param, dtype=np.float64)
+    strings, per_obs = circuit.observable_terms(param_obs, squared)
+    ga, sa, gb, sb, weight, ia, ib = second_order_variants(prog, x2, wrt[0], wrt[1], pv)
+    dims = tuple(prog.num_parameters if w == "param" else prog.num_features for w in wrt)
+    npo = circuit.num_parameters_observable
+    shape = (x2.shape[0], len(per_obs)) + ((npo,) if per_term else ()) + dims
+    out = np.zeros(shape)
+    cprog = circuit.compiled(eng, param)
+    for c0 in range(0, len(ga), chunk):
+        sl = slice(c0, c0 + chunk)
+        expv = eng.simulate_expvals(cprog, x2, strings, variants=(ga[sl], sa[sl], gb[sl], sb[sl])).cpu().numpy()
+        for v in range(expv.shape[0]):
+            vals = _term_values(expv[v], per_obs, npo, per_term)         # (N, n_obs[, P_op])
+            w = weight[c0 + v].reshape((-1,) + (1,) * (vals.ndim - 1))
+            out[..., ia[c0 + v], ib[c0 + v]] += w * vals
+    return out
+
+
+def b200_term_gradient(circuit: B200Circuit, executor: Executor, param=None, x=None, param_obs=None,
+                       wrt: str = "x", **_) -> np.ndarray:
+    """(N, n_obs, P_op, D): derivative with respect to x (or the circuit parameters) of d<O>/d param_obs — the
+    reference's "dfdopdx" / "dfdopdp" (evaluation_classes.py:130-160)."""
+    eng = executor.engine
+    prog = circuit.program
+    x2 = np.asarray(np.zeros((1, 0)) if x is None else x, dtype=np.float64)
+    if x2.ndim == 1:
+        x2 = x2.reshape(-1, max(prog.num_features, 1))
+    strings, per_obs = circuit.observable_terms(param_obs)
+    gate_idx, shift, weight, pidx = prog.shift_variants(
+        x2, wrt=wrt, p=None if param is None else np.asarray(param, dtype=np.float64))
+    npo = circuit.num_parameters_observable
+    out = np.zeros((x2.shape[0], len(per_obs), npo, prog.num_parameters if wrt == "param" else prog.num_features))
+    if len(gate_idx) == 0:
+        return out
+    expv = eng.simulate_expvals(circuit.compiled(eng, param), x2, strings, variants=(gate_idx, shift)).cpu().numpy()
+    for v in range(len(gate_idx)):
+        out[..., pidx[v]] += weight[v][:, None, None] * _term_values(expv[v], per_obs, npo, True)
     return out

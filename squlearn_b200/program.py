@@ -71,6 +71,28 @@ class Angle:
             d = 1.0 / (1.0 + v * v)
         return self.scale * pv * d
 
+    def d2theta(self, x: np.ndarray, p: Optional[np.ndarray], wrt1: str, i1: int, wrt2: str, i2: int):
+        """Second derivative of the angle with respect to (parameter / feature i1, parameter / feature i2) per sample,
+        or None when it vanishes: theta = offset + scale * p * fn(x) is linear in p, so only d2/dx2 = scale p fn''(x)
+        and d2/dp dx = scale fn'(x) survive (fn'': linear 0, arccos -x (1-x^2)^(-3/2), arctan -2x (1+x^2)^(-2))."""
+        if self.table is not None or self.feature is None:
+            return None
+        v = x[:, self.feature]
+        if wrt1 == "x" and wrt2 == "x":
+            if i1 != self.feature or i2 != self.feature or self.fn == "linear":
+                return None
+            pv = 1.0 if self.param is None else float(p[self.param])
+            d2 = -v / (1.0 - v * v) ** 1.5 if self.fn == "arccos" else -2.0 * v / (1.0 + v * v) ** 2
+            return self.scale * pv * d2
+        if wrt1 == wrt2:          # param, param
+            return None
+        ip, ix = (i1, i2) if wrt1 == "param" else (i2, i1)
+        if self.param is None or ip != self.param or ix != self.feature:
+            return None
+        d1 = np.ones_like(v) if self.fn == "linear" else (-1.0 / np.sqrt(1.0 - v * v) if self.fn == "arccos"
+                                                        else 1.0 / (1.0 + v * v))
+        return self.scale * d1
+
     def coeffs(self, p: np.ndarray) -> Tuple[float, float]:
         """(c0, c1) of the C ABI: theta = c0 + c1 * f(x[feat])."""
         pv = 1.0 if self.param is None else float(p[self.param])
@@ -218,6 +240,55 @@ class Program:
                     np.zeros(0, dtype=np.int64))
         return (np.asarray(gate_idx, dtype=np.int32), np.asarray(shifts, dtype=np.float64),
                 np.stack(weights, axis=0), np.asarray(params, dtype=np.int64))
+
+
+def _shift_rule(name: str):
+    """[(shift, coefficient)] of the parameter-shift rule of a gate (optree_derivative.py:130-158, :352-370)."""
+    if name in ("rx", "ry", "rz", "p", "cp", "rxx", "ryy", "rzz", "rzx"):
+        return [(0.5 * np.pi, 0.5), (-0.5 * np.pi, -0.5)]
+    if name in ("crx", "cry", "crz"):
+        cp_ = (np.sqrt(2.0) + 1.0) / (4.0 * np.sqrt(2.0))
+        cm_ = (np.sqrt(2.0) - 1.0) / (4.0 * np.sqrt(2.0))
+        return [(0.5 * np.pi, cp_), (-0.5 * np.pi, -cp_), (1.5 * np.pi, -cm_), (-1.5 * np.pi, cm_)]
+    raise NotImplementedError(f"no parameter-shift rule for gate {name}")
+
+
+def second_order_variants(program: "Program", x: np.ndarray, wrt1: str, wrt2: str, p: Optional[np.ndarray]):
+    """The doubly shifted circuits of d2 f / d a_i d b_j (a, b in {"param", "x"}):
+
+        d2f/da_i db_j = sum_k sum_l (dtheta_k/da_i)(dtheta_l/db_j) d2f/dtheta_k dtheta_l  +  sum_k (d2theta_k/da_i db_j) df/dtheta_k
+
+    with d2f/dtheta_k dtheta_l from the shift rule applied to both gates (two shifts per variant; the same gate twice:
+    the shifts add) and the second term (curvature of the encoding, e.g. arccos) from single shifts.  This is what the
+    reference's nested jacobians evaluate for "dfdxdx", "dfdpdx", "dfdpdp", ... (evaluation_classes.py:105-164).
+    Returns (gate1[V], shift1[V], gate2[V], shift2[V], weight[V, N], index1[V], index2[V]); gate2 = -1: single shift."""
+    g1, s1, w1, i1 = program.shift_variants(x, wrt=wrt1, p=p)
+    g2, s2, w2, i2 = program.shift_variants(x, wrt=wrt2, p=p)
+    n = x.shape[0]
+    ga, sa, gb, sb, ww, ia, ib = [], [], [], [], [], [], []
+    for a in range(len(g1)):
+        for b in range(len(g2)):
+            ga.append(g1[a]); sa.append(s1[a]); gb.append(g2[b]); sb.append(s2[b])
+            ww.append(w1[a] * w2[b]); ia.append(i1[a]); ib.append(i2[b])
+    n1 = program.num_parameters if wrt1 == "param" else program.num_features
+    n2 = program.num_parameters if wrt2 == "param" else program.num_features
+    for k, g in enumerate(program.gates):
+        if g.angle is None or g.angle.feature is None:
+            continue
+        for j1 in range(n1):
+            for j2 in range(n2):
+                d2 = g.angle.d2theta(x, p, wrt1, j1, wrt2, j2)
+                if d2 is None:
+                    continue
+                for s, c in _shift_rule(g.name):
+                    ga.append(k); sa.append(s); gb.append(-1); sb.append(0.0)
+                    ww.append(c * d2); ia.append(j1); ib.append(j2)
+    if not ga:
+        z = np.zeros(0)
+        return (z.astype(np.int32), z, z.astype(np.int32), z, np.zeros((0, n)), z.astype(np.int64), z.astype(np.int64))
+    return (np.asarray(ga, dtype=np.int32), np.asarray(sa, dtype=np.float64), np.asarray(gb, dtype=np.int32),
+            np.asarray(sb, dtype=np.float64), np.stack([np.broadcast_to(w, (n,)) for w in ww], axis=0),
+            np.asarray(ia, dtype=np.int64), np.asarray(ib, dtype=np.int64))
 
 
 def as_uint32_array(values):

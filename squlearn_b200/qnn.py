@@ -12,9 +12,10 @@ returns a dict with the requested keys plus "x", "param", "param_op".  Axis orde
 
 All x are evaluated in one engine call; "dfdp" uses the parameter-shift batch
 (optree_derivative.py:130-158), which the reference asserts equal to its autodiff routes
-(tests/qnn/lowlevel_qnn/test_lowlevel_qnn.py:36-65).  Derivatives with respect to x and
-second-order derivatives are not part of this round and raise
-NotImplementedError.
+(tests/qnn/lowlevel_qnn/test_lowlevel_qnn.py:36-65).  First-order input derivatives ("dfdx") use the same shifted
+batch with chain-rule weights; second-order keys ("dfdxdx", "dfdpdx", "dfdxdp", "dfdpdp", "dfdopdx", "dfdopdxdx",
+"laplace", "laplace_dop", ...) are assembled from doubly shifted circuits; third-order keys
+raise NotImplementedError.
 """
 
 from typing import Sequence, Union
@@ -27,20 +28,29 @@ from .executor import (
     Executor,
     b200_evaluate,
     b200_gradient,
+    b200_hessian,
     b200_operator_gradient,
+    b200_term_gradient,
 )
 from .observables import ObservableBase
 
-_DIRECT = {"f", "fcc", "dfdp", "dfccdp", "dfdop", "dfccdop", "dfdx", "dfccdx"}
+_DIRECT = {"f", "fcc", "dfdp", "dfccdp", "dfdop", "dfccdop", "dfdx", "dfccdx",
+           # second order: doubly shifted circuits (evaluation_classes.py:105-164); axes follow the key, e.g.
+           # "dfdpdx" -> (..., P, d) (the reference reorders its nested jacobians the same way,
+           # lowlevel_qnn_pennylane.py:331-338)
+           "dfdxdx", "dfdpdp", "dfdpdx", "dfdxdp", "dfccdxdx", "dfccdpdp",
+           "dfdopdx", "dfdopdp", "dfdpdop", "dfdopdop", "dfdopdxdx"}
+_SECOND = {"dfdxdx": ("x", "x"), "dfdpdp": ("param", "param"), "dfdpdx": ("param", "x"), "dfdxdp": ("x", "param"),
+           "dfccdxdx": ("x", "x"), "dfccdpdp": ("param", "param")}
 _POST = {
     "var": ("f", "fcc"), "varf": ("f", "fcc"),
     "dvardp": ("f", "dfccdp", "dfdp"), "dvarfdp": ("f", "dfccdp", "dfdp"),
     "dvardop": ("f", "dfccdop", "dfdop"), "dvarfdop": ("f", "dfccdop", "dfdop"),
+    "dvardx": ("f", "dfccdx", "dfdx"), "dvarfdx": ("f", "dfccdx", "dfdx"),
+    "laplace": ("dfdxdx",), "laplace_dop": ("dfdopdxdx",),
 }
-_NOT_YET = {"dfdxdx", "laplace", "laplace_dp", "laplace_dop", "dfdpdp", "dfdopdp",
-            "dfdpdop", "dfdopdop", "dfdpdx", "dfdxdp", "dfdxdxdp", "dfdxdpdx", "dfdpdxdx",
-            "dfdopdx", "dfdopdxdx", "dfccdxdx", "dfccdpdp", "dfccdopdx", "dfccdopdop",
-            "dvardx", "dvarfdx", "fischer"}
+# third order in the circuit angles (and the Fisher matrix): not offered
+_NOT_YET = {"laplace_dp", "dfdxdxdp", "dfdxdpdx", "dfdpdxdx", "dfccdopdx", "dfccdopdop", "fischer"}
 
 
 class LowLevelQNN:
@@ -112,6 +122,17 @@ class LowLevelQNN:
             return ex.b200_execute(b200_gradient, self._circuit, squared=sq, **kw)
         if key in ("dfdx", "dfccdx"):
             return ex.b200_execute(b200_gradient, self._circuit, squared=sq, wrt="x", **kw)
+        if key in _SECOND:
+            return ex.b200_execute(b200_hessian, self._circuit, squared=sq or key.startswith("dfcc"),
+                                   wrt=_SECOND[key], **kw)
+        if key == "dfdopdxdx":
+            return ex.b200_execute(b200_hessian, self._circuit, wrt=("x", "x"), per_term=True, **kw)
+        if key in ("dfdopdx", "dfdopdp", "dfdpdop"):
+            g = ex.b200_execute(b200_term_gradient, self._circuit, wrt="x" if key == "dfdopdx" else "param", **kw)
+            return np.swapaxes(g, -1, -2) if key == "dfdpdop" else g
+        if key == "dfdopdop":   # the observables are linear in their parameters (observable_base.py)
+            npo = self._num_parameters_observable
+            return np.zeros((x_inp.shape[0], self.num_operator, npo, npo))
         if key == "dfdop":
             return ex.b200_execute(b200_operator_gradient, self._circuit, **kw)
         if key == "dfccdop":
@@ -199,6 +220,13 @@ class LowLevelQNN:
                 f = value_dict["f"]
                 value_dict[v] = value_dict["dfccdop"] - 2.0 * np.multiply(
                     value_dict["dfdop"], np.expand_dims(f, -1))
+            elif v in ("dvardx", "dvarfdx"):
+                f = value_dict["f"]
+                value_dict[v] = value_dict["dfccdx"] - 2.0 * np.multiply(
+                    value_dict["dfdx"], np.expand_dims(f, -1))
+            elif v in ("laplace", "laplace_dop"):   # sum of the diagonal of the feature Hessian (:292-316)
+                h = value_dict[_POST[v][0]]
+                value_dict[v] = np.trace(h, axis1=-2, axis2=-1)
 
         if self.caching:
             self.result_container[cache_key] = value_dict

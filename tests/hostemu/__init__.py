@@ -46,6 +46,7 @@ def simulate(program, params, x, tile_bits=0, variants=None, team_size=32):
     n_samples, d = x.shape
     gates = program.c_gates(params)
     table = program.angle_table(x, params)
+    vg2 = vs2 = None
     if variants is None:
         nv, vg, vs = 1, None, None
     else:
@@ -54,6 +55,11 @@ def simulate(program, params, x, tile_bits=0, variants=None, team_size=32):
         nv = len(vg_arr)
         vg = vg_arr.ctypes.data_as(ctypes.c_void_p)
         vs = vs_arr.ctypes.data_as(ctypes.c_void_p)
+        if len(variants) > 2:   # second shift per variant (second-order derivatives)
+            vg2_arr = np.ascontiguousarray(variants[2], dtype=np.int32)
+            vs2_arr = np.ascontiguousarray(variants[3], dtype=np.float64)
+            vg2 = vg2_arr.ctypes.data_as(ctypes.c_void_p)
+            vs2 = vs2_arr.ctypes.data_as(ctypes.c_void_p)
     dim = 1 << program.num_qubits
     psi = np.zeros((nv, n_samples, dim), dtype=np.complex128)
     rc = lib().hostemu_simulate(
@@ -61,7 +67,7 @@ def simulate(program, params, x, tile_bits=0, variants=None, team_size=32):
         ctypes.c_int(tile_bits), ctypes.c_int64(n_samples), ctypes.c_int(d),
         x.ctypes.data_as(ctypes.c_void_p),
         table.ctypes.data_as(ctypes.c_void_p) if table is not None else None,
-        ctypes.c_int(nv), vg, vs, psi.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(team_size))
+        ctypes.c_int(nv), vg, vs, psi.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(team_size), vg2, vs2)
     if rc < 0:
         raise RuntimeError(lib().hostemu_last_error().decode())
     return (psi if variants is not None else psi[0]), rc

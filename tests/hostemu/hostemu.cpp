@@ -29,7 +29,7 @@ __attribute__((visibility("default"))) const char* hostemu_last_error() { return
 __attribute__((visibility("default"))) int hostemu_simulate(
     int n, int n_gates, const b200sq_gate* gates, int tile_bits, int64_t N, int d, const double* x,
     const double* table, int n_variants, const int32_t* var_gate, const double* var_shift,
-    double* psi_out, int team_size) {
+    double* psi_out, int team_size, const int32_t* var_gate2, const double* var_shift2) {
     try {
         std::vector<b200sq_gate> g(gates, gates + n_gates);
         const char* lift = getenv("B200SQ_ROT_LIFT");
@@ -79,6 +79,8 @@ __attribute__((visibility("default"))) int hostemu_simulate(
                         ic.sample = s;
                         ic.vgate = var_gate ? var_gate[v] : -1;
                         ic.vshift = var_gate ? var_shift[v] : 0.0;
+                        ic.vgate2 = var_gate2 ? var_gate2[v] : -1;
+                        ic.vshift2 = var_gate2 ? var_shift2[v] : 0.0;
                         uint32_t obase_in, obase_out;
                         const bool zero = item_outer(P, o, ic.ext_base, obase_in, obase_out);
                         const int64_t st = (int64_t)v * N + s;

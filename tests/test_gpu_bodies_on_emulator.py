@@ -41,3 +41,7 @@ def test_fidelity_kernel_regularization_mitigation_and_none_policy_on_emulator()
 
 def test_qnn_regressor_reference_golden_and_fit_on_emulator(goldens, regression_data):
     gpu_tests.test_qnn_regressor_reference_golden_and_fit(sq, EmuExecutor(), goldens, regression_data)
+
+
+def test_second_order_derivatives_on_emulator():
+    gpu_tests.test_second_order_derivatives_against_finite_differences(sq, EmuExecutor())

@@ -643,3 +643,49 @@ def test_qnn_regressor_config_c4_shape_trains(sq, executor):
                                ("f", "dfdp", "dfdop"))
     for key in ("f", "dfdp", "dfdop"):
         assert np.max(np.abs(vals[key] - want[key])) < GRAM_TOL, key
+
+
+# ------------------------------------------------------------------------------ second-order derivatives (row f3)
+def test_second_order_derivatives_against_finite_differences(sq, executor):
+    """"dfdxdx", "dfdpdx", "dfdxdp", "dfdpdp", "laplace", "dfdopdx", "dfdopdxdx", "laplace_dop", "dvardx"
+    (evaluation_classes.py:105-164) from doubly shifted circuits, against central differences of the first-order /
+    value results, through the non-linear arccos encoding; axes follow the key ("dfdpdx" -> (N, P, d))."""
+    d = 2
+    enc = sq.ChebyshevPQC(3, 1)
+    qnn = sq.LowLevelQNN(enc, [sq.SummedPaulis(3), sq.SinglePauli(3, 1, "X")], executor, d, caching=False)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.8, 0.8, (5, d))
+    P = enc.num_parameters
+    p, po = rng.uniform(-1, 1, P), rng.uniform(0.2, 1, 4)
+    r = qnn.evaluate(X, p, po, "f", "dfdx", "dfdp", "dfdxdx", "dfdpdx", "dfdxdp", "dfdpdp", "laplace", "dfdopdx",
+                     "dfdopdxdx", "laplace_dop", "dfdopdp", "dfdpdop", "dfdopdop", "dvardx", "dfccdxdx")
+    assert r["dfdxdx"].shape == (5, 2, d, d) and r["dfdpdx"].shape == (5, 2, P, d) and r["dfdxdp"].shape == (5, 2, d, P)
+    assert r["dfdopdxdx"].shape == (5, 2, 4, d, d) and r["laplace_dop"].shape == (5, 2, 4) and r["laplace"].shape == (5, 2)
+    h = 1e-4
+    first = lambda key, X_, p_: qnn.evaluate(X_, p_, po, key)[key]
+    hx = np.stack([(first("dfdx", X + h * np.eye(d)[j], p) - first("dfdx", X - h * np.eye(d)[j], p)) / (2 * h)
+                   for j in range(d)], axis=-1)                                   # (N, obs, d, d): [i][j] = d/dx_j dfdx_i
+    assert np.max(np.abs(r["dfdxdx"] - hx)) < 1e-6
+    assert np.max(np.abs(r["laplace"] - np.trace(hx, axis1=-2, axis2=-1))) < 1e-6
+    px = np.stack([(first("dfdp", X + h * np.eye(d)[j], p) - first("dfdp", X - h * np.eye(d)[j], p)) / (2 * h)
+                   for j in range(d)], axis=-1)                                   # (N, obs, P, d)
+    assert np.max(np.abs(r["dfdpdx"] - px)) < 1e-6
+    assert np.max(np.abs(r["dfdxdp"] - np.swapaxes(px, -1, -2))) < 1e-6
+    pp = np.stack([(first("dfdp", X, p + h * np.eye(P)[j]) - first("dfdp", X, p - h * np.eye(P)[j])) / (2 * h)
+                   for j in range(P)], axis=-1)
+    assert np.max(np.abs(r["dfdpdp"] - pp)) < 1e-6
+    # observable-parameter derivatives are exact differences (the observables are linear in param_obs)
+    for key, base in (("dfdopdx", "dfdx"), ("dfdopdp", "dfdp"), ("dfdopdxdx", "dfdxdx")):
+        g = np.stack([(qnn.evaluate(X, p, po + np.eye(4)[j], base)[base] - qnn.evaluate(X, p, po - np.eye(4)[j], base)[base]) / 2
+                      for j in range(4)], axis=2)
+        assert np.max(np.abs(r[key] - g)) < 1e-12, key
+    assert np.max(np.abs(r["dfdpdop"] - np.swapaxes(r["dfdopdp"], -1, -2))) == 0.0
+    assert np.all(r["dfdopdop"] == 0.0) and r["dfdopdop"].shape == (5, 2, 4, 4)
+    var = lambda X_: qnn.evaluate(X_, p, po, "var")["var"]
+    dv = np.stack([(var(X + h * np.eye(d)[j]) - var(X - h * np.eye(d)[j])) / (2 * h) for j in range(d)], axis=-1)
+    assert np.max(np.abs(r["dvardx"] - dv)) < 1e-6
+    fcc = lambda X_: qnn.evaluate(X_, p, po, "dfccdx")["dfccdx"]
+    hcc = np.stack([(fcc(X + h * np.eye(d)[j]) - fcc(X - h * np.eye(d)[j])) / (2 * h) for j in range(d)], axis=-1)
+    assert np.max(np.abs(r["dfccdxdx"] - hcc)) < 1e-5
+    with pytest.raises(NotImplementedError):
+        qnn.evaluate(X, p, po, "dfdxdxdp")
