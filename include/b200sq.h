@@ -91,6 +91,10 @@ typedef struct b200sq_program b200sq_program;
                                    /* cores (47-bit fixed point per state row; |dK| ~ 1e-12, see  */
                                    /* DESIGN.md); needs dim >= 64, otherwise the FP64 path runs   */
 
+#define B200SQ_GRAM_CRT 64u        /* with B200SQ_GRAM_INT8: the residue-number ("Ozaki II") form of the scheme:  */
+                                   /* 41-bit fixed point per row, one int8 product per modulus (13 for 2^16        */
+                                   /* amplitudes) and a CRT reconstruction instead of 22 digit-pair products       */
+
 #if !defined(__CUDACC_RTC__) /* host entry points: invisible to the run-time compiled device code */
 
 B200SQ_API const char* b200sq_last_error(void);
@@ -203,6 +207,14 @@ B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* 
                                        int64_t x0, int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev,
                                        int64_t plane_rows_y, int64_t y0, int64_t Ny, int64_t dim, double* K_dev,
                                        int64_t ldk, uint32_t flags, void* stream);
+
+/* CRT form of the plane interface (B200SQ_GRAM_CRT): planes are [2 s][plane_rows][2 * dim] int8 with
+ * s = b200sq_gram_crt_moduli(dim) residue planes of nat followed by s of rot (column operands: the first s);
+ * b200sq_gram_from_planes / b200sq_gram_jobs take such planes when B200SQ_GRAM_CRT is set in the (job) flags. */
+B200SQ_API int b200sq_gram_crt_moduli(int64_t dim);
+B200SQ_API int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
+                                     int64_t plane_rows, int64_t row0, int32_t* expo_dev,
+                                     const uint32_t* row_max_dev, void* stream);
 
 /* Several Gram blocks that share the row operand, in ONE persistent launch (the multi-GPU Gram: the diagonal
  * block of a rank plus every block it owns against received column planes; there is no reference counterpart,

@@ -34,7 +34,7 @@ GATE_ARITY = {
 
 FN_CONST, FN_LINEAR, FN_ARCCOS, FN_ARCTAN, FN_TABLE = range(5)
 
-GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M, GRAM_CLASSIC, GRAM_INT8 = 1, 2, 4, 8, 16, 32
+GRAM_SYMMETRIC, GRAM_DIAG_ONE, GRAM_DIAG_ZERO, GRAM_3M, GRAM_CLASSIC, GRAM_INT8, GRAM_CRT = 1, 2, 4, 8, 16, 32, 64
 
 
 class Gate(ctypes.Structure):
@@ -71,7 +71,8 @@ EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_rowmax",
-    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_simulate_expvals", "b200sq_expvals",
+    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_gram_crt_moduli",
+    "b200sq_gram_slice_crt", "b200sq_simulate_expvals", "b200sq_expvals",
     "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_wait_flags", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
     "b200sq_copy_async", "b200sq_rbf",
     "b200sq_launch_count",
@@ -139,6 +140,10 @@ def load():
     lib.b200sq_gram_slice.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp]
     lib.b200sq_gram_from_planes.restype = c.c_int
     lib.b200sq_gram_from_planes.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, i64, vp, i64, c.c_uint32, vp]
+    lib.b200sq_gram_crt_moduli.restype = c.c_int
+    lib.b200sq_gram_crt_moduli.argtypes = [i64]
+    lib.b200sq_gram_slice_crt.restype = c.c_int
+    lib.b200sq_gram_slice_crt.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, vp]
     lib.b200sq_gram_jobs.restype = c.c_int
     lib.b200sq_gram_jobs.argtypes = [vp, vp, i64, i64, c.c_int, c.POINTER(GramJob), vp]
     lib.b200sq_wait_flags.restype = c.c_int

@@ -489,6 +489,19 @@ int b200sq_gram_slice_rowmax(const void* psi_dev, int64_t N, int64_t dim, void* 
     return 0;
 }
 
+int b200sq_gram_crt_moduli(int64_t dim) { return gram_crt_supported(dim) ? gram_crt_moduli(dim) : 0; }
+
+int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
+                          int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* stream_) {
+    if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
+    if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
+    if (!gram_crt_supported(dim)) return fail(2, "the CRT Gram does not support this state dimension");
+    int e = launch_slice_crt((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
+                             (cudaStream_t)stream_, row_max_dev);
+    if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
 int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x, int64_t x0,
                             int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev, int64_t plane_rows_y,
                             int64_t y0, int64_t Ny, int64_t dim, double* K_dev, int64_t ldk, uint32_t flags,
@@ -499,6 +512,7 @@ int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev,
     if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
     if ((flags & B200SQ_GRAM_SYMMETRIC) && (planes_x_dev != planes_y_dev || x0 != y0 || Nx != Ny))
         return fail(2, "symmetric Gram needs identical operands");
+    if ((flags & B200SQ_GRAM_CRT) && !gram_crt_supported(dim)) return fail(2, "the CRT Gram does not support this state dimension");
     int e = launch_gram_planes((const int8_t*)planes_x_dev, expo_x_dev, plane_rows_x, x0, Nx,
                                (const int8_t*)planes_y_dev, expo_y_dev, plane_rows_y, y0, Ny, dim, K_dev, ldk, flags,
                                (cudaStream_t)stream_);
@@ -511,6 +525,8 @@ int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_
     if (!planes_x_dev || !expo_x_dev || (n_jobs > 0 && !jobs)) return fail(2, "NULL argument");
     if (n_jobs < 0 || plane_rows_x < 0) return fail(2, "bad sizes");
     if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
+    if (n_jobs > 0 && (jobs[0].flags & B200SQ_GRAM_CRT) && !gram_crt_supported(dim))
+        return fail(2, "the CRT Gram does not support this state dimension");
     for (int j = 0; j < n_jobs; ++j) {
         const b200sq_gram_job& J = jobs[j];
         if (!J.planes_y_dev || !J.expo_y_dev || !J.K_dev) return fail(2, "NULL pointer in a Gram job");
@@ -521,6 +537,7 @@ int b200sq_gram_jobs(const void* planes_x_dev, const int32_t* expo_x_dev, int64_
             return fail(2, "symmetric Gram job needs identical operands");
         if (J.align_yx_dev && !J.align_out_dev) return fail(2, "align_out_dev is NULL");
         if (J.K_mirror_dev && J.ldk_mirror < J.nx) return fail(2, "ldk_mirror is smaller than the block height");
+        if ((J.flags & B200SQ_GRAM_CRT) != (jobs[0].flags & B200SQ_GRAM_CRT)) return fail(2, "jobs of one launch must use one scheme");
     }
     int e = launch_gram_jobs((const int8_t*)planes_x_dev, expo_x_dev, plane_rows_x, dim, n_jobs, jobs,
                              (cudaStream_t)stream_);

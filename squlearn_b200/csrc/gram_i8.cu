@@ -21,6 +21,14 @@
 // so ONE B tile (digit plane of nat(y)) feeds two accumulators through two A tiles (digit planes of nat(x) and
 // rot(x)): the column operand only needs its 6 nat planes, which is what the multi-GPU exchange sends.
 //
+// SECOND SCHEME (B200SQ_GRAM_CRT, "Ozaki scheme II"): instead of 6 x 6 digit pairs, the integers
+// q = round(v * 2^(40 - e)) (41 bits per row scale) are reduced modulo s pairwise coprime odd numbers p_m <= 255
+// (s = 13 for K' = 2^17); one exact int8 x int8 -> int32 product per modulus gives the inner product mod p_m, and the
+// Chinese remainder theorem recovers the exact integer inner product (|.| < P / 2, P = prod p_m) in the epilogue
+// kernel with a double-double accumulation of k_m / p_m.  13 tensor-core products instead of 22 for the same
+// 1e-10 bound (the error is the 41-bit input quantisation only: no product terms are dropped).  Planes:
+// [2 s][rows][2 dim] int8, residues of nat(v) then of rot(v); W holds int32 residue sums per (tile, modulus).
+//
 // JOB TABLE.  One launch covers several Gram blocks ("jobs") that share the local row operand: job j multiplies
 // rows [x0, x0 + nx) of the local planes with rows [y0, y0 + ny) of its own column planes (the local planes for
 // the diagonal block, a received block otherwise) and writes its own K pointer.  A job may carry a READY FLAG:
@@ -39,6 +47,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -57,7 +66,13 @@ constexpr int kTileBytes = kTile * kStageK;      // 16 KiB
 constexpr int kStageBytes = 3 * kTileBytes;      // A, Bnat, Brot
 constexpr int kStages = 4;
 constexpr int kChunkK = 16384;                   // bytes of K per int32 accumulation chunk
-constexpr int kMaxClasses = 8, kMaxPairs = 8;
+constexpr int kMaxClasses = 16, kMaxPairs = 8;
+constexpr int kCrtBits = 40;                      // CRT scheme: q = round(v * 2^(kCrtBits - e))
+constexpr int kCrtMaxModuli = 16;
+// pairwise coprime odd moduli (255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
+// residues fit int8, and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
+__constant__ int c_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
+static const int h_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
 constexpr int kThreads = 256;
 
 struct I8Schedule {
@@ -97,6 +112,10 @@ struct I8Args {
     int n_chunks, chunk_bytes;
     int n_jobs, n_tiles;      // n_tiles: over all jobs
     int mn;                   // edge of an output tile: 128 (one CTA) or 256 (CTA pair)
+    int n_planes;             // nat planes per operand (rot planes follow): 6 digit slices, or s residue planes
+    int crt;                  // 1: CRT scheme (classes = moduli, W = int32 residue sums [n_tiles][s][2][mn][mn])
+    int crt_c[kCrtMaxModuli];    // (P / p_m)^-1 mod p_m
+    double crt_scale;            // P * 2^(-2 kCrtBits)
     double* W;                // [n_tiles][2][mn cols][mn rows]
     I8Schedule sched;
     I8Job jobs[kMaxJobs];
@@ -351,7 +370,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                 for (int ci = 0; ci < S.n_classes; ++ci)
                     for (int p = 0; p < S.n_pairs[ci]; ++p) {
                         const int row_an = (int)(S.pi[ci][p] * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
-                        const int row_ar = (int)((kSlices + S.pi[ci][p]) * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
+                        const int row_ar = (int)((A.n_planes + S.pi[ci][p]) * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
                         const int row_b = (int)(S.pj[ci][p] * J.rows_b + J.row0_b) + bn * MN + (int)cta_rank * kTile;
                         for (int k = k0; k < k1; k += kStageK) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -421,9 +440,12 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
             int tile, chunk;
             const int ji = decode_unit(A, u, tile, chunk);
             double* wt = A.W + (size_t)(A.jobs[ji].tile0 + tile) * (2 * MN * MN) + row;
+            int* wt32 = reinterpret_cast<int*>(A.W) + (size_t)(A.jobs[ji].tile0 + tile) * S.n_classes * (2 * MN * MN) + row;
             for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
                 const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                 const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
+                const int pm = c_crt_moduli[ci];
+                const double inv_pm = 1.0 / (double)pm;
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2u * MN);
@@ -432,11 +454,22 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                     uint32_t v[32];
                     tmem_ld32(t0 + cb * 32, v);
                     tmem_ld_wait();
-                    double* wp = wt + (size_t)(cb * 32) * MN;  // [part][col][row]
+                    if (A.crt) {
+                        // inner product of this K chunk modulo p_m (symmetric residue), summed over the chunks
+                        int* wp = wt32 + (size_t)ci * (2 * MN * MN) + (size_t)(cb * 32) * MN;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int iv = (int)v[c];
-                        if (iv != 0) red_add_f64(wp + (size_t)c * MN, (double)iv * w);
+                        for (int c = 0; c < 32; ++c) {
+                            const int iv = (int)v[c];
+                            const int r = iv - pm * __double2int_rn((double)iv * inv_pm);
+                            if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
+                        }
+                    } else {
+                        double* wp = wt + (size_t)(cb * 32) * MN;  // [part][col][row]
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int iv = (int)v[c];
+                            if (iv != 0) red_add_f64(wp + (size_t)c * MN, (double)iv * w);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -620,6 +653,187 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CRT scheme: residue planes.  planes: [2 s][n_rows][2 * dim] int8; plane m = nat(q) mod p_m (symmetric residues),
+// plane s + m = rot(q) mod p_m with rot = (-im, re), q = round(v * 2^(kCrtBits - e)).  The residue of an exact
+// integer q held in a double is q - p * rint(q / p): rint is exact because q / p is never within 1 / (2 p) of a
+// half-integer (p is odd) while the rounding error of q * (1 / p) is below 2^-11.
+
+__global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
+                                                   int64_t dim, int n_mod, int8_t* __restrict__ planes,
+                                                   int* __restrict__ expo, const uint32_t* __restrict__ row_max) {
+    const int64_t row = row0 + blockIdx.x;
+    const double2* src = psi + (int64_t)blockIdx.x * dim;
+    __shared__ double red[8];
+    __shared__ int s_e;
+    double m = 0.0;
+    if (row_max) {
+        m = __hiloint2double((int)row_max[blockIdx.x], 0);
+        if (row_max[blockIdx.x] != 0u && m == 0.0) m = 4.9e-324;
+    } else {
+        for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
+            const double2 v = src[i];
+            m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (!row_max)
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);
+        s_e = e;
+        expo[row] = e;
+    }
+    __syncthreads();
+    const double scale = ldexp(1.0, kCrtBits - s_e);
+    const size_t plane_stride = (size_t)plane_rows * 2 * dim;
+    int8_t* dst_row = planes + (size_t)row * 2 * dim;
+    for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
+        double q[16];   // (re, im) of 8 amplitudes as exact integers
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = __ldcs(src + i0 + c);
+            q[2 * c] = rint(v.x * scale);
+            q[2 * c + 1] = rint(v.y * scale);
+        }
+        for (int mi = 0; mi < n_mod; ++mi) {
+            const double pm = (double)c_crt_moduli[mi], inv = 1.0 / pm;
+            uint32_t wn[4] = {0, 0, 0, 0}, wr[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int rr = __double2int_rn(fma(-pm, rint(q[2 * c] * inv), q[2 * c]));
+                const int ri = __double2int_rn(fma(-pm, rint(q[2 * c + 1] * inv), q[2 * c + 1]));
+                const int b = 2 * c;   // byte positions b (re), b + 1 (im) of the 16-byte group
+                wn[b >> 2] |= ((uint32_t)rr & 255u) << (8 * (b & 3));
+                wn[(b + 1) >> 2] |= ((uint32_t)ri & 255u) << (8 * ((b + 1) & 3));
+                wr[b >> 2] |= ((uint32_t)(-ri) & 255u) << (8 * (b & 3));          // rot = (-im, re)
+                wr[(b + 1) >> 2] |= ((uint32_t)rr & 255u) << (8 * ((b + 1) & 3));
+            }
+            *reinterpret_cast<uint4*>(dst_row + (size_t)mi * plane_stride + 2 * i0) = make_uint4(wn[0], wn[1], wn[2], wn[3]);
+            *reinterpret_cast<uint4*>(dst_row + (size_t)(n_mod + mi) * plane_stride + 2 * i0) =
+                make_uint4(wr[0], wr[1], wr[2], wr[3]);
+        }
+    }
+}
+
+// CRT reconstruction: residues r_m of an integer x with |x| < P / 2  ->  x / P = frac(sum_m k_m / p_m) mapped to
+// (-1/2, 1/2], k_m = r_m c_m mod p_m, c_m = (P / p_m)^-1 mod p_m.  Every k_m / p_m is split into a double-double
+// (hi + lo) and the sum is accumulated error-free, so the result keeps full double precision although it is
+// ~2^-13 of the terms.
+__device__ __forceinline__ double crt_fraction(const int* __restrict__ w, size_t mod_stride, int n_mod,
+                                               const int* __restrict__ crt_c) {
+    double sh = 0.0, sl = 0.0;
+    for (int mi = 0; mi < n_mod; ++mi) {
+        const int pm = c_crt_moduli[mi];
+        const double pd = (double)pm, inv = 1.0 / pd;
+        int r = w[(size_t)mi * mod_stride];                        // sum of chunk residues: small
+        int k = (r % pm) * crt_c[mi] % pm;                         // |.| < p^2: fits
+        if (k < 0) k += pm;
+        const double kd = (double)k;
+        const double hi = kd * inv;
+        const double lo = fma(-hi, pd, kd) * inv;
+        const double t = sh + hi;
+        const double bb = t - sh;
+        sl += ((sh - (t - bb)) + (hi - bb)) + lo;
+        sh = t;
+    }
+    double f = (sh - rint(sh)) + sl;
+    if (f > 0.5) f -= 1.0;
+    if (f < -0.5) f += 1.0;
+    return f;
+}
+
+__global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ W, const __grid_constant__ I8Args A) {
+    __shared__ double sm[32][33];
+    __shared__ double s_red[2][8];
+    __shared__ int s_c[kCrtMaxModuli];
+    if (threadIdx.x < kCrtMaxModuli) s_c[threadIdx.x] = A.crt_c[threadIdx.x];
+    __syncthreads();
+    int ji = 0;
+    while (ji + 1 < A.n_jobs && (int)blockIdx.x >= A.jobs[ji].tile0 + A.jobs[ji].n_tiles) ++ji;
+    const I8Job& J = A.jobs[ji];
+    int bm, bn;
+    decode_tile(J, (int)blockIdx.x - J.tile0, bm, bn);
+    const int MN = A.mn, nsb = MN / 32, n_mod = A.sched.n_classes;
+    const size_t part = (size_t)MN * MN, mod_stride = 2 * part;
+    const int* wt = W + (size_t)blockIdx.x * n_mod * mod_stride;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t flags = J.flags;
+    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    const bool diag_tile = sym && bm == bn;
+    const int64_t nx = J.nx, ny = J.ny, ldk = J.ldk;
+    double* __restrict__ K = J.K;
+    double* __restrict__ Km = sym ? nullptr : J.K_mirror;
+    const int* __restrict__ ex = J.ex + J.row0_a;
+    const int* __restrict__ ey = J.ey + J.row0_b;
+    const double* __restrict__ ayx = J.align_yx;
+    const double* __restrict__ ayy = J.align_yy;
+    double a_ky = 0.0, a_kk = 0.0;
+    for (int sb = 0; sb < nsb * nsb; ++sb) {
+        const int sr = sb / nsb, sc = sb - sr * nsb;
+        if ((int64_t)bm * MN + sr * 32 >= nx || (int64_t)bn * MN + sc * 32 >= ny) continue;  // CTA-uniform
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+            const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+            double k = 0.0;
+            if (i < nx && j < ny) {
+                const int r2 = (diag_tile && col > row) ? col : row, c2 = (diag_tile && col > row) ? row : col;
+                const int* w0 = wt + (size_t)c2 * MN + r2;
+                const double re = crt_fraction(w0, mod_stride, n_mod, s_c) * A.crt_scale;
+                const double im = crt_fraction(w0 + part, mod_stride, n_mod, s_c) * A.crt_scale;
+                k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j]));
+                if (sym && i == j) {
+                    if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
+                    else if (flags & B200SQ_GRAM_DIAG_ZERO) k = 0.0;
+                }
+                if (ayx) {
+                    const double wgt = sym ? (bm != bn ? 2.0 : 1.0) : J.align_weight;
+                    a_ky = fma(wgt * k, ayx[i] * ayy[j], a_ky);
+                    a_kk = fma(wgt * k, k, a_kk);
+                }
+            }
+            sm[ty + 8 * qd][tx] = k;  // [col][row]
+        }
+        __syncthreads();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            {
+                const int row = sr * 32 + ty + 8 * qd, col = sc * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) K[i * ldk + j] = sm[tx][ty + 8 * qd];
+            }
+            if (sym && bm != bn) {
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) K[j * ldk + i] = sm[ty + 8 * qd][tx];
+            } else if (Km) {
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) Km[j * J.ldm + i] = sm[ty + 8 * qd][tx];
+            }
+        }
+        __syncthreads();
+    }
+    if (Km) __threadfence_system();
+    if (ayx) {
+        for (int o = 16; o > 0; o >>= 1) {
+            a_ky += __shfl_xor_sync(0xffffffffu, a_ky, o);
+            a_kk += __shfl_xor_sync(0xffffffffu, a_kk, o);
+        }
+        if (tx == 0) { s_red[0][ty] = a_ky; s_red[1][ty] = a_kk; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+            atomicAdd(J.align_out + threadIdx.x, t);
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -697,11 +911,39 @@ int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, 
     return (int)cudaGetLastError();
 }
 
+// Number of moduli of the CRT scheme for K' = 2 * dim int8 per row: the smallest s with
+// prod_{m < s} p_m > 2^(2 kCrtBits + 2) * K' (twice the largest possible |inner product|, with one bit to spare).
+int gram_crt_moduli(int64_t dim) {
+    double need = 2.0 * kCrtBits + 2.0 + log2((double)(2 * dim)), have = 0.0;
+    int s = 0;
+    while (s < kCrtMaxModuli && have < need) have += log2((double)h_crt_moduli[s++]);
+    return have >= need ? s : 0;
+}
+
+bool gram_crt_supported(int64_t dim) { return gram_i8_supported(dim) && gram_crt_moduli(dim) > 0; }
+
+int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
+                     int* expo, cudaStream_t stream, const uint32_t* row_max) {
+    if (n <= 0) return 0;
+    const int s = gram_crt_moduli(dim);
+    if (s <= 0) return (int)cudaErrorInvalidValue;
+    k_slice_crt<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, s, planes, expo, row_max);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x,
                    const uint32_t* row_max_y) {
     if (nx <= 0 || ny <= 0) return 0;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    const bool crt = (flags & B200SQ_GRAM_CRT) && gram_crt_supported(dim);
+    if (!crt) flags &= ~B200SQ_GRAM_CRT;
+    const int n_planes = crt ? gram_crt_moduli(dim) : kSlices;
+    auto slice = [&](const double2* psi, int64_t n, int8_t* planes, int* expo, const uint32_t* rm) {
+        return crt ? launch_slice_crt(psi, n, dim, planes, n, 0, expo, stream, rm)
+                   : launch_slice_i8(psi, n, dim, planes, n, 0, expo, stream, rm);
+    };
     const size_t plane_bytes = (size_t)(2 * dim);  // per row
     int8_t *px = nullptr, *py = nullptr;
     int *ex = nullptr, *ey = nullptr;
@@ -712,16 +954,16 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
         if (ex) cudaFreeAsync(ex, stream);
         if (ey && ey != ex) cudaFreeAsync(ey, stream);
     };
-    if ((e = cudaMallocAsync(&py, 2 * kSlices * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMallocAsync(&py, 2 * n_planes * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
     if ((e = cudaMallocAsync(&ey, ny * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-    launch_slice_i8(y, ny, dim, py, ny, 0, ey, stream, row_max_y);
+    slice(y, ny, py, ey, row_max_y);
     if (sym) {
         px = py;
         ex = ey;
     } else {
-        if ((e = cudaMallocAsync(&px, 2 * kSlices * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
+        if ((e = cudaMallocAsync(&px, 2 * n_planes * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
         if ((e = cudaMallocAsync(&ex, nx * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-        launch_slice_i8(x, nx, dim, px, nx, 0, ex, stream, row_max_x);
+        slice(x, nx, px, ex, row_max_x);
     }
     const int rc = launch_gram_planes(px, ex, nx, 0, nx, py, ey, ny, 0, ny, dim, k, ldk, flags, stream);
     cleanup();
@@ -770,6 +1012,14 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
     memset(&a, 0, sizeof(a));
     a.rows_a = rows_x;
     a.kbytes = (int)kbytes;
+    // one scheme per launch: digit slices (default) or CRT residues (B200SQ_GRAM_CRT on the jobs)
+    const bool crt = jobs[0].flags & B200SQ_GRAM_CRT;
+    for (int j = 1; j < n_jobs; ++j)
+        if (((jobs[j].flags & B200SQ_GRAM_CRT) != 0) != crt) return (int)cudaErrorInvalidValue;
+    const int n_mod = crt ? gram_crt_moduli(dim) : 0;
+    if (crt && n_mod <= 0) return (int)cudaErrorInvalidValue;
+    a.crt = crt ? 1 : 0;
+    a.n_planes = crt ? n_mod : kSlices;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -808,8 +1058,26 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
     }
     a.n_chunks = (int)n_chunks_of(a.chunk_bytes);
     a.mn = kTile * cg;
-    // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
-    {
+    if (crt) {
+        // one class per modulus: plane m x plane m; (P / p_m)^-1 mod p_m and P * 2^(-2 kCrtBits) for the epilogue
+        I8Schedule& s = a.sched;
+        s.n_classes = n_mod;
+        long double P = 1.0L;
+        for (int m = 0; m < n_mod; ++m) {
+            s.cls_shift[m] = 0;
+            s.n_pairs[m] = 1;
+            s.pi[m][0] = s.pj[m][0] = (uint8_t)m;
+            P *= (long double)h_crt_moduli[m];
+            int prod = 1;
+            for (int j = 0; j < n_mod; ++j)
+                if (j != m) prod = (prod * (h_crt_moduli[j] % h_crt_moduli[m])) % h_crt_moduli[m];
+            int inv = 1;
+            while ((prod * inv) % h_crt_moduli[m] != 1) ++inv;
+            a.crt_c[m] = inv;
+        }
+        a.crt_scale = (double)ldexpl(P, -2 * kCrtBits);
+    } else {
+        // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
         I8Schedule& s = a.sched;
         int nc = 0;
         s.cls_shift[nc] = 6;
@@ -831,7 +1099,7 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
     CUtensorMap mapA;
     I8Maps maps;
     memset(&maps, 0, sizeof(maps));
-    int rc = encode_planes(&mapA, (void*)px, (uint64_t)kbytes, (uint64_t)(2 * kSlices) * rows_x);
+    int rc = encode_planes(&mapA, (void*)px, (uint64_t)kbytes, (uint64_t)(2 * a.n_planes) * rows_x);
     if (rc) return rc;
     const void* map_base[kMaxJobs];
     int n_maps = 0;
@@ -869,13 +1137,14 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         if (m == n_maps) {
             map_base[n_maps++] = in.planes_y_dev;
             // only the nat planes of a column operand are read
-            rc = encode_planes(&maps.b[m], (void*)in.planes_y_dev, (uint64_t)kbytes, (uint64_t)kSlices * in.plane_rows_y);
+            rc = encode_planes(&maps.b[m], (void*)in.planes_y_dev, (uint64_t)kbytes, (uint64_t)a.n_planes * in.plane_rows_y);
             if (rc) return rc;
         }
         J.map_b = m;
         ++a.n_jobs;
     }
-    const size_t wbytes = (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
+    const size_t wbytes = crt ? (size_t)a.n_tiles * n_mod * 2 * a.mn * a.mn * sizeof(int)
+                              : (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
     if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
     a.W = W;
     cudaMemsetAsync(W, 0, wbytes, stream);
@@ -907,7 +1176,8 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         }
         count_launch();
     }
-    k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, a);
+    if (crt) k_gram_crt_final<<<a.n_tiles, 256, 0, stream>>>(reinterpret_cast<const int*>(W), a);
+    else k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, a);
     count_launch();
     e = cudaGetLastError();
     cleanup();

@@ -31,6 +31,10 @@ int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int6
 
 // Split-integer (INT8 tcgen05) Gram: see gram_i8.cu.  Falls back to nothing: callers check gram_i8_supported.
 bool gram_i8_supported(int64_t dim);
+bool gram_crt_supported(int64_t dim);
+int gram_crt_moduli(int64_t dim);   // residue planes per operand half of the CRT scheme (0: unsupported)
+int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
+                     int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr);
 int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream);
 unsigned int gram_ready_timeouts();   // jobs whose ready flag never arrived (synchronises the device)
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,

@@ -355,6 +355,8 @@ B200SQ_HD void stage_thread(const PassView& pv, const TeamMem& tm, const double2
     const uint32_t* __restrict__ jhi = tm.jt + 3 * tm.J;
     double2* __restrict__ tile = tm.tile;
     int j = 0;
+    // unrolled: the source loads of several elements are in flight together (the gather goes through L1 / L2)
+#pragma unroll 8
     for (uint32_t l = (uint32_t)tid; l < tile_elems; l += (uint32_t)TS, ++j) {
         double2 v{1.0, 0.0};
         if (has_src) {

@@ -230,6 +230,7 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
             double2* dp = dstate + (obase_out | map.out_lo);
             if (A.row_max) {
                 uint32_t hi = 0;
+#pragma unroll 8
                 for (int j = 0; j < J; ++j) {
                     const double2 v = tm.tile[smem_idx(j)];
                     __stcs(dp + tm.jt[J + j], v);
@@ -241,6 +242,7 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
                 if ((tid & 31) == 0)
                     atomicMax(A.row_max + ((int64_t)variant * A.dst_vstride + ic.sample - A.dst_off), hi);
             } else {
+#pragma unroll 8
                 for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], tm.tile[smem_idx(j)]);
             }
         }

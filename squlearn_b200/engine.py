@@ -276,8 +276,10 @@ class Engine:
         """K[i, j] = |<psi_x[i]|psi_y[j]>|^2.  ``psi_y=None`` means the symmetric Gram of psi_x;
         ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy.
         ``precision``: "fp64" (FP64 DMMA), "int8" (split-integer FP64 emulation on the INT8 tcgen05 tensor
-        cores, |dK| ~ 1e-12, north-star bound 1e-10) or "auto" (int8 where it is faster: 2^n >= 4096 and at
-        least 1024 x 512 entries); default from B200SQ_GRAM_PRECISION, else "auto"."""
+        cores: 22 digit-pair products, |dK| ~ 1e-12, north-star bound 1e-10), "crt" (the residue-number form of
+        the same idea: 13 products per entry at 2^16 amplitudes, CRT reconstruction, same bound) or "auto" (crt /
+        int8 where they are faster: 2^n >= 4096 and at least 1024 x 512 entries); default from
+        B200SQ_GRAM_PRECISION, else "auto"."""
         torch = self._torch
         rm_x = self._row_max_of(psi_x) if psi_x.is_contiguous() else None
         rm_y = rm_x if psi_y is None else (self._row_max_of(psi_y) if psi_y.is_contiguous() else None)
@@ -296,8 +298,9 @@ class Engine:
             flags |= _lib.GRAM_3M
             if os.environ.get("B200SQ_GRAM_MODE", "").lower() == "3m-classic" or three_m == "classic":
                 flags |= _lib.GRAM_CLASSIC
-        if self.gram_precision(nx, ny, dim, precision) == "int8":
-            flags |= _lib.GRAM_INT8
+        scheme = self.gram_precision(nx, ny, dim, precision)
+        if scheme in ("int8", "crt"):
+            flags |= _lib.GRAM_INT8 | (_lib.GRAM_CRT if scheme == "crt" else 0)
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
@@ -314,14 +317,25 @@ class Engine:
             return (torch.empty((12, plane_rows, 2 * dim), dtype=torch.int8, device=self.device),
                     torch.zeros((plane_rows,), dtype=torch.int32, device=self.device))
 
-    def alloc_plane_block(self, rows: int, dim: int):
-        """One contiguous int8 buffer holding the digit planes of ``rows`` states followed by their int32 row
-        exponents (a single message for the multi-GPU exchange).  Returns (buffer, planes view, expo view)."""
+    def plane_count(self, dim: int, scheme: str = "int8") -> int:
+        """Planes of ONE operand half (nat; the rot planes double it): 6 digit slices, or the CRT moduli."""
+        if scheme == "crt":
+            s = int(self._lib.b200sq_gram_crt_moduli(int(dim)))
+            if s <= 0:
+                raise ValueError("the CRT Gram does not support this state dimension")
+            return s
+        return 6
+
+    def alloc_plane_block(self, rows: int, dim: int, scheme: str = "int8"):
+        """One contiguous int8 buffer holding the planes of ``rows`` states ([2 s][rows][2 dim]: nat then rot;
+        s = 6 digit slices or the CRT moduli) followed by their int32 row exponents.  Returns (buffer, planes view,
+        expo view)."""
         torch = self._torch
-        nb = 12 * rows * 2 * dim
+        n_pl = 2 * self.plane_count(dim, scheme)
+        nb = n_pl * rows * 2 * dim
         with torch.cuda.device(self.device):
             buf = torch.empty((nb + 4 * rows,), dtype=torch.int8, device=self.device)
-        return buf, buf[:nb].view(12, rows, 2 * dim), buf[nb:].view(torch.int32)
+        return buf, buf[:nb].view(n_pl, rows, 2 * dim), buf[nb:].view(torch.int32)
 
     def alloc_bytes(self, nbytes: int):
         """Uninitialised int8 device buffer (exchange arenas and staging blocks of the multi-GPU Gram)."""
@@ -329,20 +343,23 @@ class Engine:
         with torch.cuda.device(self.device):
             return torch.empty((int(nbytes),), dtype=torch.int8, device=self.device)
 
-    def slice_states(self, psi, planes, expo, row0: int = 0):
-        """Write the digit planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes``."""
+    def slice_states(self, psi, planes, expo, row0: int = 0, scheme: Optional[str] = None):
+        """Write the planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes`` (digit slices, or
+        CRT residues when ``scheme == "crt"`` / the plane count says so)."""
         torch = self._torch
         rm = self._row_max_of(psi) if psi.is_contiguous() else None
         psi = psi.contiguous()
         if psi.dtype != torch.complex128 or psi.dim() != 2:
             raise ValueError("states must be a (N, 2^n) complex128 array")
+        if scheme is None:
+            scheme = "int8" if planes.shape[0] == 12 else "crt"
+        fn = self._lib.b200sq_gram_slice_crt if scheme == "crt" else self._lib.b200sq_gram_slice_rowmax
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.b200sq_gram_slice_rowmax(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(),
-                                                          planes.shape[1], int(row0), expo.data_ptr(),
-                                                          rm.data_ptr() if rm is not None else None, self._stream()))
+            _lib.check(fn(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(), planes.shape[1], int(row0),
+                          expo.data_ptr(), rm.data_ptr() if rm is not None else None, self._stream()))
 
     def gram_from_planes(self, planes_x, expo_x, x0: int, nx: int, planes_y=None, expo_y=None, y0: int = 0,
-                         ny: int = 0, diagonal: str = "one", out=None):
+                         ny: int = 0, diagonal: str = "one", out=None, scheme: Optional[str] = None):
         """Gram of rows [x0, x0 + nx) of planes_x against rows [y0, y0 + ny) of planes_y
         (``planes_y=None``: the symmetric Gram of the x rows)."""
         torch = self._torch
@@ -351,6 +368,10 @@ class Engine:
             planes_y, expo_y, y0, ny = planes_x, expo_x, x0, nx
         dim = planes_x.shape[2] // 2
         flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[diagonal]) if sym else 0
+        if scheme is None:
+            scheme = "int8" if planes_x.shape[0] == 12 else "crt"
+        if scheme == "crt":
+            flags |= _lib.GRAM_CRT
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((nx, ny), dtype=torch.float64, device=self.device)
@@ -371,9 +392,10 @@ class Engine:
         yd = self.to_device(y, torch.float64).reshape(-1)
         if yd.shape[0] != n:
             raise ValueError("labels and states differ in length")
-        if self.gram_precision(n, n, dim, precision) == "int8":
-            _, planes, expo = self.alloc_plane_block(n, dim)
-            self.slice_states(psi, planes, expo, 0)
+        scheme = self.gram_precision(n, n, dim, precision)
+        if scheme in ("int8", "crt"):
+            _, planes, expo = self.alloc_plane_block(n, dim, scheme)
+            self.slice_states(psi, planes, expo, 0, scheme)
             with torch.cuda.device(self.device):
                 k = torch.empty((n, n), dtype=torch.float64, device=self.device)
                 sums = torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -395,6 +417,7 @@ class Engine:
         ``mirror=(ptr, ld)`` (also store the transposed block there: the owner of the columns, maybe a peer)."""
         torch = self._torch
         ptr = lambda t: int(t) if isinstance(t, int) else t.data_ptr()
+        crt = planes_x.shape[0] != 12     # the row planes tell the scheme: 12 = digit slices, else 2 s CRT residue planes
         arr = (_lib.GramJob * max(len(jobs), 1))()
         for k, j in enumerate(jobs):
             out = j["out"]
@@ -408,6 +431,8 @@ class Engine:
             g.plane_rows_y = int(j["rows_y"])
             g.K_dev, g.ldk = out.data_ptr(), int(out.stride(0)) if out.shape[0] > 1 else max(int(out.stride(0)), out.shape[1])
             g.flags = (_lib.GRAM_SYMMETRIC | _DIAG_FLAGS[j.get("diagonal", "one")]) if j.get("symmetric") else 0
+            if crt:
+                g.flags |= _lib.GRAM_CRT
             if j.get("ready") is not None:
                 g.ready_flag_dev, g.ready_value = int(j["ready"][0]), int(j["ready"][1])
             if j.get("align") is not None:
@@ -459,15 +484,22 @@ class Engine:
 
     @staticmethod
     def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:
-        """Resolve the Gram arithmetic: "fp64" (DMMA) or "int8" (split-integer tcgen05 path)."""
+        """Resolve the Gram arithmetic: "fp64" (DMMA), "int8" (digit-slice tcgen05 path) or "crt" (residue-number
+        tcgen05 path: fewer products, more plane memory — 2 x 13 bytes per amplitude instead of 2 x 6)."""
         if precision is None:
             precision = os.environ.get("B200SQ_GRAM_PRECISION", "auto").lower()
-        if precision not in ("fp64", "int8", "auto"):
-            raise ValueError("precision must be 'fp64', 'int8' or 'auto'")
+        if precision not in ("fp64", "int8", "crt", "auto"):
+            raise ValueError("precision must be 'fp64', 'int8', 'crt' or 'auto'")
         if precision == "auto":
-            precision = "int8" if dim >= 4096 and nx * ny >= 1024 * 512 else "fp64"
-        if precision == "int8" and (dim < 64 or dim % 8):
+            if dim >= 4096 and nx * ny >= 1024 * 512:
+                # CRT while its planes (2 * 13 * 2 bytes per amplitude and operand) stay below ~48 GiB
+                precision = "crt" if 52.0 * dim * (nx + ny) < 48 * 2.0 ** 30 and dim <= 1 << 18 else "int8"
+            else:
+                precision = "fp64"
+        if precision in ("int8", "crt") and (dim < 64 or dim % 8):
             precision = "fp64"
+        if precision == "crt" and dim > 1 << 21:
+            precision = "int8"
         return precision
 
     def rbf(self, fx, fy, gamma: float):

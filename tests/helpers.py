@@ -119,3 +119,79 @@ def i8_gram(planes_x, expo_x, planes_y, expo_y):
         im += ai * 2.0 ** (-8 * c)
     scale = np.ldexp(1.0, 2 * (expo_x[:, None].astype(np.int64) + expo_y[None, :] - 12))
     return (re * re + im * im) * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# NumPy restatement of the CRT form of the split-integer Gram (csrc/gram_i8.cu, B200SQ_GRAM_CRT): residue planes of
+# q = round(v * 2^(40 - e)) modulo pairwise coprime odd p_m <= 255, one exact integer product per modulus, Chinese
+# remainder reconstruction with the kernel's double-double accumulation of k_m / p_m.
+CRT_BITS = 40
+CRT_MODULI = [255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191]
+
+
+def crt_num_moduli(dim):
+    need, have, s_ = 2.0 * CRT_BITS + 2.0 + np.log2(2.0 * dim), 0.0, 0
+    while s_ < len(CRT_MODULI) and have < need:
+        have += np.log2(float(CRT_MODULI[s_]))
+        s_ += 1
+    assert have >= need
+    return s_
+
+
+def _symres(q, p):
+    r = np.mod(q, p)
+    return np.where(r > (p - 1) // 2, r - p, r)
+
+
+def crt_slice(psi):
+    """(planes [2 s, N, 2 D] int8, expo [N] int32) like k_slice_crt."""
+    psi = np.asarray(psi, dtype=np.complex128)
+    n_rows, dim = psi.shape
+    s_ = crt_num_moduli(dim)
+    nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
+    m = np.abs(nat).max(axis=1)
+    expo = np.where(m > 0, np.frexp(m)[1], 0).astype(np.int32)
+    q = np.rint(np.ldexp(nat, (CRT_BITS - expo)[:, None])).astype(np.int64)
+    rot = np.empty_like(q)
+    rot[:, 0::2], rot[:, 1::2] = -q[:, 1::2], q[:, 0::2]
+    planes = np.zeros((2 * s_, n_rows, 2 * dim), dtype=np.int8)
+    for mi in range(s_):
+        planes[mi] = _symres(q, CRT_MODULI[mi]).astype(np.int8)
+        planes[s_ + mi] = _symres(rot, CRT_MODULI[mi]).astype(np.int8)
+    return planes, expo
+
+
+def crt_gram(planes_x, expo_x, planes_y, expo_y):
+    """|<x|y>|^2 from residue planes like k_gram_i8 (CRT classes) + k_gram_crt_final."""
+    s_ = planes_x.shape[0] // 2
+    mods = CRT_MODULI[:s_]
+    big = 1
+    for p in mods:
+        big *= p
+    from fractions import Fraction
+
+    scale = float(Fraction(big, 2 ** (2 * CRT_BITS)))
+    parts = []
+    for half in (0, s_):
+        sh = np.zeros((planes_x.shape[1], planes_y.shape[1]))
+        sl = np.zeros_like(sh)
+        for mi, p in enumerate(mods):
+            a = planes_x[half + mi].astype(np.int64)
+            b = planes_y[mi].astype(np.int64)
+            r = _symres(a @ b.T, p)
+            c = pow(big // p, -1, p)
+            k = np.mod(r * c, p).astype(np.float64)
+            inv = 1.0 / p
+            hi = k * inv
+            # fma(-hi, p, k) on the device; hi * p has at most 61 significant bits, so x87 long double is exact
+            lo = (k.astype(np.longdouble) - hi.astype(np.longdouble) * np.longdouble(p)).astype(np.float64) * inv
+            t = sh + hi
+            bb = t - sh
+            sl += ((sh - (t - bb)) + (hi - bb)) + lo
+            sh = t
+        f = (sh - np.rint(sh)) + sl
+        f = np.where(f > 0.5, f - 1.0, f)
+        f = np.where(f < -0.5, f + 1.0, f)
+        parts.append(f * scale)
+    re, im = parts
+    return (re * re + im * im) * np.ldexp(1.0, 2 * (expo_x[:, None].astype(np.int64) + expo_y[None, :]))

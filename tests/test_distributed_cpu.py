@@ -254,3 +254,23 @@ def test_sharded_parameter_shift_gloo(tmp_path, world):
                               [("summed_paulis", {}), ("single_pauli", {"qubit": 1, "op_str": "X"})],
                               np.linspace(0.2, 1.0, 5), ("dfdp",))["dfdp"]
     assert np.max(np.abs(want - ref)) < 1e-12
+
+
+def test_crt_scheme_error_on_circuit_states():
+    """NumPy restatement of the CRT (residue-number) form of the INT8 Gram against complex128: the only error is the
+    41-bit quantisation of the inputs (no product terms are dropped), and K is exactly symmetric."""
+    from tests.helpers import crt_gram, crt_num_moduli, crt_slice
+
+    assert [crt_num_moduli(1 << n) for n in (6, 12, 16, 20)] == [12, 13, 13, 14]
+    n = 10
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-0.95, 0.95, (40, 3))
+    p = oracle.chebyshev_pqc_initial_parameters(n, 2, 3, seed=0)
+    sv = oracle.simulate(oracle.chebyshev_pqc(n, 2, 3), n, X, p)
+    sv = np.concatenate([sv, sv[:2], np.eye(1, 2 ** n, 3, dtype=complex)])
+    planes, expo = crt_slice(sv)
+    assert planes.shape[0] == 24 and planes.min() >= -127 and planes.max() <= 127
+    got = crt_gram(planes, expo, planes, expo)
+    want = np.abs(sv.conj() @ sv.T) ** 2
+    assert np.max(np.abs(got - want)) < 5e-12
+    assert np.array_equal(got, got.T)

@@ -166,9 +166,10 @@ def test_gram_symmetric_and_diagonal_policies(executor, n, dim, three_m):
 INT8_TOL = 1e-10
 
 
+@pytest.mark.parametrize("scheme", ["int8", "crt"])
 @pytest.mark.parametrize("nx,ny,dim", [(1, 1, 64), (5, 3, 64), (37, 130, 128), (129, 65, 1024),
                                         (200, 260, 72), (64, 257, 4096), (700, 520, 16384)])
-def test_gram_int8_rectangular(executor, nx, ny, dim):
+def test_gram_int8_rectangular(executor, nx, ny, dim, scheme):
     import torch
 
     rng = np.random.default_rng(nx * 11 + ny)
@@ -176,14 +177,15 @@ def test_gram_int8_rectangular(executor, nx, ny, dim):
     b = rng.normal(size=(ny, dim)) + 1j * rng.normal(size=(ny, dim))
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
-    got = executor.engine.gram(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), precision="int8").cpu().numpy()
+    got = executor.engine.gram(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), precision=scheme).cpu().numpy()
     want = oracle.fidelity_gram_zgemm(a, b, False)
     assert got.shape == (nx, ny)
     assert np.max(np.abs(got - want)) < INT8_TOL
 
 
+@pytest.mark.parametrize("scheme", ["int8", "crt"])
 @pytest.mark.parametrize("n,dim", [(1, 64), (63, 128), (128, 256), (300, 512), (513, 64), (1100, 2048)])
-def test_gram_int8_symmetric_and_diagonal_policies(executor, n, dim):
+def test_gram_int8_symmetric_and_diagonal_policies(executor, n, dim, scheme):
     import torch
 
     rng = np.random.default_rng(n)
@@ -191,9 +193,9 @@ def test_gram_int8_symmetric_and_diagonal_policies(executor, n, dim):
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     t = torch.from_numpy(a).cuda()
     eng = executor.engine
-    k_one = eng.gram(t, None, diagonal="one", precision="int8").cpu().numpy()
-    k_zero = eng.gram(t, None, diagonal="zero", precision="int8").cpu().numpy()
-    k_cmp = eng.gram(t, None, diagonal="computed", precision="int8").cpu().numpy()
+    k_one = eng.gram(t, None, diagonal="one", precision=scheme).cpu().numpy()
+    k_zero = eng.gram(t, None, diagonal="zero", precision=scheme).cpu().numpy()
+    k_cmp = eng.gram(t, None, diagonal="computed", precision=scheme).cpu().numpy()
     want = oracle.fidelity_gram_zgemm(a, a, True, "off_diagonal")
     assert np.max(np.abs(k_one - want)) < INT8_TOL
     assert np.array_equal(k_one, k_one.T)                 # exactly symmetric (mirrored)
@@ -205,7 +207,8 @@ def test_gram_int8_symmetric_and_diagonal_policies(executor, n, dim):
         assert np.max(np.abs(k_one[off] - k_cmp[off])) < INT8_TOL
 
 
-def test_gram_int8_adversarial_states(executor):
+@pytest.mark.parametrize("scheme", ["int8", "crt"])
+def test_gram_int8_adversarial_states(executor, scheme):
     """Rows with very different scales: basis states (one amplitude of modulus 1), exact duplicates,
     near-duplicates, a uniform superposition and states with a few large and many tiny amplitudes."""
     import torch
@@ -228,7 +231,7 @@ def test_gram_int8_adversarial_states(executor):
         v = rng.normal(size=dim) * np.exp(rng.uniform(-6, 0, dim)) + 1j * rng.normal(size=dim)
         rows.append(v / np.linalg.norm(v))
     a = np.array(rows)
-    got = executor.engine.gram(torch.from_numpy(a).cuda(), None, diagonal="computed", precision="int8").cpu().numpy()
+    got = executor.engine.gram(torch.from_numpy(a).cuda(), None, diagonal="computed", precision=scheme).cpu().numpy()
     want = oracle.fidelity_gram_zgemm(a, a, True, "all")
     np.fill_diagonal(want, np.abs(np.einsum("ij,ij->i", a.conj(), a)) ** 2)
     assert np.max(np.abs(got - want)) < INT8_TOL
@@ -245,9 +248,19 @@ def test_gram_int8_matches_fp64_on_circuit_states(sq, executor):
     psi = _states(sq, executor, enc.get_program(d), p, X)
     t = torch.from_numpy(psi).cuda()
     k64 = executor.engine.gram(t, None, precision="fp64")
-    k8 = executor.engine.gram(t, None, precision="int8")
-    assert float((k64 - k8).abs().max()) < 2e-11
-    assert torch.equal(k8, k8.T)
+    for scheme in ("int8", "crt"):
+        k8 = executor.engine.gram(t, None, precision=scheme)
+        assert float((k64 - k8).abs().max()) < 2e-11, scheme
+        assert torch.equal(k8, k8.T)
+    # the digit planes of the CRT scheme equal the NumPy restatement bit for bit
+    from tests.helpers import crt_slice
+
+    eng = executor.engine
+    _, planes, expo = eng.alloc_plane_block(64, 1 << n, "crt")
+    eng.slice_states(t[:64].clone(), planes, expo, 0, "crt")
+    want_planes, want_expo = crt_slice(psi[:64])
+    assert np.array_equal(expo.cpu().numpy(), want_expo)
+    assert np.array_equal(planes.cpu().numpy(), want_planes)
 
 
 def test_row_maxima_from_the_gate_pass_feed_the_digit_slicing(sq, executor):
@@ -294,13 +307,14 @@ def test_config_c5_size_int8_gram_on_16_points(sq, executor):
     eng = executor.engine
     psi = eng.simulate(sq.B200Circuit(enc.get_program(d)).compiled(eng, p), X)
     err_sv = float(np.max(np.abs(psi.cpu().numpy() - want_sv)))
-    k8 = eng.gram(psi, None, diagonal="computed", precision="int8").cpu().numpy()
-    k8r = eng.gram(psi[:5], psi[3:], precision="int8").cpu().numpy()
     want = np.abs(want_sv.conj() @ want_sv.T) ** 2
-    err, err_r = float(np.max(np.abs(k8 - want))), float(np.max(np.abs(k8r - want[:5, 3:])))
-    print(f"C5-size (n=20) INT8 Gram on 16 points: |K - oracle| = {err:.2e} (rect {err_r:.2e}), states {err_sv:.2e}")
     assert err_sv < STATE_TOL
-    assert err < INT8_TOL and err_r < INT8_TOL
+    for scheme in ("int8", "crt"):
+        k8 = eng.gram(psi, None, diagonal="computed", precision=scheme).cpu().numpy()
+        k8r = eng.gram(psi[:5], psi[3:], precision=scheme).cpu().numpy()
+        err, err_r = float(np.max(np.abs(k8 - want))), float(np.max(np.abs(k8r - want[:5, 3:])))
+        print(f"C5-size (n=20) {scheme} Gram on 16 points: |K - oracle| = {err:.2e} (rect {err_r:.2e}), states {err_sv:.2e}")
+        assert err < INT8_TOL and err_r < INT8_TOL
 
 
 # ------------------------------------------------------------------------------ expectation values
@@ -464,7 +478,7 @@ def test_qnn_goldens_and_gradients(sq, executor, goldens, regression_data):
     single = qnn.evaluate(Xb[0], p, pop, "f")["f"]
     assert single.shape == (2,) and np.allclose(single, w["f"][0])
     with pytest.raises(NotImplementedError):
-        qnn.evaluate(Xb[:2], p, pop, "dfdxdx")
+        qnn.evaluate(Xb[:2], p, pop, "dfdxdxdp")      # third order in the circuit angles is not offered
 
 
 def test_optree_gradient_golden_through_the_product(sq, executor, goldens):
