@@ -400,9 +400,10 @@ def run_gpu_arm(args):
         del psi_chk
 
     line = None
-    dtype_str = ("f64 (complex128 states; Gram via exact int8 slices of a 47-bit fixed-point split, FP64 recombination)"
-                 if eng.gram_precision(n_points // world if multi else n_points, n_points, dim) == "int8"
-                 else "f64 (complex128)")
+    scheme = eng.gram_precision(n_points, n_points, dim)
+    dtype_str = {"int8": "f64 (complex128 states; Gram via exact int8 slices of a 47-bit fixed-point split, FP64 recombination)",
+                 "crt": "f64 (complex128 states; Gram via exact int8 residue products of a 41-bit fixed-point split, "
+                        "CRT reconstruction in double-double)"}.get(scheme, "f64 (complex128)")
     if rank == 0:
         assert k_host is not None and k_host.shape == (n_points, n_points)
         line = {
@@ -427,12 +428,12 @@ def run_gpu_arm(args):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
             except Exception:
                 pass
-            if eng.gram_precision(n_points, n_points, dim) == "int8":
+            if scheme in ("int8", "crt"):
                 mn = 256
                 tm = (n_points + mn - 1) // mn
                 tiles = tm * (tm + 1) // 2
                 entries_computed = tiles * mn * mn
-                pairs = 22
+                pairs = 22 if scheme == "int8" else eng.plane_count(dim, "crt")
                 ops = 2.0 * pairs * 2 * (2 * dim) * entries_computed  # int8 multiply-adds x 2
                 achieved = ops / (g_ms * 1e-3) / 1e12
                 bf16 = float(peaks.get("bf16_tflops", 1590.0))
@@ -446,10 +447,11 @@ def run_gpu_arm(args):
                 fp64_equiv = 8.0 * dim * (n_points * (n_points + 1) / 2) / (g_ms * 1e-3) / 1e12
                 line["roofline"] = {
                     "kernel": "k_gram_i8<2> (tcgen05.mma kind::i8 on CTA pairs, TMA operands, TMEM s32 accumulators) "
-                              "+ k_slice_i8 + k_gram_i8_final", "bound": "tensor",
+                              + ("+ k_slice_i8 + k_gram_i8_final" if scheme == "int8" else
+                                 "+ k_slice_crt + k_gram_crt_final (CRT reconstruction)"), "bound": "tensor",
                     "achieved": achieved, "peak": i8_peak, "unit": "TFLOP/s", "frac": achieved / i8_peak,
                     "traffic": traffic.get("k_gram_i8"), "ms_per_launch": g_ms,
-                    "algorithmic": f"split-integer FP64 emulation: {pairs} int8 slice pairs x 2 (Re, Im) x 2*2^n "
+                    "algorithmic": f"split-integer FP64 emulation ({'digit slices' if scheme == 'int8' else 'residues modulo ' + str(pairs) + ' coprime moduli'}): {pairs} int8 plane pairs x 2 (Re, Im) x 2*2^n "
                                    f"multiply-adds per entry x {entries_computed} entries computed ({tiles} "
                                    f"lower-triangle 256x256 tiles); the duration is the whole b200sq_gram call "
                                    f"(digit slicing, memset, tcgen05 kernel, |.|^2 kernel)",

@@ -216,6 +216,14 @@ B200SQ_API int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim
                                      int64_t plane_rows, int64_t row0, int32_t* expo_dev,
                                      const uint32_t* row_max_dev, void* stream);
 
+/* Residue planes of a COLUMN block from its 6 nat digit planes (what the multi-GPU exchange delivers: 6 instead of
+ * 13 bytes per component): rows [row0_d, row0_d + N) of digit planes [>= 6][plane_rows_d][2 * dim] ->
+ * rows [row0_o, row0_o + N) of residue planes [s][plane_rows_o][2 * dim] (nat residues only; the row exponents of
+ * the digit planes stay valid).                                                                          */
+B200SQ_API int b200sq_gram_digits_to_crt(const void* digit_planes_dev, int64_t plane_rows_d, int64_t row0_d, int64_t N,
+                                         int64_t dim, void* crt_planes_dev, int64_t plane_rows_o, int64_t row0_o,
+                                         void* stream);
+
 /* Several Gram blocks that share the row operand, in ONE persistent launch (the multi-GPU Gram: the diagonal
  * block of a rank plus every block it owns against received column planes; there is no reference counterpart,
  * the reference evaluates the pair loop of fidelity_kernel_statevector.py:358-383 on one host).

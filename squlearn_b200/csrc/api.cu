@@ -223,7 +223,7 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.xmask = p->d_masks;
         a.zmask = p->d_masks ? p->d_masks + n_terms : nullptr;
         a.out = out;
-        a.row_max = (a.dst == psi && psi && P.out_bits == pl.n) ? row_max : nullptr;
+        a.row_max = (last && a.dst == psi && psi && P.out_bits == pl.n) ? row_max : nullptr;  // the FINAL amplitudes only
         tile_pass_geometry(P, &a);
         a.total_items = n_states << P.n_obits;
         // Large batches run a kernel specialised for this pass at run time (compiled once per program);
@@ -499,6 +499,18 @@ int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* pla
     int e = launch_slice_crt((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
                              (cudaStream_t)stream_, row_max_dev);
     if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
+    return 0;
+}
+
+int b200sq_gram_digits_to_crt(const void* digit_planes_dev, int64_t plane_rows_d, int64_t row0_d, int64_t N,
+                              int64_t dim, void* crt_planes_dev, int64_t plane_rows_o, int64_t row0_o, void* stream_) {
+    if (!digit_planes_dev || !crt_planes_dev) return fail(2, "NULL argument");
+    if (N < 0 || row0_d < 0 || row0_o < 0 || row0_d + N > plane_rows_d || row0_o + N > plane_rows_o)
+        return fail(2, "rows outside the planes");
+    if (!gram_crt_supported(dim)) return fail(2, "the CRT Gram does not support this state dimension");
+    int e = launch_digits_to_crt((const int8_t*)digit_planes_dev, plane_rows_d, row0_d, N, dim, (int8_t*)crt_planes_dev,
+                                 plane_rows_o, row0_o, (cudaStream_t)stream_);
+    if (e) return cuda_fail(e, "digits-to-residues launch");
     return 0;
 }
 

@@ -260,12 +260,22 @@ __device__ __forceinline__ void decode_tile(const I8Job& A, int t, int& bm, int&
 
 // Work unit u -> (job, tile inside the job, K chunk).  Units are job-major (a job's column planes may still be
 // in flight: earlier jobs run first), chunk-major inside a job.
-__device__ __forceinline__ int decode_unit(const I8Args& A, int u, int& tile, int& chunk) {
+// The digit scheme runs all its weight classes inside a unit (c0 = 0, c1 = n_classes); the CRT scheme makes every
+// (tile, K chunk, modulus) a unit of its own (upc = n_classes units per tile and chunk, modulus-major so that the
+// workers of a wave read the same residue planes): a whole 128 KiB of K accumulates in TMEM before one drain.
+__device__ __forceinline__ int decode_unit(const I8Args& A, int u, int& tile, int& chunk, int& c0, int& c1) {
+    const int upc = A.crt ? A.sched.n_classes : 1;
+    const int per_tile = A.n_chunks * upc;
     int j = 0;
-    while (j + 1 < A.n_jobs && u >= (A.jobs[j].tile0 + A.jobs[j].n_tiles) * A.n_chunks) ++j;
-    const int ul = u - A.jobs[j].tile0 * A.n_chunks;
-    chunk = ul / A.jobs[j].n_tiles;
-    tile = ul - chunk * A.jobs[j].n_tiles;
+    while (j + 1 < A.n_jobs && u >= (A.jobs[j].tile0 + A.jobs[j].n_tiles) * per_tile) ++j;
+    int ul = u - A.jobs[j].tile0 * per_tile;
+    const int nt = A.jobs[j].n_tiles;
+    const int cls = ul / (A.n_chunks * nt);
+    ul -= cls * A.n_chunks * nt;
+    chunk = ul / nt;
+    tile = ul - chunk * nt;
+    c0 = A.crt ? cls : 0;
+    c1 = A.crt ? cls + 1 : A.sched.n_classes;
     return j;
 }
 
@@ -334,7 +344,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-    const int n_units = A.n_tiles * A.n_chunks;
+    const int n_units = A.n_tiles * A.n_chunks * (A.crt ? A.sched.n_classes : 1);
     const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
     const I8Schedule& S = A.sched;
 
@@ -345,8 +355,8 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
             uint32_t phase = 0;
             uint32_t ready_jobs = 0;   // jobs whose ready flag has been seen
             for (int u = worker; u < n_units; u += n_workers) {
-                int tile, chunk;
-                const int ji = decode_unit(A, u, tile, chunk);
+                int tile, chunk, c0, c1;
+                const int ji = decode_unit(A, u, tile, chunk, c0, c1);
                 const I8Job& J = A.jobs[ji];
                 if (J.ready && !(ready_jobs >> ji & 1u)) {
                     // column planes pushed by a peer's copy engine: wait for its flag, then order the TMA
@@ -367,7 +377,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                 decode_tile(J, tile, bm, bn);
                 const int k0 = chunk * A.chunk_bytes;
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
-                for (int ci = 0; ci < S.n_classes; ++ci)
+                for (int ci = c0; ci < c1; ++ci)
                     for (int p = 0; p < S.n_pairs[ci]; ++p) {
                         const int row_an = (int)(S.pi[ci][p] * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
                         const int row_ar = (int)((A.n_planes + S.pi[ci][p]) * A.rows_a + J.row0_a) + bm * MN + (int)cta_rank * kTile;
@@ -399,11 +409,11 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
             uint32_t phase = 0;
             uint32_t acc_it = 0;
             for (int u = worker; u < n_units; u += n_workers) {
-                int tile, chunk;
-                decode_unit(A, u, tile, chunk);
+                int tile, chunk, c0, c1;
+                decode_unit(A, u, tile, chunk, c0, c1);
                 const int k0 = chunk * A.chunk_bytes;
                 const int k1 = min(A.kbytes, k0 + A.chunk_bytes);
-                for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
+                for (int ci = c0; ci < c1; ++ci, ++acc_it) {
                     const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
@@ -437,11 +447,11 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
         const int row = (int)cta_rank * kTile + q * 32 + lane;
         uint32_t acc_it = 0;
         for (int u = worker; u < n_units; u += n_workers) {
-            int tile, chunk;
-            const int ji = decode_unit(A, u, tile, chunk);
+            int tile, chunk, c0, c1;
+            const int ji = decode_unit(A, u, tile, chunk, c0, c1);
             double* wt = A.W + (size_t)(A.jobs[ji].tile0 + tile) * (2 * MN * MN) + row;
             int* wt32 = reinterpret_cast<int*>(A.W) + (size_t)(A.jobs[ji].tile0 + tile) * S.n_classes * (2 * MN * MN) + row;
-            for (int ci = 0; ci < S.n_classes; ++ci, ++acc_it) {
+            for (int ci = c0; ci < c1; ++ci, ++acc_it) {
                 const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                 const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
                 const int pm = c_crt_moduli[ci];
@@ -455,13 +465,16 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                     tmem_ld32(t0 + cb * 32, v);
                     tmem_ld_wait();
                     if (A.crt) {
-                        // inner product of this K chunk modulo p_m (symmetric residue), summed over the chunks
+                        // inner product of this K chunk modulo p_m (symmetric residue): stored when the unit covers
+                        // the whole K (the usual case: 128 KiB of K stay exact in int32), else summed over the chunks
                         int* wp = wt32 + (size_t)ci * (2 * MN * MN) + (size_t)(cb * 32) * MN;
+                        const bool single = A.n_chunks == 1;
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int iv = (int)v[c];
                             const int r = iv - pm * __double2int_rn((double)iv * inv_pm);
-                            if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
+                            if (single) wp[(size_t)c * MN] = r;
+                            else if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
                         }
                     } else {
                         double* wp = wt + (size_t)(cb * 32) * MN;  // [part][col][row]
@@ -719,6 +732,45 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
     }
 }
 
+// Digit planes -> residue planes, for column blocks that arrive as digit planes (the multi-GPU exchange sends the
+// 6 nat digit planes: 6 instead of 13 bytes per component; the receiver derives the residues).  The 47-bit digits
+// hold q47 = round(v 2^(46 - e)); the CRT integer is q = round(q47 / 2^(46 - kCrtBits)) (half up), a valid
+// kCrtBits-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
+__global__ void __launch_bounds__(256) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
+                                                       int64_t kbytes, int n_mod, int8_t* __restrict__ out,
+                                                       int64_t rows_o, int64_t row0_o) {
+    const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
+    const int8_t* src = digits + (size_t)(row0_d + blockIdx.x) * kbytes;
+    int8_t* dst = out + (size_t)(row0_o + blockIdx.x) * kbytes;
+    constexpr int kDrop = kTopBits - kCrtBits;   // low bits of q47 that are rounded away
+    for (int64_t k0 = (int64_t)threadIdx.x * 16; k0 < kbytes; k0 += (int64_t)blockDim.x * 16) {
+        long long q47[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) q47[b] = 0;
+#pragma unroll
+        for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
+            const uint4 w = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)sl * stride_d + k0));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                q47[b] = q47[b] * 256 + (long long)(int8_t)((ww[b >> 2] >> (8 * (b & 3))) & 255u);
+        }
+        double q[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
+        for (int mi = 0; mi < n_mod; ++mi) {
+            const double pm = (double)c_crt_moduli[mi], inv = 1.0 / pm;
+            uint32_t wn[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const int r = __double2int_rn(fma(-pm, rint(q[b] * inv), q[b]));
+                wn[b >> 2] |= ((uint32_t)r & 255u) << (8 * (b & 3));
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)mi * stride_o + k0) = make_uint4(wn[0], wn[1], wn[2], wn[3]);
+        }
+    }
+}
+
 // CRT reconstruction: residues r_m of an integer x with |x| < P / 2  ->  x / P = frac(sum_m k_m / p_m) mapped to
 // (-1/2, 1/2], k_m = r_m c_m mod p_m, c_m = (P / p_m)^-1 mod p_m.  Every k_m / p_m is split into a double-double
 // (hi + lo) and the sum is accumulated error-free, so the result keeps full double precision although it is
@@ -932,6 +984,16 @@ int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes,
     return (int)cudaGetLastError();
 }
 
+int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, int64_t n, int64_t dim, int8_t* out,
+                         int64_t rows_o, int64_t row0_o, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const int s = gram_crt_moduli(dim);
+    if (s <= 0) return (int)cudaErrorInvalidValue;
+    k_digits_to_crt<<<(unsigned)n, 256, 0, stream>>>(digits, rows_d, row0_d, 2 * dim, s, out, rows_o, row0_o);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x,
                    const uint32_t* row_max_y) {
@@ -1039,13 +1101,16 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
     // cta_group::2) halve the L2 -> SMEM operand traffic per MMA but need enough units to fill the machine;
     // otherwise single CTAs with 128 x 128 tiles (TMEM double buffered) run.  The chunk is halved (down to 4 KiB)
     // while the last wave of the persistent workers would be less than ~85 % full.
-    int chunk_max = (int)(kbytes < kChunkK ? ((kbytes + kStageK - 1) / kStageK) * kStageK : kChunkK);
+    // (CRT: one plane pair per accumulator, so 128 KiB of K stay exact: 127^2 * 2^17 < 2^31)
+    const int chunk_cap = crt ? (1 << 17) : kChunkK;
+    int chunk_max = (int)(kbytes < chunk_cap ? ((kbytes + kStageK - 1) / kStageK) * kStageK : chunk_cap);
     auto n_chunks_of = [&](int cb) { return (kbytes + cb - 1) / cb; };
-    const int cg = force_cg ? force_cg : (count_tiles(256) * n_chunks_of(std::min(chunk_max, 4096)) >= sms / 2 ? 2 : 1);
+    const int cg = force_cg ? force_cg
+                            : (count_tiles(256) * (crt ? n_mod : 1) * n_chunks_of(std::min(chunk_max, 4096)) >= sms / 2 ? 2 : 1);
     const int workers_max = sms / cg;
     a.chunk_bytes = chunk_max;
     {
-        const int64_t tiles = count_tiles(kTile * cg);
+        const int64_t tiles = count_tiles(kTile * cg) * (crt ? n_mod : 1);
         auto efficiency = [&](int cb) {
             const int64_t units = tiles * n_chunks_of(cb);
             const int64_t waves = (units + workers_max - 1) / workers_max;
@@ -1054,7 +1119,7 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         while (a.chunk_bytes > 4096 && a.chunk_bytes / 2 >= kStageK && efficiency(a.chunk_bytes) < 0.85 &&
                efficiency(a.chunk_bytes / 2) > efficiency(a.chunk_bytes) + 0.02)
             a.chunk_bytes /= 2;
-        if (force_chunk >= kStageK && force_chunk <= kChunkK && force_chunk % kStageK == 0) a.chunk_bytes = force_chunk;
+        if (force_chunk >= kStageK && force_chunk <= chunk_cap && force_chunk % kStageK == 0) a.chunk_bytes = force_chunk;
     }
     a.n_chunks = (int)n_chunks_of(a.chunk_bytes);
     a.mn = kTile * cg;
@@ -1147,9 +1212,9 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
                               : (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
     if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
     a.W = W;
-    cudaMemsetAsync(W, 0, wbytes, stream);
+    if (!(crt && a.n_chunks == 1)) cudaMemsetAsync(W, 0, wbytes, stream);   // (whole-K CRT units store, they do not add)
     const int smem = kStages * kStageBytes + 1024 + 256;
-    const int n_units = a.n_tiles * a.n_chunks;
+    const int n_units = a.n_tiles * a.n_chunks * (crt ? n_mod : 1);
     {
         auto kern = cg == 2 ? k_gram_i8<2> : k_gram_i8<1>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) {

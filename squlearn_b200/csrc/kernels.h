@@ -36,6 +36,8 @@ int gram_crt_moduli(int64_t dim);   // residue planes per operand half of the CR
 int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
                      int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr);
 int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream);
+int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, int64_t n, int64_t dim, int8_t* out,
+                         int64_t rows_o, int64_t row0_o, cudaStream_t stream);
 unsigned int gram_ready_timeouts();   // jobs whose ready flag never arrived (synchronises the device)
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
                    int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x = nullptr,

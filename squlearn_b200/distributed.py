@@ -256,6 +256,12 @@ class ShardedFidelityKernel:
         nat_bytes = 6 * n_local * 2 * dim
         mode = self._exchange_mode(eng, equal, n_local, nat_bytes + 4 * n_local)
 
+        # Arithmetic of the blocks: digit slices ("int8") or residues ("crt": fewer tensor-core products).  Either
+        # way the 6 nat DIGIT planes travel (6 bytes per component; 13 residue planes would more than double the
+        # exchange): with "crt" every rank turns its own states into residue planes directly and each received block
+        # with digits_to_crt, on a side stream, as the block lands.
+        scheme = eng.gram_precision(parts[-1][1], parts[-1][1], dim, self.precision)
+        crt = scheme == "crt" and hasattr(eng, "digits_to_crt")
         buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
         if mode == "ipc":
             peer = self._peer_setup(eng, parts, jobs, dim)
@@ -268,11 +274,15 @@ class ShardedFidelityKernel:
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
         _mark("states")
         eng.slice_states(psi_local, planes, expo, 0)
+        a_planes, a_expo = planes, expo          # row operand of the Gram jobs
+        if crt:
+            _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
+            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt")
         del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
 
         glist = []
         if n_local:
-            glist.append({"x0": 0, "nx": n_local, "planes_y": planes, "expo_y": expo, "rows_y": n_local, "y0": 0,
+            glist.append({"x0": 0, "nx": n_local, "planes_y": a_planes, "expo_y": a_expo, "rows_y": n_local, "y0": 0,
                           "ny": n_local, "out": rows[:, r0:r1], "symmetric": True, "diagonal": self.diagonal})
         if mode == "ipc":
             peer["epoch"] += 1
@@ -347,6 +357,9 @@ class ShardedFidelityKernel:
             for req in reqs:
                 req.wait()
             _mark("exchange")
+        if crt and mine:
+            self._convert_blocks(eng, mine, dim, mode, peer if mode == "ipc" else None,
+                                 epoch_t if mode == "ipc" else None)
         for j in mine:
             ra, rb = j["rows"]
             w = j["cols"][1] - j["cols"][0]
@@ -355,7 +368,7 @@ class ShardedFidelityKernel:
                           "rows_y": j["rows_y"], "y0": j["y0"], "ny": w, "out": j["blk"], "ready": j["ready"],
                           "mirror": j.get("mirror")})
         if glist:
-            eng.gram_jobs(planes, expo, glist)
+            eng.gram_jobs(a_planes, a_expo, glist)
         if mode == "ipc" and store_mirror:
             # tell every owner that its mirrored blocks are stored; wait for the ranks that store into my rows
             for q in sorted({j["owner"] for j in mine}):
@@ -364,6 +377,39 @@ class ShardedFidelityKernel:
                 eng.wait_flags(arena.data_ptr() + peer["offs"]["done"], peer["writers"], epoch)
             return rows, None       # nothing left for the NCCL mirror exchange
         return rows, mine
+
+    def _convert_blocks(self, eng, mine, dim, mode, peer, epoch_t):
+        """CRT arithmetic: residue planes of every received digit block (b200sq_gram_digits_to_crt).  With the ipc
+        exchange the conversions run on their own stream, each behind a wait for its block's arrival flag and
+        followed by a flag of its own that the block's Gram job waits for — so a block is converted while earlier
+        blocks are multiplied and later ones are still in flight.  Otherwise (NCCL exchanges: all blocks are there)
+        they simply run in stream order."""
+        import torch
+
+        n_mod = eng.plane_count(dim, "crt")
+        ptr = lambda t: int(t) if isinstance(t, int) else t.data_ptr()
+        if mode == "ipc":
+            if "conv_flags" not in peer:
+                peer["conv_flags"] = torch.zeros(self.world, dtype=torch.int32, device=eng.device)
+                peer["conv_stream"] = torch.cuda.Stream(device=eng.device)
+            cs, cflags = peer["conv_stream"], peer["conv_flags"]
+            cs.wait_stream(torch.cuda.current_stream(eng.device))   # the epoch scalar, and last step's Gram is behind us
+            flags_ptr = peer["arena"].data_ptr() + peer["offs"]["flags"]
+        for j in mine:
+            w = j["cols"][1] - j["cols"][0]
+            conv = self._bytes(eng, ("conv", j["owner"], j["cols"]), n_mod * w * 2 * dim)
+            expo_ptr = ptr(j["expo_y"]) + 4 * j["y0"]
+            if mode == "ipc":
+                with torch.cuda.stream(cs):
+                    eng.wait_flags(flags_ptr, [j["owner"]], j["ready"][1])
+                    eng.digits_to_crt(j["planes_y"], j["rows_y"], j["y0"], w, dim, conv, w, 0)
+                    eng.copy_async(cflags.data_ptr() + 4 * j["owner"], epoch_t.data_ptr(), 4, cs)
+                j["ready"] = (cflags.data_ptr() + 4 * j["owner"], j["ready"][1])
+            else:
+                eng.digits_to_crt(j["planes_y"], j["rows_y"], j["y0"], w, dim, conv, w, 0)
+            j["planes_y"], j["expo_y"], j["rows_y"], j["y0"] = conv, expo_ptr, w, 0
+        if mode == "ipc":
+            epoch_t.record_stream(cs)
 
     def _rows_states(self, eng, x, parts, jobs, rows, dim):
         """The FP64 path: exchange only the statevector rows the jobs need (NCCL point-to-point over NVLink:
@@ -440,8 +486,8 @@ class ShardedFidelityKernel:
         jobs = gram_jobs(parts)
         n_local = r1 - r0
         dev = getattr(eng, "device", "cpu")
-        use_planes = (hasattr(eng, "gram_jobs")
-                      and eng.gram_precision(n, n, dim, self.precision) == "int8")  # same decision on every rank
+        use_planes = (hasattr(eng, "gram_jobs")      # same decision on every rank
+                      and eng.gram_precision(n, n, dim, self.precision) in ("int8", "crt"))
         if use_planes:
             rows, mine = self._rows_planes(eng, x, parts, jobs, dim)
         else:
@@ -488,7 +534,7 @@ class ShardedFidelityKernel:
         buf = self._bytes(eng, tag, nb + 4 * rows)
         return buf, buf[:nb].view(6, rows, 2 * dim), buf[nb:].view(torch.int32)
 
-    def _plane_block(self, eng, tag, rows: int, dim: int):
+    def _plane_block(self, eng, tag, rows: int, dim: int, scheme: str = "int8"):
         """Plane buffers are kept between calls (tens of GiB per rank at n = 20: re-allocating them every
         evaluation fragments the caching allocator at the edge of the 180 GB)."""
         key = (tag, rows, dim)
@@ -496,7 +542,8 @@ class ShardedFidelityKernel:
         if blk is None:
             for k in [k for k in self._blocks if isinstance(k, tuple) and k[0] == tag]:   # shape changed: drop the old one
                 del self._blocks[k]
-            blk = self._blocks[key] = eng.alloc_plane_block(rows, dim)
+            blk = self._blocks[key] = eng.alloc_plane_block(rows, dim, scheme) if scheme != "int8" \
+                else eng.alloc_plane_block(rows, dim)
         return blk
 
     def _global_rank(self, group_rank: int) -> int:

@@ -358,6 +358,14 @@ class Engine:
             _lib.check(fn(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(), planes.shape[1], int(row0),
                           expo.data_ptr(), rm.data_ptr() if rm is not None else None, self._stream()))
 
+    def digits_to_crt(self, digits, rows_d: int, row0_d: int, n: int, dim: int, out, rows_o: int, row0_o: int = 0):
+        """Residue planes ([s][rows_o][2 dim], nat only) of ``n`` rows of digit planes ([>= 6][rows_d][2 dim]); the
+        operands may be tensors or raw device pointers (received blocks of the multi-GPU exchange)."""
+        ptr = lambda t: int(t) if isinstance(t, int) else t.data_ptr()
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_gram_digits_to_crt(ptr(digits), int(rows_d), int(row0_d), int(n), int(dim),
+                                                           ptr(out), int(rows_o), int(row0_o), self._stream()))
+
     def gram_from_planes(self, planes_x, expo_x, x0: int, nx: int, planes_y=None, expo_y=None, y0: int = 0,
                          ny: int = 0, diagonal: str = "one", out=None, scheme: Optional[str] = None):
         """Gram of rows [x0, x0 + nx) of planes_x against rows [y0, y0 + ny) of planes_y
