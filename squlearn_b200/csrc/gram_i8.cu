@@ -774,22 +774,30 @@ __global__ void __launch_bounds__(256) k_digits_to_crt(const int8_t* __restrict_
 // CRT reconstruction: residues r_m of an integer x with |x| < P / 2  ->  x / P = frac(sum_m k_m / p_m) mapped to
 // (-1/2, 1/2], k_m = r_m c_m mod p_m, c_m = (P / p_m)^-1 mod p_m.  Every k_m / p_m is split into a double-double
 // (hi + lo) and the sum is accumulated error-free, so the result keeps full double precision although it is
-// ~2^-13 of the terms.
+// ~2^-13 of the terms.  The (hi, lo) pairs come from a shared-memory table indexed by (modulus, residue + 127),
+// built once per CTA: one table look-up and one error-free addition per modulus and entry.
+constexpr int kCrtTabStride = 256;   // residues -127 .. 127 (+ padding) per modulus
+
+__device__ __forceinline__ double2 crt_term(int r, int pm, int c) {
+    int k = (r % pm) * c % pm;
+    if (k < 0) k += pm;
+    const double pd = (double)pm, inv = 1.0 / pd, kd = (double)k;
+    const double hi = kd * inv;
+    return double2{hi, fma(-hi, pd, kd) * inv};
+}
+
 __device__ __forceinline__ double crt_fraction(const int* __restrict__ w, size_t mod_stride, int n_mod,
-                                               const int* __restrict__ crt_c) {
+                                               const int* __restrict__ crt_c, const double2* __restrict__ tab) {
     double sh = 0.0, sl = 0.0;
+#pragma unroll 4
     for (int mi = 0; mi < n_mod; ++mi) {
-        const int pm = c_crt_moduli[mi];
-        const double pd = (double)pm, inv = 1.0 / pd;
-        int r = w[(size_t)mi * mod_stride];                        // sum of chunk residues: small
-        int k = (r % pm) * crt_c[mi] % pm;                         // |.| < p^2: fits
-        if (k < 0) k += pm;
-        const double kd = (double)k;
-        const double hi = kd * inv;
-        const double lo = fma(-hi, pd, kd) * inv;
-        const double t = sh + hi;
+        const int r = w[(size_t)mi * mod_stride];
+        // a single K chunk stores symmetric residues (|r| <= 127): table; sums over chunks: reduce first
+        const double2 t2 = ((unsigned)(r + 127) < 255u) ? tab[mi * kCrtTabStride + r + 127]
+                                                        : crt_term(r, c_crt_moduli[mi], crt_c[mi]);
+        const double t = sh + t2.x;
         const double bb = t - sh;
-        sl += ((sh - (t - bb)) + (hi - bb)) + lo;
+        sl += ((sh - (t - bb)) + (t2.x - bb)) + t2.y;
         sh = t;
     }
     double f = (sh - rint(sh)) + sl;
@@ -802,7 +810,12 @@ __global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ 
     __shared__ double sm[32][33];
     __shared__ double s_red[2][8];
     __shared__ int s_c[kCrtMaxModuli];
+    extern __shared__ double2 s_tab[];   // [n_mod][kCrtTabStride]
     if (threadIdx.x < kCrtMaxModuli) s_c[threadIdx.x] = A.crt_c[threadIdx.x];
+    for (int t = threadIdx.x; t < A.sched.n_classes * kCrtTabStride; t += blockDim.x) {
+        const int mi = t / kCrtTabStride, r = t - mi * kCrtTabStride - 127;
+        s_tab[t] = crt_term(r, c_crt_moduli[mi], A.crt_c[mi]);
+    }
     __syncthreads();
     int ji = 0;
     while (ji + 1 < A.n_jobs && (int)blockIdx.x >= A.jobs[ji].tile0 + A.jobs[ji].n_tiles) ++ji;
@@ -824,7 +837,7 @@ __global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ 
     const double* __restrict__ ayx = J.align_yx;
     const double* __restrict__ ayy = J.align_yy;
     double a_ky = 0.0, a_kk = 0.0;
-    for (int sb = 0; sb < nsb * nsb; ++sb) {
+    for (int sb = blockIdx.y; sb < nsb * nsb; sb += gridDim.y) {   // a tile is shared by gridDim.y CTAs
         const int sr = sb / nsb, sc = sb - sr * nsb;
         if ((int64_t)bm * MN + sr * 32 >= nx || (int64_t)bn * MN + sc * 32 >= ny) continue;  // CTA-uniform
 #pragma unroll
@@ -835,8 +848,8 @@ __global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ 
             if (i < nx && j < ny) {
                 const int r2 = (diag_tile && col > row) ? col : row, c2 = (diag_tile && col > row) ? row : col;
                 const int* w0 = wt + (size_t)c2 * MN + r2;
-                const double re = crt_fraction(w0, mod_stride, n_mod, s_c) * A.crt_scale;
-                const double im = crt_fraction(w0 + part, mod_stride, n_mod, s_c) * A.crt_scale;
+                const double re = crt_fraction(w0, mod_stride, n_mod, s_c, s_tab) * A.crt_scale;
+                const double im = crt_fraction(w0 + part, mod_stride, n_mod, s_c, s_tab) * A.crt_scale;
                 k = ldexp(re * re + im * im, 2 * (ex[i] + ey[j]));
                 if (sym && i == j) {
                     if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
@@ -1241,7 +1254,16 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         }
         count_launch();
     }
-    if (crt) k_gram_crt_final<<<a.n_tiles, 256, 0, stream>>>(reinterpret_cast<const int*>(W), a);
+    if (crt) {
+        const int tab_bytes = n_mod * kCrtTabStride * (int)sizeof(double2);
+        if ((e = cudaFuncSetAttribute(k_gram_crt_final, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes)) != cudaSuccess) {
+            cleanup();
+            return (int)e;
+        }
+        const int split = a.mn == 256 ? 4 : 2;   // CTAs per tile: enough of them to fill the machine
+        k_gram_crt_final<<<dim3((unsigned)a.n_tiles, (unsigned)split), 256, tab_bytes, stream>>>(
+            reinterpret_cast<const int*>(W), a);
+    }
     else k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, a);
     count_launch();
     e = cudaGetLastError();
