@@ -274,16 +274,9 @@ class ShardedFidelityKernel:
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
         _mark("states")
         eng.slice_states(psi_local, planes, expo, 0)
-        a_planes, a_expo = planes, expo          # row operand of the Gram jobs
-        if crt:
-            _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
-            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt")
-        del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+        if not crt:
+            del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
 
-        glist = []
-        if n_local:
-            glist.append({"x0": 0, "nx": n_local, "planes_y": a_planes, "expo_y": a_expo, "rows_y": n_local, "y0": 0,
-                          "ny": n_local, "out": rows[:, r0:r1], "symmetric": True, "diagonal": self.diagonal})
         if mode == "ipc":
             peer["epoch"] += 1
             epoch = peer["epoch"]
@@ -357,6 +350,17 @@ class ShardedFidelityKernel:
             for req in reqs:
                 req.wait()
             _mark("exchange")
+        # row operand of the Gram jobs: the digit planes, or (CRT) the residue planes of the local states — sliced
+        # here, after the pushes are on their way, so that the exchange overlaps it
+        a_planes, a_expo = planes, expo
+        if crt:
+            _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
+            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt")
+            del psi_local
+        glist = []
+        if n_local:
+            glist.append({"x0": 0, "nx": n_local, "planes_y": a_planes, "expo_y": a_expo, "rows_y": n_local, "y0": 0,
+                          "ny": n_local, "out": rows[:, r0:r1], "symmetric": True, "diagonal": self.diagonal})
         if crt and mine:
             self._convert_blocks(eng, mine, dim, mode, peer if mode == "ipc" else None,
                                  epoch_t if mode == "ipc" else None)
