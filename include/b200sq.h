@@ -216,6 +216,14 @@ B200SQ_API int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim
                                      int64_t plane_rows, int64_t row0, int32_t* expo_dev,
                                      const uint32_t* row_max_dev, void* stream);
 
+/* b200sq_gram_slice_crt that also writes the 6 nat DIGIT planes ([6][digit_rows][2 * dim]: what the multi-GPU
+ * exchange sends) from the same read of the states; the residues are then those b200sq_gram_digits_to_crt derives
+ * from these digits, so sender and receivers hold identical integers for a state.                        */
+B200SQ_API int b200sq_gram_slice_crt_digits(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
+                                            int64_t plane_rows, int64_t row0, int32_t* expo_dev,
+                                            const uint32_t* row_max_dev, void* digit_planes_dev, int64_t digit_rows,
+                                            int64_t digit_row0, void* stream);
+
 /* Residue planes of a COLUMN block from its 6 nat digit planes (what the multi-GPU exchange delivers: 6 instead of
  * 13 bytes per component): rows [row0_d, row0_d + N) of digit planes [>= 6][plane_rows_d][2 * dim] ->
  * rows [row0_o, row0_o + N) of residue planes [s][plane_rows_o][2 * dim] (nat residues only; the row exponents of

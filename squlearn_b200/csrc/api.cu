@@ -493,11 +493,19 @@ int b200sq_gram_crt_moduli(int64_t dim) { return gram_crt_supported(dim) ? gram_
 
 int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
                           int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* stream_) {
+    return b200sq_gram_slice_crt_digits(psi_dev, N, dim, planes_dev, plane_rows, row0, expo_dev, row_max_dev, nullptr,
+                                        0, 0, stream_);
+}
+
+int b200sq_gram_slice_crt_digits(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
+                                 int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* digit_planes_dev,
+                                 int64_t digit_rows, int64_t digit_row0, void* stream_) {
     if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
     if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
+    if (digit_planes_dev && (digit_row0 < 0 || digit_row0 + N > digit_rows)) return fail(2, "rows outside the digit planes");
     if (!gram_crt_supported(dim)) return fail(2, "the CRT Gram does not support this state dimension");
     int e = launch_slice_crt((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
-                             (cudaStream_t)stream_, row_max_dev);
+                             (cudaStream_t)stream_, row_max_dev, (int8_t*)digit_planes_dev, digit_rows, digit_row0);
     if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
     return 0;
 }

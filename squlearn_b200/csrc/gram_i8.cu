@@ -72,6 +72,8 @@ constexpr int kCrtMaxModuli = 16;
 // pairwise coprime odd moduli (255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
 // residues fit int8, and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
 __constant__ int c_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
+__constant__ double c_crt_inv[kCrtMaxModuli] = {1.0 / 255, 1.0 / 253, 1.0 / 251, 1.0 / 247, 1.0 / 241, 1.0 / 239, 1.0 / 233, 1.0 / 229,
+                                                1.0 / 227, 1.0 / 223, 1.0 / 217, 1.0 / 211, 1.0 / 199, 1.0 / 197, 1.0 / 193, 1.0 / 191};
 static const int h_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
 constexpr int kThreads = 256;
 
@@ -455,7 +457,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                 const uint32_t acc = acc_it % ACC, acc_phase = (acc_it / ACC) & 1u;
                 const double w = __hiloint2double((1023 - 8 * S.cls_shift[ci]) << 20, 0);  // 2^(-8 c)
                 const int pm = c_crt_moduli[ci];
-                const double inv_pm = 1.0 / (double)pm;
+                const double inv_pm = c_crt_inv[ci];
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2u * MN);
@@ -672,9 +674,13 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
 // integer q held in a double is q - p * rint(q / p): rint is exact because q / p is never within 1 / (2 p) of a
 // half-integer (p is odd) while the rounding error of q * (1 / p) is below 2^-11.
 
+// `digits` (optional): also write the 6 nat DIGIT planes of the rows ([6][digit_rows][2 dim], what the multi-GPU
+// exchange sends) from the same read of the states; the residues are then taken from the integer a receiver
+// reconstructs from those digits (k_digits_to_crt), so every rank works with identical integers for a state.
 __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
                                                    int64_t dim, int n_mod, int8_t* __restrict__ planes,
-                                                   int* __restrict__ expo, const uint32_t* __restrict__ row_max) {
+                                                   int* __restrict__ expo, const uint32_t* __restrict__ row_max,
+                                                   int8_t* __restrict__ digits, int64_t digit_rows, int64_t digit_row0) {
     const int64_t row = row0 + blockIdx.x;
     const double2* src = psi + (int64_t)blockIdx.x * dim;
     __shared__ double red[8];
@@ -701,19 +707,41 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
         expo[row] = e;
     }
     __syncthreads();
-    const double scale = ldexp(1.0, kCrtBits - s_e);
+    const double scale = ldexp(1.0, kCrtBits - s_e), scale47 = ldexp(1.0, kTopBits - s_e);
     const size_t plane_stride = (size_t)plane_rows * 2 * dim;
     int8_t* dst_row = planes + (size_t)row * 2 * dim;
+    const size_t digit_stride = (size_t)digit_rows * 2 * dim;
+    int8_t* dig_row = digits ? digits + (size_t)(digit_row0 + blockIdx.x) * 2 * dim : nullptr;
+    constexpr int kDrop = kTopBits - kCrtBits;
     for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
         double q[16];   // (re, im) of 8 amplitudes as exact integers
+        if (digits) {
+            long long q47[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const double2 v = __ldcs(src + i0 + c);
-            q[2 * c] = rint(v.x * scale);
-            q[2 * c + 1] = rint(v.y * scale);
+            for (int c = 0; c < 8; ++c) {
+                const double2 v = __ldcs(src + i0 + c);
+                q47[2 * c] = __double2ll_rn(v.x * scale47);
+                q47[2 * c + 1] = __double2ll_rn(v.y * scale47);
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
+#pragma unroll
+            for (int sl = kSlices - 1; sl >= 0; --sl) {
+                uint32_t wd[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int b = 0; b < 16; ++b) wd[b >> 2] = pack_digit(q47[b], wd[b >> 2], b & 3);
+                *reinterpret_cast<uint4*>(dig_row + (size_t)sl * digit_stride + 2 * i0) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double2 v = __ldcs(src + i0 + c);
+                q[2 * c] = rint(v.x * scale);
+                q[2 * c + 1] = rint(v.y * scale);
+            }
         }
         for (int mi = 0; mi < n_mod; ++mi) {
-            const double pm = (double)c_crt_moduli[mi], inv = 1.0 / pm;
+            const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
             uint32_t wn[4] = {0, 0, 0, 0}, wr[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -759,7 +787,7 @@ __global__ void __launch_bounds__(256) k_digits_to_crt(const int8_t* __restrict_
 #pragma unroll
         for (int b = 0; b < 16; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
         for (int mi = 0; mi < n_mod; ++mi) {
-            const double pm = (double)c_crt_moduli[mi], inv = 1.0 / pm;
+            const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
             uint32_t wn[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int b = 0; b < 16; ++b) {
@@ -988,11 +1016,13 @@ int gram_crt_moduli(int64_t dim) {
 bool gram_crt_supported(int64_t dim) { return gram_i8_supported(dim) && gram_crt_moduli(dim) > 0; }
 
 int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                     int* expo, cudaStream_t stream, const uint32_t* row_max) {
+                     int* expo, cudaStream_t stream, const uint32_t* row_max, int8_t* digits, int64_t digit_rows,
+                     int64_t digit_row0) {
     if (n <= 0) return 0;
     const int s = gram_crt_moduli(dim);
     if (s <= 0) return (int)cudaErrorInvalidValue;
-    k_slice_crt<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, s, planes, expo, row_max);
+    k_slice_crt<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, s, planes, expo, row_max, digits,
+                                                 digit_rows, digit_row0);
     count_launch();
     return (int)cudaGetLastError();
 }

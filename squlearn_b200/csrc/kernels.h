@@ -34,7 +34,8 @@ bool gram_i8_supported(int64_t dim);
 bool gram_crt_supported(int64_t dim);
 int gram_crt_moduli(int64_t dim);   // residue planes per operand half of the CRT scheme (0: unsupported)
 int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                     int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr);
+                     int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr, int8_t* digits = nullptr,
+                     int64_t digit_rows = 0, int64_t digit_row0 = 0);
 int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream);
 int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, int64_t n, int64_t dim, int8_t* out,
                          int64_t rows_o, int64_t row0_o, cudaStream_t stream);

@@ -262,7 +262,12 @@ class ShardedFidelityKernel:
         # with digits_to_crt, on a side stream, as the block lands.
         scheme = eng.gram_precision(parts[-1][1], parts[-1][1], dim, self.precision)
         crt = scheme == "crt" and hasattr(eng, "digits_to_crt")
-        buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
+        if crt:   # residue planes for the local rows + their 6 nat digit planes for the exchange, from ONE read
+            buf_local, planes, expo = self._nat_block(eng, "local_nat", n_local, dim)
+            _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
+        else:
+            buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
+            a_planes, a_expo = planes, expo      # row operand of the Gram jobs
         if mode == "ipc":
             peer = self._peer_setup(eng, parts, jobs, dim)
             if peer["pushed"] is not None:   # my previous pushes read the local planes
@@ -273,9 +278,12 @@ class ShardedFidelityKernel:
                                if hasattr(eng, "device") else "cpu")
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
         _mark("states")
-        eng.slice_states(psi_local, planes, expo, 0)
-        if not crt:
-            del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+        if crt:
+            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt", digits=planes)
+            expo = a_expo
+        else:
+            eng.slice_states(psi_local, planes, expo, 0)
+        del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
 
         if mode == "ipc":
             peer["epoch"] += 1
@@ -317,7 +325,7 @@ class ShardedFidelityKernel:
             gathered = self._bytes(eng, "gathered", self.world * block)
             send = self._bytes(eng, "send", block)
             send[:nat_bytes].copy_(buf_local[:nat_bytes])
-            send[nat_bytes:].copy_(expo.view(torch.int8))
+            send[nat_bytes:].copy_(expo.contiguous().view(torch.int8))
             dist.all_gather_into_tensor(gathered, send, group=self.group)
             _mark("diag")
             _mark("exchange")
@@ -350,13 +358,6 @@ class ShardedFidelityKernel:
             for req in reqs:
                 req.wait()
             _mark("exchange")
-        # row operand of the Gram jobs: the digit planes, or (CRT) the residue planes of the local states — sliced
-        # here, after the pushes are on their way, so that the exchange overlaps it
-        a_planes, a_expo = planes, expo
-        if crt:
-            _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
-            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt")
-            del psi_local
         glist = []
         if n_local:
             glist.append({"x0": 0, "nx": n_local, "planes_y": a_planes, "expo_y": a_expo, "rows_y": n_local, "y0": 0,

@@ -343,9 +343,10 @@ class Engine:
         with torch.cuda.device(self.device):
             return torch.empty((int(nbytes),), dtype=torch.int8, device=self.device)
 
-    def slice_states(self, psi, planes, expo, row0: int = 0, scheme: Optional[str] = None):
+    def slice_states(self, psi, planes, expo, row0: int = 0, scheme: Optional[str] = None, digits=None):
         """Write the planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes`` (digit slices, or
-        CRT residues when ``scheme == "crt"`` / the plane count says so)."""
+        CRT residues when ``scheme == "crt"`` / the plane count says so).  ``digits`` (CRT only): a [6][N][2 dim]
+        int8 tensor that receives the nat digit planes of the same states (the multi-GPU exchange format)."""
         torch = self._torch
         rm = self._row_max_of(psi) if psi.is_contiguous() else None
         psi = psi.contiguous()
@@ -353,10 +354,17 @@ class Engine:
             raise ValueError("states must be a (N, 2^n) complex128 array")
         if scheme is None:
             scheme = "int8" if planes.shape[0] == 12 else "crt"
-        fn = self._lib.b200sq_gram_slice_crt if scheme == "crt" else self._lib.b200sq_gram_slice_rowmax
+        rmp = rm.data_ptr() if rm is not None else None
         with torch.cuda.device(self.device):
-            _lib.check(fn(psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(), planes.shape[1], int(row0),
-                          expo.data_ptr(), rm.data_ptr() if rm is not None else None, self._stream()))
+            if scheme == "crt":
+                _lib.check(self._lib.b200sq_gram_slice_crt_digits(
+                    psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(), planes.shape[1], int(row0),
+                    expo.data_ptr(), rmp, digits.data_ptr() if digits is not None else None,
+                    digits.shape[1] if digits is not None else 0, 0, self._stream()))
+            else:
+                _lib.check(self._lib.b200sq_gram_slice_rowmax(
+                    psi.data_ptr(), psi.shape[0], psi.shape[1], planes.data_ptr(), planes.shape[1], int(row0),
+                    expo.data_ptr(), rmp, self._stream()))
 
     def digits_to_crt(self, digits, rows_d: int, row0_d: int, n: int, dim: int, out, rows_o: int, row0_o: int = 0):
         """Residue planes ([s][rows_o][2 dim], nat only) of ``n`` rows of digit planes ([>= 6][rows_d][2 dim]); the
