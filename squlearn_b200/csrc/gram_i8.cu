@@ -764,38 +764,36 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 // 6 nat digit planes: 6 instead of 13 bytes per component; the receiver derives the residues).  The 47-bit digits
 // hold q47 = round(v 2^(46 - e)); the CRT integer is q = round(q47 / 2^(46 - kCrtBits)) (half up), a valid
 // kCrtBits-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
-__global__ void __launch_bounds__(256) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
-                                                       int64_t kbytes, int n_mod, int8_t* __restrict__ out,
-                                                       int64_t rows_o, int64_t row0_o) {
+// (The kernel runs NEXT TO the persistent Gram kernel, which keeps ~28 K registers and 198 KB of shared memory per SM:
+// four components per thread keep it below 48 registers so that several CTAs fit beside it.)
+__global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
+                                                          int64_t kbytes, int n_mod, int8_t* __restrict__ out,
+                                                          int64_t rows_o, int64_t row0_o) {
     const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
-    const int8_t* src = digits + (size_t)(row0_d + blockIdx.x) * kbytes;
-    int8_t* dst = out + (size_t)(row0_o + blockIdx.x) * kbytes;
+    const int8_t* src = digits + (size_t)(row0_d + blockIdx.y) * kbytes;
+    int8_t* dst = out + (size_t)(row0_o + blockIdx.y) * kbytes;
     constexpr int kDrop = kTopBits - kCrtBits;   // low bits of q47 that are rounded away
-    for (int64_t k0 = (int64_t)threadIdx.x * 16; k0 < kbytes; k0 += (int64_t)blockDim.x * 16) {
-        long long q47[16];
+    const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (k0 >= kbytes) return;
+    long long q47[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int b = 0; b < 16; ++b) q47[b] = 0;
+    for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
+        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(src + (size_t)sl * stride_d + k0));
 #pragma unroll
-        for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
-            const uint4 w = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)sl * stride_d + k0));
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        for (int b = 0; b < 4; ++b) q47[b] = q47[b] * 256 + (long long)(int8_t)((w >> (8 * b)) & 255u);
+    }
+    double q[4];
 #pragma unroll
-            for (int b = 0; b < 16; ++b)
-                q47[b] = q47[b] * 256 + (long long)(int8_t)((ww[b >> 2] >> (8 * (b & 3))) & 255u);
+    for (int b = 0; b < 4; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
+    for (int mi = 0; mi < n_mod; ++mi) {
+        const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
+        uint32_t wn = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = __double2int_rn(fma(-pm, rint(q[b] * inv), q[b]));
+            wn |= ((uint32_t)r & 255u) << (8 * b);
         }
-        double q[16];
-#pragma unroll
-        for (int b = 0; b < 16; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
-        for (int mi = 0; mi < n_mod; ++mi) {
-            const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
-            uint32_t wn[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const int r = __double2int_rn(fma(-pm, rint(q[b] * inv), q[b]));
-                wn[b >> 2] |= ((uint32_t)r & 255u) << (8 * (b & 3));
-            }
-            *reinterpret_cast<uint4*>(dst + (size_t)mi * stride_o + k0) = make_uint4(wn[0], wn[1], wn[2], wn[3]);
-        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)mi * stride_o + k0) = wn;
     }
 }
 
@@ -1032,7 +1030,9 @@ int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, i
     if (n <= 0) return 0;
     const int s = gram_crt_moduli(dim);
     if (s <= 0) return (int)cudaErrorInvalidValue;
-    k_digits_to_crt<<<(unsigned)n, 256, 0, stream>>>(digits, rows_d, row0_d, 2 * dim, s, out, rows_o, row0_o);
+    const int64_t kbytes = 2 * dim;
+    const dim3 grid((unsigned)((kbytes / 4 + 255) / 256), (unsigned)n);
+    k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, s, out, rows_o, row0_o);
     count_launch();
     return (int)cudaGetLastError();
 }

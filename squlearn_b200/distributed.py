@@ -396,7 +396,7 @@ class ShardedFidelityKernel:
         if mode == "ipc":
             if "conv_flags" not in peer:
                 peer["conv_flags"] = torch.zeros(self.world, dtype=torch.int32, device=eng.device)
-                peer["conv_stream"] = torch.cuda.Stream(device=eng.device)
+                peer["conv_stream"] = torch.cuda.Stream(device=eng.device, priority=-1)   # ahead of the Gram's CTAs
             cs, cflags = peer["conv_stream"], peer["conv_flags"]
             cs.wait_stream(torch.cuda.current_stream(eng.device))   # the epoch scalar, and last step's Gram is behind us
             flags_ptr = peer["arena"].data_ptr() + peer["offs"]["flags"]
