@@ -668,6 +668,18 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
     }
 }
 
+// Symmetric residue of an exact integer q held in a double, modulo the odd p, WITHOUT conversion instructions (FRND /
+// F2I on 64-bit types run at a quarter of the FP64 rate): with M = 1.5 * 2^52, fma(q, 1/p, M) - M is q / p rounded
+// to the nearest integer k (exactly: q / p is never within 1 / (2 p) of a half-integer, the product's error is
+// < 2^-11), and fma(-p, k, q + M) = M + r exactly, whose low 32 bits are r in two's complement.  qm = q + M.
+constexpr double kRoundMagic = 6755399441055744.0;   // 1.5 * 2^52
+__device__ __forceinline__ int crt_residue(double q, double qm, double pm, double inv) {
+    const double k = fma(q, inv, kRoundMagic) - kRoundMagic;
+    return __double2loint(fma(-pm, k, qm));
+}
+// round to nearest (ties to even) without FRND: |x| < 2^51
+__device__ __forceinline__ double magic_rint(double x) { return (x + kRoundMagic) - kRoundMagic; }
+
 // ---------------------------------------------------------------------------------------------
 // CRT scheme: residue planes.  planes: [2 s][n_rows][2 * dim] int8; plane m = nat(q) mod p_m (symmetric residues),
 // plane s + m = rot(q) mod p_m with rot = (-im, re), q = round(v * 2^(kCrtBits - e)).  The residue of an exact
@@ -712,7 +724,7 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
     int8_t* dst_row = planes + (size_t)row * 2 * dim;
     const size_t digit_stride = (size_t)digit_rows * 2 * dim;
     int8_t* dig_row = digits ? digits + (size_t)(digit_row0 + blockIdx.x) * 2 * dim : nullptr;
-    constexpr int kDrop = kTopBits - kCrtBits;
+    const double drop = ldexp(1.0, -(kTopBits - kCrtBits));
     for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
         double q[16];   // (re, im) of 8 amplitudes as exact integers
         if (digits) {
@@ -720,11 +732,14 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double2 v = __ldcs(src + i0 + c);
-                q47[2 * c] = __double2ll_rn(v.x * scale47);
-                q47[2 * c + 1] = __double2ll_rn(v.y * scale47);
+                const double a = magic_rint(v.x * scale47), b = magic_rint(v.y * scale47);
+                q47[2 * c] = (long long)a;
+                q47[2 * c + 1] = (long long)b;
+                // the CRT integer is the digit integer rounded to kCrtBits (ties to even), exactly what a receiver
+                // derives from the digits (k_digits_to_crt)
+                q[2 * c] = magic_rint(a * drop);
+                q[2 * c + 1] = magic_rint(b * drop);
             }
-#pragma unroll
-            for (int b = 0; b < 16; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
 #pragma unroll
             for (int sl = kSlices - 1; sl >= 0; --sl) {
                 uint32_t wd[4] = {0, 0, 0, 0};
@@ -736,17 +751,20 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double2 v = __ldcs(src + i0 + c);
-                q[2 * c] = rint(v.x * scale);
-                q[2 * c + 1] = rint(v.y * scale);
+                q[2 * c] = magic_rint(v.x * scale);
+                q[2 * c + 1] = magic_rint(v.y * scale);
             }
         }
+        double qm[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) qm[b] = q[b] + kRoundMagic;
         for (int mi = 0; mi < n_mod; ++mi) {
             const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
             uint32_t wn[4] = {0, 0, 0, 0}, wr[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int rr = __double2int_rn(fma(-pm, rint(q[2 * c] * inv), q[2 * c]));
-                const int ri = __double2int_rn(fma(-pm, rint(q[2 * c + 1] * inv), q[2 * c + 1]));
+                const int rr = crt_residue(q[2 * c], qm[2 * c], pm, inv);
+                const int ri = crt_residue(q[2 * c + 1], qm[2 * c + 1], pm, inv);
                 const int b = 2 * c;   // byte positions b (re), b + 1 (im) of the 16-byte group
                 wn[b >> 2] |= ((uint32_t)rr & 255u) << (8 * (b & 3));
                 wn[(b + 1) >> 2] |= ((uint32_t)ri & 255u) << (8 * ((b + 1) & 3));
@@ -762,7 +780,7 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 
 // Digit planes -> residue planes, for column blocks that arrive as digit planes (the multi-GPU exchange sends the
 // 6 nat digit planes: 6 instead of 13 bytes per component; the receiver derives the residues).  The 47-bit digits
-// hold q47 = round(v 2^(46 - e)); the CRT integer is q = round(q47 / 2^(46 - kCrtBits)) (half up), a valid
+// hold q47 = round(v 2^(46 - e)); the CRT integer is q = round(q47 / 2^(46 - kCrtBits)) (ties to even), a valid
 // kCrtBits-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
 // (The kernel runs NEXT TO the persistent Gram kernel, which keeps ~28 K registers and 198 KB of shared memory per SM:
 // four components per thread keep it below 48 registers so that several CTAs fit beside it.)
@@ -772,25 +790,33 @@ __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restri
     const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
     const int8_t* src = digits + (size_t)(row0_d + blockIdx.y) * kbytes;
     int8_t* dst = out + (size_t)(row0_o + blockIdx.y) * kbytes;
-    constexpr int kDrop = kTopBits - kCrtBits;   // low bits of q47 that are rounded away
     const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (k0 >= kbytes) return;
-    long long q47[4] = {0, 0, 0, 0};
+    // the 47-bit digit integer from two 24-bit halves (int32 arithmetic), then rounded to kCrtBits (ties to even)
+    int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
         const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(src + (size_t)sl * stride_d + k0));
 #pragma unroll
-        for (int b = 0; b < 4; ++b) q47[b] = q47[b] * 256 + (long long)(int8_t)((w >> (8 * b)) & 255u);
+        for (int b = 0; b < 4; ++b) {
+            const int d = (int)(int8_t)((w >> (8 * b)) & 255u);
+            if (sl < 3) hi[b] = hi[b] * 256 + d;
+            else lo[b] = lo[b] * 256 + d;
+        }
     }
-    double q[4];
+    const double drop = ldexp(1.0, -(kTopBits - kCrtBits));
+    double q[4], qm[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) q[b] = (double)((q47[b] + (1ll << (kDrop - 1))) >> kDrop);
+    for (int b = 0; b < 4; ++b) {
+        q[b] = magic_rint(fma((double)hi[b], 16777216.0, (double)lo[b]) * drop);
+        qm[b] = q[b] + kRoundMagic;
+    }
     for (int mi = 0; mi < n_mod; ++mi) {
         const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
         uint32_t wn = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int r = __double2int_rn(fma(-pm, rint(q[b] * inv), q[b]));
+            const int r = crt_residue(q[b], qm[b], pm, inv);
             wn |= ((uint32_t)r & 255u) << (8 * b);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)mi * stride_o + k0) = wn;

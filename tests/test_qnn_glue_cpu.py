@@ -76,4 +76,4 @@ def test_dfdx_shapes_multi_output_and_linear_encoding():
     single = qnn.evaluate(X[0], p, [], "dfdx")["dfdx"]
     assert single.shape == (2, d) and np.allclose(single, r["dfdx"][0])
     with pytest.raises(NotImplementedError):
-        qnn.evaluate(X, p, [], "dfdxdx")
+        qnn.evaluate(X, p, [], "dfdxdxdp")
