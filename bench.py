@@ -402,8 +402,8 @@ def run_gpu_arm(args):
     line = None
     scheme = eng.gram_precision(n_points, n_points, dim)
     dtype_str = {"int8": "f64 (complex128 states; Gram via exact int8 slices of a 47-bit fixed-point split, FP64 recombination)",
-                 "crt": "f64 (complex128 states; Gram via exact int8 residue products of a 41-bit fixed-point split, "
-                        "CRT reconstruction in double-double)"}.get(scheme, "f64 (complex128)")
+                 "crt": "f64 (complex128 states; Gram via exact int8 residue products of a 44-bit fixed-point split "
+                        "relative to the row norm, CRT reconstruction in double-double)"}.get(scheme, "f64 (complex128)")
     if rank == 0:
         assert k_host is not None and k_host.shape == (n_points, n_points)
         line = {

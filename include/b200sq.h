@@ -36,7 +36,7 @@ extern "C" {
 #define B200SQ_API
 #endif
 
-#define B200SQ_ABI_VERSION 2
+#define B200SQ_ABI_VERSION 3
 #define B200SQ_MAX_QUBITS 26
 
 /* Gate vocabulary = the reference's gate table
@@ -139,14 +139,22 @@ B200SQ_API int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const dou
                     const double* angle_table_dev, int n_variants, const int32_t* var_gate,
                     const double* var_shift, void* psi_dev, void* stream);
 
-/* b200sq_simulate that also reduces, per output state, the maximum of the HIGH 32-bit words of max(|re|, |im|)
- * into row_max_dev [n_variants][N] uint32 (zeroed here, atomicMax from the last gate pass's store epilogue): the
- * power-of-two row scale the INT8 Gram's digit slicing needs, so that b200sq_gram_rowmax / b200sq_gram_slice_rowmax
- * read the states once instead of twice.  The maxima describe psi as written by this call: pass them only with
+/* Per-state statistics of a batch of states, reduced by the store epilogue of the last gate pass (atomicMax /
+ * atomicAdd; zeroed by b200sq_simulate_rowmax): max_hi = the HIGH 32-bit word of max(|re|, |im|) over the row (it
+ * holds the exponent: the power-of-two row scale of the digit slicing), norm2 = sum |amplitude|^2 (the row scale of
+ * the CRT slicing comes from the 2-norm).  All-zero statistics mean "not available".                     */
+typedef struct b200sq_row_stats {
+    double norm2;
+    uint32_t max_hi;
+    uint32_t reserved;
+} b200sq_row_stats;
+
+/* b200sq_simulate that also fills row_stats_dev [n_variants][N], so that b200sq_gram_rowmax / b200sq_gram_slice_*
+ * read the states once instead of twice.  The statistics describe psi as written by this call: pass them only with
  * those very states.                                                                                  */
 B200SQ_API int b200sq_simulate_rowmax(b200sq_program* prog, int64_t N, int d, const double* x_dev,
                                       const double* angle_table_dev, int n_variants, const int32_t* var_gate,
-                                      const double* var_shift, void* psi_dev, uint32_t* row_max_dev, void* stream);
+                                      const double* var_shift, void* psi_dev, b200sq_row_stats* row_stats_dev, void* stream);
 
 /* Simulate and reduce to Pauli expectation values without keeping the states when the state
  * fits one tile (n <= tile_bits); otherwise states go through `workspace_dev`.
@@ -183,11 +191,11 @@ B200SQ_API int b200sq_expvals(const void* psi_dev, int64_t N, int n_qubits, int 
 B200SQ_API int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
                 double* K_dev, int64_t ldk, uint32_t flags, void* stream);
 
-/* b200sq_gram with the row maxima b200sq_simulate_rowmax produced for psi_x / psi_y (either may be NULL; only the
- * INT8 path uses them).                                                                                 */
+/* b200sq_gram with the row statistics b200sq_simulate_rowmax produced for psi_x / psi_y (either may be NULL; only
+ * the INT8 paths use them).                                                                                 */
 B200SQ_API int b200sq_gram_rowmax(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
-                                  double* K_dev, int64_t ldk, uint32_t flags, const uint32_t* row_max_x_dev,
-                                  const uint32_t* row_max_y_dev, void* stream);
+                                  double* K_dev, int64_t ldk, uint32_t flags, const b200sq_row_stats* row_stats_x_dev,
+                                  const b200sq_row_stats* row_stats_y_dev, void* stream);
 
 /* The two halves of the B200SQ_GRAM_INT8 path, for callers that reuse or exchange the digit planes (the
  * multi-GPU Gram sends planes, not complex128 states: 12 instead of 16 bytes per amplitude, sliced once).
@@ -202,7 +210,7 @@ B200SQ_API int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, vo
                                  int64_t row0, int32_t* expo_dev, void* stream);
 B200SQ_API int b200sq_gram_slice_rowmax(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
                                         int64_t plane_rows, int64_t row0, int32_t* expo_dev,
-                                        const uint32_t* row_max_dev, void* stream);
+                                        const b200sq_row_stats* row_stats_dev, void* stream);
 B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* expo_x_dev, int64_t plane_rows_x,
                                        int64_t x0, int64_t Nx, const void* planes_y_dev, const int32_t* expo_y_dev,
                                        int64_t plane_rows_y, int64_t y0, int64_t Ny, int64_t dim, double* K_dev,
@@ -210,22 +218,26 @@ B200SQ_API int b200sq_gram_from_planes(const void* planes_x_dev, const int32_t* 
 
 /* CRT form of the plane interface (B200SQ_GRAM_CRT): planes are [2 s][plane_rows][2 * dim] int8 with
  * s = b200sq_gram_crt_moduli(dim) residue planes of nat followed by s of rot (column operands: the first s);
- * b200sq_gram_from_planes / b200sq_gram_jobs take such planes when B200SQ_GRAM_CRT is set in the (job) flags. */
+ * b200sq_gram_from_planes / b200sq_gram_jobs take such planes when B200SQ_GRAM_CRT is set in the (job) flags.
+ * A row is quantised as round(v * 2^(B - e)) with B = b200sq_gram_crt_bits(dim) and e (expo) the smallest integer
+ * that keeps 2^(B - e) |row|_2 below sqrt(P / 2), P the product of the s moduli; s is the smallest count whose B
+ * holds the worst-case error 2 sqrt(2 dim) 2^-B of a unit-norm Gram entry below 1e-10 (B200SQ_CRT_TOL).      */
 B200SQ_API int b200sq_gram_crt_moduli(int64_t dim);
+B200SQ_API int b200sq_gram_crt_bits(int64_t dim);
 B200SQ_API int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
                                      int64_t plane_rows, int64_t row0, int32_t* expo_dev,
-                                     const uint32_t* row_max_dev, void* stream);
+                                     const b200sq_row_stats* row_stats_dev, void* stream);
 
 /* b200sq_gram_slice_crt that also writes the 6 nat DIGIT planes ([6][digit_rows][2 * dim]: what the multi-GPU
  * exchange sends) from the same read of the states; the residues are then those b200sq_gram_digits_to_crt derives
  * from these digits, so sender and receivers hold identical integers for a state.                        */
 B200SQ_API int b200sq_gram_slice_crt_digits(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
                                             int64_t plane_rows, int64_t row0, int32_t* expo_dev,
-                                            const uint32_t* row_max_dev, void* digit_planes_dev, int64_t digit_rows,
+                                            const b200sq_row_stats* row_stats_dev, void* digit_planes_dev, int64_t digit_rows,
                                             int64_t digit_row0, void* stream);
 
 /* Residue planes of a COLUMN block from its 6 nat digit planes (what the multi-GPU exchange delivers: 6 instead of
- * 13 bytes per component): rows [row0_d, row0_d + N) of digit planes [>= 6][plane_rows_d][2 * dim] ->
+ * s bytes per component): rows [row0_d, row0_d + N) of digit planes [>= 6][plane_rows_d][2 * dim] ->
  * rows [row0_o, row0_o + N) of residue planes [s][plane_rows_o][2 * dim] (nat residues only; the row exponents of
  * the digit planes stay valid).                                                                          */
 B200SQ_API int b200sq_gram_digits_to_crt(const void* digit_planes_dev, int64_t plane_rows_d, int64_t row0_d, int64_t N,

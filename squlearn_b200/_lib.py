@@ -71,7 +71,7 @@ EXPORTS = [
     "b200sq_last_error", "b200sq_abi_version", "b200sq_device_count", "b200sq_program_create",
     "b200sq_program_destroy", "b200sq_program_set_coeffs", "b200sq_program_num_passes",
     "b200sq_program_dump", "b200sq_program_jit_compile", "b200sq_simulate", "b200sq_simulate_rowmax",
-    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_gram_crt_moduli",
+    "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_gram_crt_moduli", "b200sq_gram_crt_bits",
     "b200sq_gram_slice_crt", "b200sq_gram_slice_crt_digits", "b200sq_gram_digits_to_crt", "b200sq_simulate_expvals", "b200sq_expvals",
     "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_wait_flags", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
     "b200sq_copy_async", "b200sq_rbf",
@@ -142,6 +142,8 @@ def load():
     lib.b200sq_gram_from_planes.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, i64, i64, vp, i64, c.c_uint32, vp]
     lib.b200sq_gram_crt_moduli.restype = c.c_int
     lib.b200sq_gram_crt_moduli.argtypes = [i64]
+    lib.b200sq_gram_crt_bits.restype = c.c_int
+    lib.b200sq_gram_crt_bits.argtypes = [i64]
     lib.b200sq_gram_slice_crt.restype = c.c_int
     lib.b200sq_gram_slice_crt.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, vp]
     lib.b200sq_gram_slice_crt_digits.restype = c.c_int
@@ -164,7 +166,7 @@ def load():
     lib.b200sq_copy_async.argtypes = [vp, vp, c.c_size_t, vp]
     lib.b200sq_rbf.restype = c.c_int
     lib.b200sq_rbf.argtypes = [vp, i64, vp, i64, c.c_int, dbl, vp, i64, vp]
-    if lib.b200sq_abi_version() != 2:
+    if lib.b200sq_abi_version() != 3:
         raise RuntimeError("libb200sq.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -164,7 +164,7 @@ int upload_masks(b200sq_program* p, int n_terms, const uint32_t* xm, const uint3
 // stream-ordered scratch allocation (at most two buffers, ping-pong).
 int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v0, int nv, int d,
                const double* x, const double* table, bool have_variants, double2* psi, int64_t psi_off,
-               bool fuse_expvals, int n_terms, double* out, cudaStream_t stream, uint32_t* row_max = nullptr) {
+               bool fuse_expvals, int n_terms, double* out, cudaStream_t stream, RowStats* row_stats = nullptr) {
     const Plan& pl = p->plan;
     const int64_t n_states = (int64_t)nv * ns;
     double2* ws[2] = {nullptr, nullptr};
@@ -223,7 +223,7 @@ int run_passes(b200sq_program* p, int64_t n_total, int64_t s0, int64_t ns, int v
         a.xmask = p->d_masks;
         a.zmask = p->d_masks ? p->d_masks + n_terms : nullptr;
         a.out = out;
-        a.row_max = (last && a.dst == psi && psi && P.out_bits == pl.n) ? row_max : nullptr;  // the FINAL amplitudes only
+        a.row_stats = (last && a.dst == psi && psi && P.out_bits == pl.n) ? row_stats : nullptr;  // the FINAL amplitudes only
         tile_pass_geometry(P, &a);
         a.total_items = n_states << P.n_obits;
         // Large batches run a kernel specialised for this pass at run time (compiled once per program);
@@ -363,7 +363,7 @@ int b200sq_simulate(b200sq_program* prog, int64_t N, int d, const double* x_dev,
 
 int b200sq_simulate_rowmax(b200sq_program* prog, int64_t N, int d, const double* x_dev,
                            const double* angle_table_dev, int n_variants, const int32_t* var_gate,
-                           const double* var_shift, void* psi_dev, uint32_t* row_max_dev, void* stream_) {
+                           const double* var_shift, void* psi_dev, b200sq_row_stats* row_stats_dev, void* stream_) {
     if (!prog || !psi_dev) return fail(2, "NULL argument");
     if (N < 0 || n_variants < 1) return fail(2, "bad batch size");
     if (N == 0) return 0;
@@ -371,12 +371,12 @@ int b200sq_simulate_rowmax(b200sq_program* prog, int64_t N, int d, const double*
     int e;
     if ((e = ensure_device(prog, stream))) return e;
     if ((e = upload_variants(prog, n_variants, var_gate, var_shift, stream))) return e;
-    if (row_max_dev) {
-        cudaError_t ce = cudaMemsetAsync(row_max_dev, 0, (size_t)n_variants * (size_t)N * sizeof(uint32_t), stream);
+    if (row_stats_dev) {
+        cudaError_t ce = cudaMemsetAsync(row_stats_dev, 0, (size_t)n_variants * (size_t)N * sizeof(b200sq_row_stats), stream);
         if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemsetAsync (row maxima)");
     }
     return run_passes(prog, N, 0, N, 0, n_variants, d, x_dev, angle_table_dev, var_gate != nullptr,
-                      (double2*)psi_dev, 0, false, 0, nullptr, stream, row_max_dev);
+                      (double2*)psi_dev, 0, false, 0, nullptr, stream, reinterpret_cast<RowStats*>(row_stats_dev));
 }
 
 int b200sq_simulate_expvals(b200sq_program* prog, int64_t N, int d, const double* x_dev,
@@ -452,8 +452,8 @@ int b200sq_gram(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_
 }
 
 int b200sq_gram_rowmax(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev, int64_t Ny, int64_t dim,
-                       double* K_dev, int64_t ldk, uint32_t flags, const uint32_t* row_max_x_dev,
-                       const uint32_t* row_max_y_dev, void* stream_) {
+                       double* K_dev, int64_t ldk, uint32_t flags, const b200sq_row_stats* row_stats_x_dev,
+                       const b200sq_row_stats* row_stats_y_dev, void* stream_) {
     if (!psi_x_dev || !psi_y_dev || !K_dev) return fail(2, "NULL argument");
     if (Nx < 0 || Ny < 0 || dim < 1 || ldk < Ny) return fail(2, "bad sizes");
     if ((flags & B200SQ_GRAM_SYMMETRIC) && (Nx != Ny || ldk < Nx))
@@ -461,7 +461,8 @@ int b200sq_gram_rowmax(const void* psi_x_dev, int64_t Nx, const void* psi_y_dev,
     int e;
     if ((flags & B200SQ_GRAM_INT8) && gram_i8_supported(dim))
         e = launch_gram_i8((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
-                           (cudaStream_t)stream_, row_max_x_dev, row_max_y_dev);
+                           (cudaStream_t)stream_, reinterpret_cast<const RowStats*>(row_stats_x_dev),
+                           reinterpret_cast<const RowStats*>(row_stats_y_dev));
     else
         e = launch_gram((const double2*)psi_x_dev, Nx, (const double2*)psi_y_dev, Ny, dim, K_dev, ldk, flags,
                         (cudaStream_t)stream_);
@@ -479,33 +480,35 @@ int b200sq_gram_slice(const void* psi_dev, int64_t N, int64_t dim, void* planes_
 }
 
 int b200sq_gram_slice_rowmax(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
-                             int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* stream_) {
+                             int64_t row0, int32_t* expo_dev, const b200sq_row_stats* row_stats_dev, void* stream_) {
     if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
     if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
     if (!gram_i8_supported(dim)) return fail(2, "the INT8 Gram needs dim >= 64 and dim % 8 == 0");
     int e = launch_slice_i8((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
-                            (cudaStream_t)stream_, row_max_dev);
+                            (cudaStream_t)stream_, reinterpret_cast<const RowStats*>(row_stats_dev));
     if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
     return 0;
 }
 
 int b200sq_gram_crt_moduli(int64_t dim) { return gram_crt_supported(dim) ? gram_crt_moduli(dim) : 0; }
+int b200sq_gram_crt_bits(int64_t dim) { return gram_crt_supported(dim) ? gram_crt_bits(dim) : 0; }
+static_assert(sizeof(b200sq_row_stats) == sizeof(RowStats) && sizeof(RowStats) == 16, "row statistics layout");
 
 int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
-                          int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* stream_) {
-    return b200sq_gram_slice_crt_digits(psi_dev, N, dim, planes_dev, plane_rows, row0, expo_dev, row_max_dev, nullptr,
+                          int64_t row0, int32_t* expo_dev, const b200sq_row_stats* row_stats_dev, void* stream_) {
+    return b200sq_gram_slice_crt_digits(psi_dev, N, dim, planes_dev, plane_rows, row0, expo_dev, row_stats_dev, nullptr,
                                         0, 0, stream_);
 }
 
 int b200sq_gram_slice_crt_digits(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev, int64_t plane_rows,
-                                 int64_t row0, int32_t* expo_dev, const uint32_t* row_max_dev, void* digit_planes_dev,
+                                 int64_t row0, int32_t* expo_dev, const b200sq_row_stats* row_stats_dev, void* digit_planes_dev,
                                  int64_t digit_rows, int64_t digit_row0, void* stream_) {
     if (!psi_dev || !planes_dev || !expo_dev) return fail(2, "NULL argument");
     if (N < 0 || row0 < 0 || row0 + N > plane_rows) return fail(2, "rows outside the planes");
     if (digit_planes_dev && (digit_row0 < 0 || digit_row0 + N > digit_rows)) return fail(2, "rows outside the digit planes");
     if (!gram_crt_supported(dim)) return fail(2, "the CRT Gram does not support this state dimension");
     int e = launch_slice_crt((const double2*)psi_dev, N, dim, (int8_t*)planes_dev, plane_rows, row0, expo_dev,
-                             (cudaStream_t)stream_, row_max_dev, (int8_t*)digit_planes_dev, digit_rows, digit_row0);
+                             (cudaStream_t)stream_, reinterpret_cast<const RowStats*>(row_stats_dev), (int8_t*)digit_planes_dev, digit_rows, digit_row0);
     if (e) return cuda_fail(e, "slice launch (no CUDA device? b200sq has no CPU path)");
     return 0;
 }

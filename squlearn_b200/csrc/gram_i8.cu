@@ -22,12 +22,15 @@
 // rot(x)): the column operand only needs its 6 nat planes, which is what the multi-GPU exchange sends.
 //
 // SECOND SCHEME (B200SQ_GRAM_CRT, "Ozaki scheme II"): instead of 6 x 6 digit pairs, the integers
-// q = round(v * 2^(40 - e)) (41 bits per row scale) are reduced modulo s pairwise coprime odd numbers p_m <= 255
-// (s = 13 for K' = 2^17); one exact int8 x int8 -> int32 product per modulus gives the inner product mod p_m, and the
-// Chinese remainder theorem recovers the exact integer inner product (|.| < P / 2, P = prod p_m) in the epilogue
-// kernel with a double-double accumulation of k_m / p_m.  13 tensor-core products instead of 22 for the same
-// 1e-10 bound (the error is the 41-bit input quantisation only: no product terms are dropped).  Planes:
-// [2 s][rows][2 dim] int8, residues of nat(v) then of rot(v); W holds int32 residue sums per (tile, modulus).
+// q = round(v * 2^(B - e)) are reduced modulo s pairwise coprime numbers p_m <= 256 (256 and odd numbers); one exact
+// int8 x int8 -> int32 product per modulus gives the inner product mod p_m, and the Chinese remainder theorem recovers
+// the exact integer inner product (|.| < P / 2, P = prod p_m) in the epilogue kernel with a double-double accumulation
+// of k_m / p_m.  The row scale 2^e comes from the row's 2-NORM, not its maximum: by Cauchy-Schwarz
+// |q_x . q_y| <= |q_x| |q_y| <= R^2 with R = sqrt(P / 2), so e is the smallest integer with 2^(B - e) |x| <= R and no
+// factor K' is wasted on a worst case that cannot happen.  s = 11, B = 43 for K' = 2^17: 11 tensor-core products
+// instead of 22 for a worst-case bound of 2 sqrt(K') 2^-B = 8e-11 on K (unit-norm rows; the error is the input
+// quantisation only: no product terms are dropped).  Planes: [2 s][rows][2 dim] int8, residues of nat(v) then of
+// rot(v); W holds int32 residue sums per (tile, modulus).
 //
 // JOB TABLE.  One launch covers several Gram blocks ("jobs") that share the local row operand: job j multiplies
 // rows [x0, x0 + nx) of the local planes with rows [y0, y0 + ny) of its own column planes (the local planes for
@@ -67,14 +70,17 @@ constexpr int kStageBytes = 3 * kTileBytes;      // A, Bnat, Brot
 constexpr int kStages = 4;
 constexpr int kChunkK = 16384;                   // bytes of K per int32 accumulation chunk
 constexpr int kMaxClasses = 16, kMaxPairs = 8;
-constexpr int kCrtBits = 40;                      // CRT scheme: q = round(v * 2^(kCrtBits - e))
+constexpr int kCrtDigitBits = 46;                 // CRT exchange digits: q46 = round(v * 2^(kCrtDigitBits - e)), e from the row norm
+constexpr int kCrtMaxBits = kCrtDigitBits - 1;    // upper limit of B (the digits must carry at least one guard bit)
 constexpr int kCrtMaxModuli = 16;
-// pairwise coprime odd moduli (255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
-// residues fit int8, and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
-__constant__ int c_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
-__constant__ double c_crt_inv[kCrtMaxModuli] = {1.0 / 255, 1.0 / 253, 1.0 / 251, 1.0 / 247, 1.0 / 241, 1.0 / 239, 1.0 / 233, 1.0 / 229,
-                                                1.0 / 227, 1.0 / 223, 1.0 / 217, 1.0 / 211, 1.0 / 199, 1.0 / 197, 1.0 / 193, 1.0 / 191};
-static const int h_crt_moduli[kCrtMaxModuli] = {255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191};
+// pairwise coprime moduli (256; 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
+// residues fit int8 (256: -128 stands for +-128), and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
+// (for p = 256 a wrapped int32 sum is still right modulo 256)
+#define B200SQ_CRT_MODULI 256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193
+__constant__ int c_crt_moduli[kCrtMaxModuli] = {B200SQ_CRT_MODULI};
+__constant__ double c_crt_inv[kCrtMaxModuli] = {1.0 / 256, 1.0 / 255, 1.0 / 253, 1.0 / 251, 1.0 / 247, 1.0 / 241, 1.0 / 239, 1.0 / 233,
+                                                1.0 / 229, 1.0 / 227, 1.0 / 223, 1.0 / 217, 1.0 / 211, 1.0 / 199, 1.0 / 197, 1.0 / 193};
+static const int h_crt_moduli[kCrtMaxModuli] = {B200SQ_CRT_MODULI};
 constexpr int kThreads = 256;
 
 struct I8Schedule {
@@ -117,7 +123,7 @@ struct I8Args {
     int n_planes;             // nat planes per operand (rot planes follow): 6 digit slices, or s residue planes
     int crt;                  // 1: CRT scheme (classes = moduli, W = int32 residue sums [n_tiles][s][2][mn][mn])
     int crt_c[kCrtMaxModuli];    // (P / p_m)^-1 mod p_m
-    double crt_scale;            // P * 2^(-2 kCrtBits)
+    double crt_scale;            // P * 2^(-2 B)
     double* W;                // [n_tiles][2][mn cols][mn rows]
     I8Schedule sched;
     I8Job jobs[kMaxJobs];
@@ -474,7 +480,8 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int iv = (int)v[c];
-                            const int r = iv - pm * __double2int_rn((double)iv * inv_pm);
+                            int r = iv - pm * __double2int_rn((double)iv * inv_pm);
+                            if (r == 128) r = -128;   // (p = 256 only)
                             if (single) wp[(size_t)c * MN] = r;
                             else if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
                         }
@@ -509,8 +516,8 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
 
 // ---------------------------------------------------------------------------------------------
 // Digit planes.  planes: [2 * kSlices][n_rows][2 * dim] int8; plane s = digits of nat = (re, im), plane
-// kSlices + s = digits of rot = (-im, re).  One CTA per state row.  `row_max` (optional): high words of the row
-// maxima max(|re|, |im|) already reduced by the producer of the states (the last gate pass, see TileArgs::row_max),
+// kSlices + s = digits of rot = (-im, re).  One CTA per state row.  `row_stats` (optional): high words of the row
+// maxima max(|re|, |im|) already reduced by the producer of the states (the last gate pass, see TileArgs::row_stats),
 // which saves this kernel's first sweep over the state (the high word has the exponent: all the scale needs).
 
 __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int byte) {
@@ -521,15 +528,16 @@ __device__ __forceinline__ uint32_t pack_digit(long long& q, uint32_t word, int 
 
 __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
                                                   int64_t dim, int8_t* __restrict__ planes, int* __restrict__ expo,
-                                                  const uint32_t* __restrict__ row_max) {
+                                                  const RowStats* __restrict__ row_stats) {
     const int64_t row = row0 + blockIdx.x;   // row inside the planes; state blockIdx.x of psi
     const double2* src = psi + (int64_t)blockIdx.x * dim;
     __shared__ double red[8];
     __shared__ int s_e;
     double m = 0.0;
-    if (row_max) {
-        m = __hiloint2double((int)row_max[blockIdx.x], 0);
-        if (row_max[blockIdx.x] != 0u && m == 0.0) m = 4.9e-324;   // (cannot happen for a normalised state)
+    const uint32_t max_hi = row_stats ? row_stats[blockIdx.x].max_hi : 0u;   // 0: no statistics for this row
+    if (max_hi != 0u) {
+        m = __hiloint2double((int)max_hi, 0);
+        if (m == 0.0) m = 4.9e-324;   // (cannot happen for a normalised state)
     } else {
         for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
             const double2 v = src[i];
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(const double2* __restrict__ ps
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (!row_max)
+        if (max_hi == 0u)
             for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
         int e = 0;
         if (m > 0.0) frexp(m, &e);  // m = f * 2^e, f in [0.5, 1): every |v| < 2^e
@@ -668,10 +676,11 @@ __global__ void __launch_bounds__(256) k_gram_i8_final(const double* __restrict_
     }
 }
 
-// Symmetric residue of an exact integer q held in a double, modulo the odd p, WITHOUT conversion instructions (FRND /
+// Symmetric residue of an exact integer q held in a double, modulo p, WITHOUT conversion instructions (FRND /
 // F2I on 64-bit types run at a quarter of the FP64 rate): with M = 1.5 * 2^52, fma(q, 1/p, M) - M is q / p rounded
-// to the nearest integer k (exactly: q / p is never within 1 / (2 p) of a half-integer, the product's error is
-// < 2^-11), and fma(-p, k, q + M) = M + r exactly, whose low 32 bits are r in two's complement.  qm = q + M.
+// to the nearest integer k (odd p: q / p is never within 1 / (2 p) of a half-integer and the product's error is
+// < 2^-8; p = 256: the product is exact), and fma(-p, k, q + M) = M + r exactly, whose low 32 bits are r in two's
+// complement.  qm = q + M.
 constexpr double kRoundMagic = 6755399441055744.0;   // 1.5 * 2^52
 __device__ __forceinline__ int crt_residue(double q, double qm, double pm, double inv) {
     const double k = fma(q, inv, kRoundMagic) - kRoundMagic;
@@ -682,60 +691,71 @@ __device__ __forceinline__ double magic_rint(double x) { return (x + kRoundMagic
 
 // ---------------------------------------------------------------------------------------------
 // CRT scheme: residue planes.  planes: [2 s][n_rows][2 * dim] int8; plane m = nat(q) mod p_m (symmetric residues),
-// plane s + m = rot(q) mod p_m with rot = (-im, re), q = round(v * 2^(kCrtBits - e)).  The residue of an exact
-// integer q held in a double is q - p * rint(q / p): rint is exact because q / p is never within 1 / (2 p) of a
-// half-integer (p is odd) while the rounding error of q * (1 / p) is below 2^-11.
+// plane s + m = rot(q) mod p_m with rot = (-im, re), q = round(v * 2^(B - e)), e = the smallest integer with
+// 2^(B - e) |row|_2 <= R (CrtPlan).  The residue of an exact integer q held in a double is q - p * rint(q / p): rint
+// is exact because q / p is never within 1 / (2 p) of a half-integer for odd p while the rounding error of q * (1 / p)
+// is below 2^-8; for p = 256 the product is exact and a tie leaves r = +-128, both the byte 0x80.
+
+struct CrtPlan {
+    int n_mod;       // moduli in use
+    int bits;        // B
+    double e_bias;   // B - log2(R_eff): e = ceil(log2 |row|_2 + e_bias)
+};
 
 // `digits` (optional): also write the 6 nat DIGIT planes of the rows ([6][digit_rows][2 dim], what the multi-GPU
-// exchange sends) from the same read of the states; the residues are then taken from the integer a receiver
-// reconstructs from those digits (k_digits_to_crt), so every rank works with identical integers for a state.
+// exchange sends) from the same read of the states: q46 = round(v * 2^(kCrtDigitBits - e)) with the SAME row
+// exponent; the residues are then taken from the integer a receiver reconstructs from those digits
+// (k_digits_to_crt), so every rank works with identical integers for a state.
 __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
-                                                   int64_t dim, int n_mod, int8_t* __restrict__ planes,
-                                                   int* __restrict__ expo, const uint32_t* __restrict__ row_max,
+                                                   int64_t dim, const CrtPlan plan, int8_t* __restrict__ planes,
+                                                   int* __restrict__ expo, const RowStats* __restrict__ row_stats,
                                                    int8_t* __restrict__ digits, int64_t digit_rows, int64_t digit_row0) {
     const int64_t row = row0 + blockIdx.x;
     const double2* src = psi + (int64_t)blockIdx.x * dim;
+    const int n_mod = plan.n_mod;
     __shared__ double red[8];
     __shared__ int s_e;
-    double m = 0.0;
-    if (row_max) {
-        m = __hiloint2double((int)row_max[blockIdx.x], 0);
-        if (row_max[blockIdx.x] != 0u && m == 0.0) m = 4.9e-324;
-    } else {
+    double n2 = row_stats ? row_stats[blockIdx.x].norm2 : 0.0;   // 0: no statistics for this row
+    const bool have = n2 > 0.0;
+    if (!have) {
+        double a0 = 0.0, a1 = 0.0;
         for (int64_t i = threadIdx.x; i < dim; i += blockDim.x) {
             const double2 v = src[i];
-            m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+            a0 = fma(v.x, v.x, a0);
+            a1 = fma(v.y, v.y, a1);
         }
-        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        n2 = a0 + a1;
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = n2;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (!row_max)
-            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        if (!have)
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) n2 += red[w];
+        // (1e-9: the summation error of n2 and of log2 can never push a row over R)
         int e = 0;
-        if (m > 0.0) frexp(m, &e);
+        if (n2 > 0.0) e = (int)ceil(0.5 * log2(n2) + plan.e_bias + 1e-9);
         s_e = e;
         expo[row] = e;
     }
     __syncthreads();
-    const double scale = ldexp(1.0, kCrtBits - s_e), scale47 = ldexp(1.0, kTopBits - s_e);
+    const double scale = ldexp(1.0, plan.bits - s_e), scale_d = ldexp(1.0, kCrtDigitBits - s_e);
     const size_t plane_stride = (size_t)plane_rows * 2 * dim;
     int8_t* dst_row = planes + (size_t)row * 2 * dim;
     const size_t digit_stride = (size_t)digit_rows * 2 * dim;
     int8_t* dig_row = digits ? digits + (size_t)(digit_row0 + blockIdx.x) * 2 * dim : nullptr;
-    const double drop = ldexp(1.0, -(kTopBits - kCrtBits));
+    const double drop = ldexp(1.0, -(kCrtDigitBits - plan.bits));
     for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
         double q[16];   // (re, im) of 8 amplitudes as exact integers
         if (digits) {
-            long long q47[16];
+            long long qd[16];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double2 v = __ldcs(src + i0 + c);
-                const double a = magic_rint(v.x * scale47), b = magic_rint(v.y * scale47);
-                q47[2 * c] = (long long)a;
-                q47[2 * c + 1] = (long long)b;
-                // the CRT integer is the digit integer rounded to kCrtBits (ties to even), exactly what a receiver
+                const double a = magic_rint(v.x * scale_d), b = magic_rint(v.y * scale_d);
+                qd[2 * c] = (long long)a;
+                qd[2 * c + 1] = (long long)b;
+                // the CRT integer is the digit integer rounded to B bits (ties to even), exactly what a receiver
                 // derives from the digits (k_digits_to_crt)
                 q[2 * c] = magic_rint(a * drop);
                 q[2 * c + 1] = magic_rint(b * drop);
@@ -744,7 +764,7 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
             for (int sl = kSlices - 1; sl >= 0; --sl) {
                 uint32_t wd[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int b = 0; b < 16; ++b) wd[b >> 2] = pack_digit(q47[b], wd[b >> 2], b & 3);
+                for (int b = 0; b < 16; ++b) wd[b >> 2] = pack_digit(qd[b], wd[b >> 2], b & 3);
                 *reinterpret_cast<uint4*>(dig_row + (size_t)sl * digit_stride + 2 * i0) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             }
         } else {
@@ -779,20 +799,20 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 }
 
 // Digit planes -> residue planes, for column blocks that arrive as digit planes (the multi-GPU exchange sends the
-// 6 nat digit planes: 6 instead of 13 bytes per component; the receiver derives the residues).  The 47-bit digits
-// hold q47 = round(v 2^(46 - e)); the CRT integer is q = round(q47 / 2^(46 - kCrtBits)) (ties to even), a valid
-// kCrtBits-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
+// 6 nat digit planes: 6 instead of s bytes per component; the receiver derives the residues).  The digits hold
+// q46 = round(v 2^(kCrtDigitBits - e)); the CRT integer is q = round(q46 / 2^(kCrtDigitBits - B)) (ties to even), a
+// valid B-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
 // (The kernel runs NEXT TO the persistent Gram kernel, which keeps ~28 K registers and 198 KB of shared memory per SM:
 // four components per thread keep it below 48 registers so that several CTAs fit beside it.)
 __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
-                                                          int64_t kbytes, int n_mod, int8_t* __restrict__ out,
+                                                          int64_t kbytes, int n_mod, double drop, int8_t* __restrict__ out,
                                                           int64_t rows_o, int64_t row0_o) {
     const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
     const int8_t* src = digits + (size_t)(row0_d + blockIdx.y) * kbytes;
     int8_t* dst = out + (size_t)(row0_o + blockIdx.y) * kbytes;
     const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (k0 >= kbytes) return;
-    // the 47-bit digit integer from two 24-bit halves (int32 arithmetic), then rounded to kCrtBits (ties to even)
+    // the digit integer from two 24-bit halves (int32 arithmetic), then rounded to B bits (ties to even)
     int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
@@ -804,7 +824,6 @@ __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restri
             else lo[b] = lo[b] * 256 + d;
         }
     }
-    const double drop = ldexp(1.0, -(kTopBits - kCrtBits));
     double q[4], qm[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -826,9 +845,9 @@ __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restri
 // CRT reconstruction: residues r_m of an integer x with |x| < P / 2  ->  x / P = frac(sum_m k_m / p_m) mapped to
 // (-1/2, 1/2], k_m = r_m c_m mod p_m, c_m = (P / p_m)^-1 mod p_m.  Every k_m / p_m is split into a double-double
 // (hi + lo) and the sum is accumulated error-free, so the result keeps full double precision although it is
-// ~2^-13 of the terms.  The (hi, lo) pairs come from a shared-memory table indexed by (modulus, residue + 127),
+// ~2^-13 of the terms.  The (hi, lo) pairs come from a shared-memory table indexed by (modulus, residue + 128),
 // built once per CTA: one table look-up and one error-free addition per modulus and entry.
-constexpr int kCrtTabStride = 256;   // residues -127 .. 127 (+ padding) per modulus
+constexpr int kCrtTabStride = 256;   // residues -128 .. 127 per modulus
 
 __device__ __forceinline__ double2 crt_term(int r, int pm, int c) {
     int k = (r % pm) * c % pm;
@@ -844,8 +863,8 @@ __device__ __forceinline__ double crt_fraction(const int* __restrict__ w, size_t
 #pragma unroll 4
     for (int mi = 0; mi < n_mod; ++mi) {
         const int r = w[(size_t)mi * mod_stride];
-        // a single K chunk stores symmetric residues (|r| <= 127): table; sums over chunks: reduce first
-        const double2 t2 = ((unsigned)(r + 127) < 255u) ? tab[mi * kCrtTabStride + r + 127]
+        // a single K chunk stores symmetric residues (-128 <= r <= 127): table; sums over chunks: reduce first
+        const double2 t2 = ((unsigned)(r + 128) < 256u) ? tab[mi * kCrtTabStride + r + 128]
                                                         : crt_term(r, c_crt_moduli[mi], crt_c[mi]);
         const double t = sh + t2.x;
         const double bb = t - sh;
@@ -865,7 +884,7 @@ __global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ 
     extern __shared__ double2 s_tab[];   // [n_mod][kCrtTabStride]
     if (threadIdx.x < kCrtMaxModuli) s_c[threadIdx.x] = A.crt_c[threadIdx.x];
     for (int t = threadIdx.x; t < A.sched.n_classes * kCrtTabStride; t += blockDim.x) {
-        const int mi = t / kCrtTabStride, r = t - mi * kCrtTabStride - 127;
+        const int mi = t / kCrtTabStride, r = t - mi * kCrtTabStride - 128;
         s_tab[t] = crt_term(r, c_crt_moduli[mi], A.crt_c[mi]);
     }
     __syncthreads();
@@ -1021,31 +1040,64 @@ unsigned int gram_ready_timeouts() {
 bool gram_i8_supported(int64_t dim) { return dim >= 64 && dim % 8 == 0 && 2 * dim <= (1ll << 30); }
 
 int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                    int* expo, cudaStream_t stream, const uint32_t* row_max) {
+                    int* expo, cudaStream_t stream, const RowStats* row_stats) {
     if (n <= 0) return 0;
-    k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo, row_max);
+    k_slice_i8<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, planes, expo, row_stats);
     count_launch();
     return (int)cudaGetLastError();
 }
 
-// Number of moduli of the CRT scheme for K' = 2 * dim int8 per row: the smallest s with
-// prod_{m < s} p_m > 2^(2 kCrtBits + 2) * K' (twice the largest possible |inner product|, with one bit to spare).
-int gram_crt_moduli(int64_t dim) {
-    double need = 2.0 * kCrtBits + 2.0 + log2((double)(2 * dim)), have = 0.0;
-    int s = 0;
-    while (s < kCrtMaxModuli && have < need) have += log2((double)h_crt_moduli[s++]);
-    return have >= need ? s : 0;
+// Moduli and bits of the CRT scheme for K' = 2 * dim int8 per row.  With s moduli, P = prod p_m and R = sqrt(P / 2),
+// a row scaled to 2^(B - e) |x|_2 <= R_eff = R - (rounding slack) has |q_x . q_y| <= |q_x|_2 |q_y|_2 < P / 2
+// (Cauchy-Schwarz), so the symmetric CRT reconstruction is exact; B = floor(log2 R_eff), at most kCrtMaxBits.  A
+// unit-norm row gets e = 0, components are off by at most 2^-B / 2, an inner product by sqrt(K') 2^-B and a Gram
+// entry by 2 sqrt(K') 2^-B: s is the smallest count whose B keeps that below the tolerance (1e-10, B200SQ_CRT_TOL).
+static double crt_tolerance() {
+    static const double tol = [] {
+        const char* t = getenv("B200SQ_CRT_TOL");
+        const double v = t ? atof(t) : 0.0;
+        return v > 0.0 ? v : 1e-10;
+    }();
+    return tol;
 }
+
+static CrtPlan crt_plan(int64_t dim) {
+    CrtPlan pl;
+    pl.n_mod = 0;
+    pl.bits = 0;
+    pl.e_bias = 0.0;
+    const double kp = (double)(2 * dim);
+    const int need = (int)ceil(log2(2.0 * sqrt(kp) / crt_tolerance()));
+    long double P = 1.0L;
+    for (int s = 1; s <= kCrtMaxModuli; ++s) {
+        P *= (long double)h_crt_moduli[s - 1];
+        // every component of q is off by at most 5/8 (rounding, twice when the digits are rounded first):
+        // |q|_2 <= 2^(B - e) |x|_2 + 0.625 sqrt(K')
+        const long double r_eff = sqrtl(P / 2.0L) - 0.625L * sqrtl((long double)kp) - 1.0L;
+        if (r_eff < 2.0L) continue;
+        const int bits = std::min((int)floorl(log2l(r_eff)), kCrtMaxBits);
+        if (bits >= need || (s == kCrtMaxModuli && bits >= 30)) {
+            pl.n_mod = s;
+            pl.bits = bits;
+            pl.e_bias = (double)((long double)bits - log2l(r_eff));
+            return pl;
+        }
+    }
+    return pl;
+}
+
+int gram_crt_moduli(int64_t dim) { return crt_plan(dim).n_mod; }
+int gram_crt_bits(int64_t dim) { return crt_plan(dim).bits; }
 
 bool gram_crt_supported(int64_t dim) { return gram_i8_supported(dim) && gram_crt_moduli(dim) > 0; }
 
 int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                     int* expo, cudaStream_t stream, const uint32_t* row_max, int8_t* digits, int64_t digit_rows,
+                     int* expo, cudaStream_t stream, const RowStats* row_stats, int8_t* digits, int64_t digit_rows,
                      int64_t digit_row0) {
     if (n <= 0) return 0;
-    const int s = gram_crt_moduli(dim);
-    if (s <= 0) return (int)cudaErrorInvalidValue;
-    k_slice_crt<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, s, planes, expo, row_max, digits,
+    const CrtPlan pl = crt_plan(dim);
+    if (pl.n_mod <= 0) return (int)cudaErrorInvalidValue;
+    k_slice_crt<<<(unsigned)n, 256, 0, stream>>>(psi, plane_rows, row0, dim, pl, planes, expo, row_stats, digits,
                                                  digit_rows, digit_row0);
     count_launch();
     return (int)cudaGetLastError();
@@ -1054,24 +1106,25 @@ int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes,
 int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, int64_t n, int64_t dim, int8_t* out,
                          int64_t rows_o, int64_t row0_o, cudaStream_t stream) {
     if (n <= 0) return 0;
-    const int s = gram_crt_moduli(dim);
-    if (s <= 0) return (int)cudaErrorInvalidValue;
+    const CrtPlan pl = crt_plan(dim);
+    if (pl.n_mod <= 0) return (int)cudaErrorInvalidValue;
     const int64_t kbytes = 2 * dim;
     const dim3 grid((unsigned)((kbytes / 4 + 255) / 256), (unsigned)n);
-    k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, s, out, rows_o, row0_o);
+    k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, pl.n_mod, ldexp(1.0, -(kCrtDigitBits - pl.bits)),
+                                              out, rows_o, row0_o);
     count_launch();
     return (int)cudaGetLastError();
 }
 
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
-                   int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x,
-                   const uint32_t* row_max_y) {
+                   int64_t ldk, uint32_t flags, cudaStream_t stream, const RowStats* row_stats_x,
+                   const RowStats* row_stats_y) {
     if (nx <= 0 || ny <= 0) return 0;
     const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
     const bool crt = (flags & B200SQ_GRAM_CRT) && gram_crt_supported(dim);
     if (!crt) flags &= ~B200SQ_GRAM_CRT;
     const int n_planes = crt ? gram_crt_moduli(dim) : kSlices;
-    auto slice = [&](const double2* psi, int64_t n, int8_t* planes, int* expo, const uint32_t* rm) {
+    auto slice = [&](const double2* psi, int64_t n, int8_t* planes, int* expo, const RowStats* rm) {
         return crt ? launch_slice_crt(psi, n, dim, planes, n, 0, expo, stream, rm)
                    : launch_slice_i8(psi, n, dim, planes, n, 0, expo, stream, rm);
     };
@@ -1087,14 +1140,14 @@ int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, i
     };
     if ((e = cudaMallocAsync(&py, 2 * n_planes * (size_t)ny * plane_bytes, stream)) != cudaSuccess) return (int)e;
     if ((e = cudaMallocAsync(&ey, ny * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-    slice(y, ny, py, ey, row_max_y);
+    slice(y, ny, py, ey, row_stats_y);
     if (sym) {
         px = py;
         ex = ey;
     } else {
         if ((e = cudaMallocAsync(&px, 2 * n_planes * (size_t)nx * plane_bytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
         if ((e = cudaMallocAsync(&ex, nx * sizeof(int), stream)) != cudaSuccess) { cleanup(); return (int)e; }
-        slice(x, nx, px, ex, row_max_x);
+        slice(x, nx, px, ex, row_stats_x);
     }
     const int rc = launch_gram_planes(px, ex, nx, 0, nx, py, ey, ny, 0, ny, dim, k, ldk, flags, stream);
     cleanup();
@@ -1193,7 +1246,7 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
     a.n_chunks = (int)n_chunks_of(a.chunk_bytes);
     a.mn = kTile * cg;
     if (crt) {
-        // one class per modulus: plane m x plane m; (P / p_m)^-1 mod p_m and P * 2^(-2 kCrtBits) for the epilogue
+        // one class per modulus: plane m x plane m; (P / p_m)^-1 mod p_m and P * 2^(-2 B) for the epilogue
         I8Schedule& s = a.sched;
         s.n_classes = n_mod;
         long double P = 1.0L;
@@ -1209,7 +1262,7 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
             while ((prod * inv) % h_crt_moduli[m] != 1) ++inv;
             a.crt_c[m] = inv;
         }
-        a.crt_scale = (double)ldexpl(P, -2 * kCrtBits);
+        a.crt_scale = (double)ldexpl(P, -2 * gram_crt_bits(dim));
     } else {
         // classes from the smallest weight to the largest: c = 5 .. 0, plus the correlated pair (3, 3) of c = 6
         I8Schedule& s = a.sched;

@@ -33,21 +33,22 @@ int launch_gram(const double2* x, int64_t nx, const double2* y, int64_t ny, int6
 bool gram_i8_supported(int64_t dim);
 bool gram_crt_supported(int64_t dim);
 int gram_crt_moduli(int64_t dim);   // residue planes per operand half of the CRT scheme (0: unsupported)
+int gram_crt_bits(int64_t dim);     // B of the CRT scheme: a row is quantised as round(v * 2^(B - e))
 int launch_slice_crt(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                     int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr, int8_t* digits = nullptr,
+                     int* expo, cudaStream_t stream, const RowStats* row_stats = nullptr, int8_t* digits = nullptr,
                      int64_t digit_rows = 0, int64_t digit_row0 = 0);
 int launch_wait_flags(const uint32_t* flags, const int32_t* which, int n, uint32_t value, cudaStream_t stream);
 int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, int64_t n, int64_t dim, int8_t* out,
                          int64_t rows_o, int64_t row0_o, cudaStream_t stream);
 unsigned int gram_ready_timeouts();   // jobs whose ready flag never arrived (synchronises the device)
 int launch_gram_i8(const double2* x, int64_t nx, const double2* y, int64_t ny, int64_t dim, double* k,
-                   int64_t ldk, uint32_t flags, cudaStream_t stream, const uint32_t* row_max_x = nullptr,
-                   const uint32_t* row_max_y = nullptr);
+                   int64_t ldk, uint32_t flags, cudaStream_t stream, const RowStats* row_stats_x = nullptr,
+                   const RowStats* row_stats_y = nullptr);
 
 // Digit planes of n states into rows [row0, row0 + n) of `planes` ([12][plane_rows][2 dim] int8) and their
 // power-of-two row scales into expo[row0 ...]; Gram from planes.
 int launch_slice_i8(const double2* psi, int64_t n, int64_t dim, int8_t* planes, int64_t plane_rows, int64_t row0,
-                    int* expo, cudaStream_t stream, const uint32_t* row_max = nullptr);
+                    int* expo, cudaStream_t stream, const RowStats* row_stats = nullptr);
 int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t dim, int n_jobs,
                      const b200sq_gram_job* jobs, cudaStream_t stream);
 int launch_gram_planes(const int8_t* px, const int* ex, int64_t rows_x, int64_t x0, int64_t nx, const int8_t* py,

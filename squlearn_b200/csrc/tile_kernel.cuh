@@ -7,6 +7,13 @@
 
 namespace b200sq {
 
+// Per-state statistics reduced by the store epilogue of the last pass (same layout as b200sq_row_stats).
+struct RowStats {
+    double norm2;
+    uint32_t max_hi;
+    uint32_t reserved;
+};
+
 struct TileArgs {
     const unsigned char* blob;   // device copy of the pass blob (plan.hpp: build_pass_blob)
     int32_t blob_bytes;
@@ -32,9 +39,10 @@ struct TileArgs {
     const uint32_t* xmask;     // device
     const uint32_t* zmask;
     double* out;               // [n_variants_total][n_total][n_terms]
-    uint32_t* row_max;         // nullptr, or per output state (indexed like dst): running maximum of the high words of
-                               // max(|re|, |im|) over the stored amplitudes (atomicMax; zeroed by the launcher) — the
-                               // row scale the INT8 Gram's digit slicing needs, without a sweep of its own
+    RowStats* row_stats;       // nullptr, or per output state (indexed like dst; zeroed by the launcher): max_hi = running
+                               // maximum of the high words of max(|re|, |im|) over the stored amplitudes (atomicMax),
+                               // norm2 = sum of |amplitude|^2 (atomicAdd) — the row scales the INT8 Gram's slicing
+                               // needs (digit form: maximum; CRT form: 2-norm), without a sweep of its own
     int32_t team_size, log2ts, teams_per_cta, team_elems;
     int64_t total_items;
 };
@@ -228,8 +236,9 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
         // ---- epilogue
         if (A.store && in_range) {
             double2* dp = dstate + (obase_out | map.out_lo);
-            if (A.row_max) {
+            if (A.row_stats) {
                 uint32_t hi = 0;
+                double n2 = 0.0;
 #pragma unroll 8
                 for (int j = 0; j < J; ++j) {
                     const double2 v = tm.tile[smem_idx(j)];
@@ -237,10 +246,21 @@ __device__ __forceinline__ void tile_pass_body(const TileArgs& A, Rounds run_rou
                     const uint32_t hx = (uint32_t)__double2hiint(v.x) & 0x7fffffffu;
                     const uint32_t hy = (uint32_t)__double2hiint(v.y) & 0x7fffffffu;
                     hi = max(hi, max(hx, hy));
+                    n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
                 }
-                hi = __reduce_max_sync(__activemask(), hi);
-                if ((tid & 31) == 0)
-                    atomicMax(A.row_max + ((int64_t)variant * A.dst_vstride + ic.sample - A.dst_off), hi);
+                const unsigned am = __activemask();
+                hi = __reduce_max_sync(am, hi);
+                RowStats* rs = A.row_stats + ((int64_t)variant * A.dst_vstride + ic.sample - A.dst_off);
+                if (am == 0xffffffffu) {
+                    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                    if ((tid & 31) == 0) {
+                        atomicMax(&rs->max_hi, hi);
+                        atomicAdd(&rs->norm2, n2);
+                    }
+                } else {   // (teams are whole warps: not reached)
+                    atomicMax(&rs->max_hi, hi);
+                    atomicAdd(&rs->norm2, n2);
+                }
             } else {
 #pragma unroll 8
                 for (int j = 0; j < J; ++j) __stcs(dp + tm.jt[J + j], tm.tile[smem_idx(j)]);

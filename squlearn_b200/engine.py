@@ -209,9 +209,10 @@ class Engine:
         with torch.cuda.device(self.device):
             psi = torch.empty((nv, n_samples, 1 << prog.num_qubits), dtype=torch.complex128,
                               device=self.device)
-            # the last gate pass also reduces the row maxima the INT8 Gram's digit slicing needs (one int per
-            # state): a later gram() / slice_states() of exactly this tensor then reads the states once, not twice
-            row_max = torch.empty((nv, n_samples), dtype=torch.int32, device=self.device) \
+            # the last gate pass also reduces the row statistics the INT8 Gram's slicing needs (b200sq_row_stats, 16
+            # bytes per state: row maximum for the digit form, 2-norm for the CRT form): a later gram() /
+            # slice_states() of exactly this tensor then reads the states once, not twice
+            row_max = torch.empty((nv, n_samples, 4), dtype=torch.int32, device=self.device) \
                 if gram_i8_ok(1 << prog.num_qubits) else None
             _lib.check(self._lib.b200sq_simulate_rowmax(
                 cprog.handle, n_samples, xd.shape[1], xd.data_ptr(),
@@ -226,7 +227,7 @@ class Engine:
 
     @staticmethod
     def _row_max_of(psi):
-        """The row maxima simulate() attached to this very tensor, if it has not been written to since."""
+        """The row statistics simulate() attached to this very tensor, if it has not been written to since."""
         tag = getattr(psi, "_b200sq_row_max", None)
         if tag is not None and tag[1] == psi._version and tag[0].shape[0] == psi.shape[0]:
             return tag[0]
@@ -277,7 +278,7 @@ class Engine:
         ``diagonal`` in {"one", "zero", "computed"} then sets the diagonal policy.
         ``precision``: "fp64" (FP64 DMMA), "int8" (split-integer FP64 emulation on the INT8 tcgen05 tensor
         cores: 22 digit-pair products, |dK| ~ 1e-12, north-star bound 1e-10), "crt" (the residue-number form of
-        the same idea: 13 products per entry at 2^16 amplitudes, CRT reconstruction, same bound) or "auto" (crt /
+        the same idea: 11 products per entry at 2^16 amplitudes, CRT reconstruction, same bound) or "auto" (crt /
         int8 where they are faster: 2^n >= 4096 and at least 1024 x 512 entries); default from
         B200SQ_GRAM_PRECISION, else "auto"."""
         torch = self._torch
@@ -501,15 +502,15 @@ class Engine:
     @staticmethod
     def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:
         """Resolve the Gram arithmetic: "fp64" (DMMA), "int8" (digit-slice tcgen05 path) or "crt" (residue-number
-        tcgen05 path: fewer products, more plane memory — 2 x 13 bytes per amplitude instead of 2 x 6)."""
+        tcgen05 path: fewer products, more plane memory — 2 x 11..12 bytes per amplitude component instead of 2 x 6)."""
         if precision is None:
             precision = os.environ.get("B200SQ_GRAM_PRECISION", "auto").lower()
         if precision not in ("fp64", "int8", "crt", "auto"):
             raise ValueError("precision must be 'fp64', 'int8', 'crt' or 'auto'")
         if precision == "auto":
             if dim >= 4096 and nx * ny >= 1024 * 512:
-                # CRT while its planes (2 * 13 * 2 bytes per amplitude and operand) stay below ~48 GiB
-                precision = "crt" if 52.0 * dim * (nx + ny) < 48 * 2.0 ** 30 and dim <= 1 << 18 else "int8"
+                # CRT while its planes (2 * 12 * 2 bytes per amplitude and operand) stay below ~48 GiB
+                precision = "crt" if 48.0 * dim * (nx + ny) < 48 * 2.0 ** 30 and dim <= 1 << 18 else "int8"
             else:
                 precision = "fp64"
         if precision in ("int8", "crt") and (dim < 64 or dim % 8):

@@ -123,41 +123,85 @@ def i8_gram(planes_x, expo_x, planes_y, expo_y):
 
 # ------------------------------------------------------------------------------------------------
 # NumPy restatement of the CRT form of the split-integer Gram (csrc/gram_i8.cu, B200SQ_GRAM_CRT): residue planes of
-# q = round(v * 2^(40 - e)) modulo pairwise coprime odd p_m <= 255, one exact integer product per modulus, Chinese
-# remainder reconstruction with the kernel's double-double accumulation of k_m / p_m.
-CRT_BITS = 40
-CRT_MODULI = [255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191]
+# q = round(v * 2^(B - e)) modulo pairwise coprime p_m <= 256 (256 and odd numbers), e the smallest integer with
+# 2^(B - e) |row|_2 <= R_eff ~ sqrt(P / 2) (Cauchy-Schwarz keeps every inner product below P / 2), one exact integer
+# product per modulus, Chinese remainder reconstruction with the kernel's double-double accumulation of k_m / p_m.
+CRT_MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193]
+CRT_DIGIT_BITS = 46
+CRT_TOL = 1e-10
+
+
+def crt_plan(dim):
+    """(number of moduli, B, e_bias) like crt_plan() of gram_i8.cu."""
+    from decimal import Decimal, getcontext
+
+    getcontext().prec = 60
+    kp = 2 * dim
+    need = int(np.ceil(np.log2(2.0 * np.sqrt(kp) / CRT_TOL)))
+    big = 1
+    for s_ in range(1, len(CRT_MODULI) + 1):
+        big *= CRT_MODULI[s_ - 1]
+        r_eff = (Decimal(big) / 2).sqrt() - Decimal("0.625") * Decimal(kp).sqrt() - 1
+        if r_eff < 2:
+            continue
+        log2r = float(r_eff.ln() / Decimal(2).ln())
+        bits = min(int(np.floor(log2r)), CRT_DIGIT_BITS - 1)
+        if bits >= need or (s_ == len(CRT_MODULI) and bits >= 30):
+            return s_, bits, bits - log2r
+    raise AssertionError("no CRT plan")
 
 
 def crt_num_moduli(dim):
-    need, have, s_ = 2.0 * CRT_BITS + 2.0 + np.log2(2.0 * dim), 0.0, 0
-    while s_ < len(CRT_MODULI) and have < need:
-        have += np.log2(float(CRT_MODULI[s_]))
-        s_ += 1
-    assert have >= need
-    return s_
+    return crt_plan(dim)[0]
 
 
 def _symres(q, p):
     r = np.mod(q, p)
-    return np.where(r > (p - 1) // 2, r - p, r)
+    return np.where(r > (p - 1) // 2, r - p, r)   # (p = 256: -128 .. 127)
 
 
-def crt_slice(psi):
-    """(planes [2 s, N, 2 D] int8, expo [N] int32) like k_slice_crt."""
+def crt_expo(psi, dim):
+    _, bits, e_bias = crt_plan(dim)
+    n2 = np.sum(np.abs(np.asarray(psi, dtype=np.complex128)) ** 2, axis=1)
+    return np.where(n2 > 0, np.ceil(0.5 * np.log2(np.where(n2 > 0, n2, 1.0)) + e_bias + 1e-9), 0).astype(np.int32)
+
+
+def crt_slice(psi, via_digits=False):
+    """(planes [2 s, N, 2 D] int8, expo [N] int32) like k_slice_crt; ``via_digits``: the integers a receiver derives
+    from the exchange digits (round to CRT_DIGIT_BITS first, then to B bits, ties to even)."""
     psi = np.asarray(psi, dtype=np.complex128)
     n_rows, dim = psi.shape
-    s_ = crt_num_moduli(dim)
+    s_, bits, _ = crt_plan(dim)
     nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
-    m = np.abs(nat).max(axis=1)
-    expo = np.where(m > 0, np.frexp(m)[1], 0).astype(np.int32)
-    q = np.rint(np.ldexp(nat, (CRT_BITS - expo)[:, None])).astype(np.int64)
+    expo = crt_expo(psi, dim)
+    if via_digits:
+        qd = np.rint(np.ldexp(nat, (CRT_DIGIT_BITS - expo)[:, None]))
+        q = np.rint(qd * 2.0 ** -(CRT_DIGIT_BITS - bits)).astype(np.int64)
+    else:
+        q = np.rint(np.ldexp(nat, (bits - expo)[:, None])).astype(np.int64)
     rot = np.empty_like(q)
     rot[:, 0::2], rot[:, 1::2] = -q[:, 1::2], q[:, 0::2]
     planes = np.zeros((2 * s_, n_rows, 2 * dim), dtype=np.int8)
     for mi in range(s_):
         planes[mi] = _symres(q, CRT_MODULI[mi]).astype(np.int8)
         planes[s_ + mi] = _symres(rot, CRT_MODULI[mi]).astype(np.int8)
+    return planes, expo
+
+
+def crt_digits(psi):
+    """(digits [6, N, 2 D] int8, expo [N] int32): the nat digit planes k_slice_crt writes for the multi-GPU exchange,
+    balanced base-256 digits of round(v * 2^(CRT_DIGIT_BITS - e)) with the CRT row exponent."""
+    psi = np.asarray(psi, dtype=np.complex128)
+    n_rows, dim = psi.shape
+    nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
+    expo = crt_expo(psi, dim)
+    q = np.rint(np.ldexp(nat, (CRT_DIGIT_BITS - expo)[:, None])).astype(np.int64)
+    planes = np.zeros((I8_SLICES, n_rows, 2 * dim), dtype=np.int8)
+    for s_ in range(I8_SLICES - 1, 0, -1):
+        d = ((q + 128) & 255) - 128
+        q = (q - d) >> 8
+        planes[s_] = d.astype(np.int8)
+    planes[0] = q.astype(np.int8)
     return planes, expo
 
 
@@ -170,7 +214,8 @@ def crt_gram(planes_x, expo_x, planes_y, expo_y):
         big *= p
     from fractions import Fraction
 
-    scale = float(Fraction(big, 2 ** (2 * CRT_BITS)))
+    bits = crt_plan(planes_x.shape[2] // 2)[1]
+    scale = float(Fraction(big, 2 ** (2 * bits)))
     parts = []
     for half in (0, s_):
         sh = np.zeros((planes_x.shape[1], planes_y.shape[1]))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(names) == sorted(_lib.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.b200sq_abi_version() == 2
+    assert lib.b200sq_abi_version() == 3
 
 
 def test_gate_struct_layout_matches_header():

@@ -258,10 +258,16 @@ def test_sharded_parameter_shift_gloo(tmp_path, world):
 
 def test_crt_scheme_error_on_circuit_states():
     """NumPy restatement of the CRT (residue-number) form of the INT8 Gram against complex128: the only error is the
-    41-bit quantisation of the inputs (no product terms are dropped), and K is exactly symmetric."""
+    B-bit quantisation of the inputs relative to the row norm (no product terms are dropped), and K is exactly
+    symmetric; the worst-case bound 2 sqrt(K') 2^-B of a unit-norm entry stays below 1e-10."""
     from tests.helpers import crt_gram, crt_num_moduli, crt_slice
 
-    assert [crt_num_moduli(1 << n) for n in (6, 12, 16, 20)] == [12, 13, 13, 14]
+    from tests.helpers import crt_plan
+
+    assert [crt_num_moduli(1 << n) for n in (6, 12, 16, 20)] == [10, 11, 11, 12]
+    assert [crt_plan(1 << n)[1] for n in (6, 12, 16, 20)] == [39, 43, 43, 45]
+    for n_ in (6, 12, 16, 18, 20):
+        assert 2.0 * np.sqrt(2.0 ** (n_ + 1)) * 2.0 ** -crt_plan(1 << n_)[1] <= 1e-10
     n = 10
     rng = np.random.default_rng(1)
     X = rng.uniform(-0.95, 0.95, (40, 3))
@@ -269,8 +275,15 @@ def test_crt_scheme_error_on_circuit_states():
     sv = oracle.simulate(oracle.chebyshev_pqc(n, 2, 3), n, X, p)
     sv = np.concatenate([sv, sv[:2], np.eye(1, 2 ** n, 3, dtype=complex)])
     planes, expo = crt_slice(sv)
-    assert planes.shape[0] == 24 and planes.min() >= -127 and planes.max() <= 127
+    assert planes.shape[0] == 22 and np.array_equal(expo[:40], np.zeros(40, dtype=np.int32))
     got = crt_gram(planes, expo, planes, expo)
     want = np.abs(sv.conj() @ sv.T) ** 2
     assert np.max(np.abs(got - want)) < 5e-12
     assert np.array_equal(got, got.T)
+    # rows of any scale (the exponent follows the row norm) and the integers a receiver derives from the exchange digits
+    sv2 = sv * np.array([3.7, 1e-3, 0.49, 17.0] * 11)[:sv.shape[0], None]
+    for via in (False, True):
+        pl2, ex2 = crt_slice(sv2, via_digits=via)
+        got2 = crt_gram(pl2, ex2, pl2, ex2)
+        want2 = np.abs(sv2.conj() @ sv2.T) ** 2
+        assert np.max(np.abs(got2 - want2) / np.maximum(want2.max(axis=0)[None, :] ** 0.5 * want2.max(axis=1)[:, None] ** 0.5, 1e-300)) < 1e-11

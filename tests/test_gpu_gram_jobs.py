@@ -169,27 +169,32 @@ def test_crt_planes_from_digits_agree_between_sender_and_receiver(eng):
     (b200sq_gram_slice_crt_digits), are residues of the SAME integers: the nat halves agree bit for bit, and a Gram block
     from converted planes equals the oracle."""
     import torch
-    from tests.helpers import i8_slice
+    from tests.helpers import crt_digits, crt_slice
 
     dim, n = 2048, 70
     rng = np.random.default_rng(21)
     a = _random_states(rng, n, dim)
+    a[:8] *= np.array([3.0, 0.01, 0.7, 1.9, 1.0, 1e-5, 40.0, 0.26])[:, None]   # rows of any norm
     t = torch.from_numpy(a).cuda()
     _, cplanes, cexpo = eng.alloc_plane_block(n, dim, "crt")
     digits = torch.empty((6, n, 2 * dim), dtype=torch.int8, device="cuda")
     eng.slice_states(t, cplanes, cexpo, 0, "crt", digits=digits)
-    want_digits, want_expo = i8_slice(a)
-    assert np.array_equal(digits.cpu().numpy(), want_digits[:6]) and np.array_equal(cexpo.cpu().numpy(), want_expo)
+    want_digits, want_expo = crt_digits(a)
+    assert np.array_equal(cexpo.cpu().numpy(), want_expo) and np.array_equal(digits.cpu().numpy(), want_digits)
+    assert np.array_equal(cplanes.cpu().numpy(), crt_slice(a, via_digits=True)[0])
     s_ = cplanes.shape[0] // 2
     conv = torch.empty((s_, n, 2 * dim), dtype=torch.int8, device="cuda")
     eng.digits_to_crt(digits, n, 0, n, dim, conv, n, 0)
     assert torch.equal(conv, cplanes[:s_])
     b = _random_states(rng, 33, dim)
-    _, bd, be = eng.alloc_plane_block(33, dim)                      # digit planes of a "remote" block
-    eng.slice_states(torch.from_numpy(b).cuda(), bd, be, 0)
+    _, bplanes, be = eng.alloc_plane_block(33, dim, "crt")          # a "remote" block: only its digits travel
+    bd = torch.empty((6, 33, 2 * dim), dtype=torch.int8, device="cuda")
+    eng.slice_states(torch.from_numpy(b).cuda(), bplanes, be, 0, "crt", digits=bd)
     bconv = torch.empty((s_, 33, 2 * dim), dtype=torch.int8, device="cuda")
     eng.digits_to_crt(bd, 33, 0, 33, dim, bconv, 33, 0)
     k = torch.empty((n, 33), dtype=torch.float64, device="cuda")
     eng.gram_jobs(cplanes, cexpo, [{"x0": 0, "nx": n, "planes_y": bconv, "expo_y": be, "rows_y": 33, "y0": 0, "ny": 33,
                                     "out": k}])
-    assert np.max(np.abs(k.cpu().numpy() - oracle.fidelity_gram_zgemm(a, b, False))) < INT8_TOL
+    want = oracle.fidelity_gram_zgemm(a, b, False)
+    scale = np.sum(np.abs(a) ** 2, axis=1)[:, None]                  # |<x|y>|^2 scales with |x|^2 (|y| = 1)
+    assert np.max(np.abs(k.cpu().numpy() - want) / scale) < INT8_TOL
