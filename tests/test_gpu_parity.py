@@ -264,9 +264,10 @@ def test_gram_int8_matches_fp64_on_circuit_states(sq, executor):
 
 
 def test_row_maxima_from_the_gate_pass_feed_the_digit_slicing(sq, executor):
-    """simulate() tags its output with the per-state maxima the last gate pass reduced (b200sq_simulate_rowmax);
-    gram() / slice_states() of that very tensor then skip their own max sweep.  Same digits, same exponents as the
-    two-sweep slicing of an untagged copy; an in-place write invalidates the tag."""
+    """simulate() tags its output with the per-state statistics the last gate pass reduced (b200sq_simulate_rowmax:
+    b200sq_row_stats = {norm2, max_hi, reserved}); gram() / slice_states() of that very tensor then skip their own
+    sweep.  Same planes, same exponents as the two-sweep slicing of an untagged copy (digit and CRT form); an
+    in-place write invalidates the tag."""
     import torch
 
     n, d, N = 12, 3, 300
@@ -279,12 +280,15 @@ def test_row_maxima_from_the_gate_pass_feed_the_digit_slicing(sq, executor):
         rm = eng._row_max_of(psi)
         assert rm is not None
         want_hi = (psi.view(torch.float64).abs().amax(dim=1).view(torch.int64) >> 32).to(torch.int32)
-        assert torch.equal(rm, want_hi)
-        _, p1, e1 = eng.alloc_plane_block(N, 1 << n)
-        _, p2, e2 = eng.alloc_plane_block(N, 1 << n)
-        eng.slice_states(psi, p1, e1)
-        eng.slice_states(psi.clone(), p2, e2)                        # untagged: two sweeps
-        assert torch.equal(e1, e2) and torch.equal(p1, p2)
+        assert rm.shape == (N, 4) and torch.equal(rm[:, 2], want_hi)
+        norm2 = rm[:, :2].contiguous().view(torch.float64).reshape(N)
+        assert float((norm2 - 1.0).abs().max()) < 1e-13
+        for scheme in ("int8", "crt"):
+            _, p1, e1 = eng.alloc_plane_block(N, 1 << n, scheme)
+            _, p2, e2 = eng.alloc_plane_block(N, 1 << n, scheme)
+            eng.slice_states(psi, p1, e1, 0, scheme)
+            eng.slice_states(psi.clone(), p2, e2, 0, scheme)         # untagged: two sweeps
+            assert torch.equal(e1, e2) and torch.equal(p1, p2), scheme
         k_tag = eng.gram(psi, None, precision="int8")
         k_ref = eng.gram(psi.clone(), None, precision="int8")
         assert float((k_tag - k_ref).abs().max()) < 1e-14
