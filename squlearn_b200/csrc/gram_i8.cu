@@ -70,8 +70,7 @@ constexpr int kStageBytes = 3 * kTileBytes;      // A, Bnat, Brot
 constexpr int kStages = 4;
 constexpr int kChunkK = 16384;                   // bytes of K per int32 accumulation chunk
 constexpr int kMaxClasses = 16, kMaxPairs = 8;
-constexpr int kCrtDigitBits = 46;                 // CRT exchange digits: q46 = round(v * 2^(kCrtDigitBits - e)), e from the row norm
-constexpr int kCrtMaxBits = kCrtDigitBits - 1;    // upper limit of B (the digits must carry at least one guard bit)
+constexpr int kCrtMaxBits = 45;                   // upper limit of B: |q| < 2^46 fits the 6 balanced base-256 exchange digits
 constexpr int kCrtMaxModuli = 16;
 // pairwise coprime moduli (256; 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
 // residues fit int8 (256: -128 stands for +-128), and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
@@ -472,18 +471,31 @@ k_gram_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ I8Ma
                     uint32_t v[32];
                     tmem_ld32(t0 + cb * 32, v);
                     tmem_ld_wait();
-                    if (A.crt) {
-                        // inner product of this K chunk modulo p_m (symmetric residue): stored when the unit covers
-                        // the whole K (the usual case: 128 KiB of K stay exact in int32), else summed over the chunks
+                    if (A.crt && A.n_chunks == 1) {
+                        // the unit covers the whole K (the usual case: 128 KiB of K stay exact in int32): the inner
+                        // products modulo p_m, as symmetric residues, are STORED as int8: W8[tile][modulus][part][row][col]
+                        uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int iv = (int)v[c];
+                            const int r = iv - pm * __double2int_rn((double)iv * inv_pm);   // (p = 256: +128 and -128 are the same byte)
+                            pk[c >> 2] |= ((uint32_t)r & 255u) << (8 * (c & 3));
+                        }
+                        const int col0 = cb * 32;   // Re: [0, MN), Im: [MN, 2 MN)
+                        int8_t* w8 = reinterpret_cast<int8_t*>(A.W) +
+                                     ((size_t)(A.jobs[ji].tile0 + tile) * S.n_classes + ci) * (2 * MN * MN) +
+                                     (size_t)(col0 / MN) * (MN * MN) + (size_t)row * MN + (col0 % MN);
+                        reinterpret_cast<uint4*>(w8)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        reinterpret_cast<uint4*>(w8)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    } else if (A.crt) {
+                        // K cut into chunks: the residues of the chunks are summed (int32 W[tile][modulus][part][col][row])
                         int* wp = wt32 + (size_t)ci * (2 * MN * MN) + (size_t)(cb * 32) * MN;
-                        const bool single = A.n_chunks == 1;
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int iv = (int)v[c];
                             int r = iv - pm * __double2int_rn((double)iv * inv_pm);
                             if (r == 128) r = -128;   // (p = 256 only)
-                            if (single) wp[(size_t)c * MN] = r;
-                            else if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
+                            if (r != 0) atomicAdd(wp + (size_t)c * MN, r);
                         }
                     } else {
                         double* wp = wt + (size_t)(cb * 32) * MN;  // [part][col][row]
@@ -703,9 +715,8 @@ struct CrtPlan {
 };
 
 // `digits` (optional): also write the 6 nat DIGIT planes of the rows ([6][digit_rows][2 dim], what the multi-GPU
-// exchange sends) from the same read of the states: q46 = round(v * 2^(kCrtDigitBits - e)) with the SAME row
-// exponent; the residues are then taken from the integer a receiver reconstructs from those digits
-// (k_digits_to_crt), so every rank works with identical integers for a state.
+// exchange sends) from the same read of the states: the balanced base-256 digits of the SAME integers q, so a
+// receiver's residues (k_digits_to_crt) are bit-identical to the sender's and the exchange costs no precision.
 __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ psi, int64_t plane_rows, int64_t row0,
                                                    int64_t dim, const CrtPlan plan, int8_t* __restrict__ planes,
                                                    int* __restrict__ expo, const RowStats* __restrict__ row_stats,
@@ -739,40 +750,29 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
         expo[row] = e;
     }
     __syncthreads();
-    const double scale = ldexp(1.0, plan.bits - s_e), scale_d = ldexp(1.0, kCrtDigitBits - s_e);
+    const double scale = ldexp(1.0, plan.bits - s_e);
     const size_t plane_stride = (size_t)plane_rows * 2 * dim;
     int8_t* dst_row = planes + (size_t)row * 2 * dim;
     const size_t digit_stride = (size_t)digit_rows * 2 * dim;
     int8_t* dig_row = digits ? digits + (size_t)(digit_row0 + blockIdx.x) * 2 * dim : nullptr;
-    const double drop = ldexp(1.0, -(kCrtDigitBits - plan.bits));
     for (int64_t i0 = (int64_t)threadIdx.x * 8; i0 < dim; i0 += (int64_t)blockDim.x * 8) {
         double q[16];   // (re, im) of 8 amplitudes as exact integers
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = __ldcs(src + i0 + c);
+            q[2 * c] = magic_rint(v.x * scale);
+            q[2 * c + 1] = magic_rint(v.y * scale);
+        }
         if (digits) {
             long long qd[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double2 v = __ldcs(src + i0 + c);
-                const double a = magic_rint(v.x * scale_d), b = magic_rint(v.y * scale_d);
-                qd[2 * c] = (long long)a;
-                qd[2 * c + 1] = (long long)b;
-                // the CRT integer is the digit integer rounded to B bits (ties to even), exactly what a receiver
-                // derives from the digits (k_digits_to_crt)
-                q[2 * c] = magic_rint(a * drop);
-                q[2 * c + 1] = magic_rint(b * drop);
-            }
+            for (int b = 0; b < 16; ++b) qd[b] = (long long)q[b];
 #pragma unroll
             for (int sl = kSlices - 1; sl >= 0; --sl) {
                 uint32_t wd[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int b = 0; b < 16; ++b) wd[b >> 2] = pack_digit(qd[b], wd[b >> 2], b & 3);
                 *reinterpret_cast<uint4*>(dig_row + (size_t)sl * digit_stride + 2 * i0) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double2 v = __ldcs(src + i0 + c);
-                q[2 * c] = magic_rint(v.x * scale);
-                q[2 * c + 1] = magic_rint(v.y * scale);
             }
         }
         double qm[16];
@@ -799,20 +799,19 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 }
 
 // Digit planes -> residue planes, for column blocks that arrive as digit planes (the multi-GPU exchange sends the
-// 6 nat digit planes: 6 instead of s bytes per component; the receiver derives the residues).  The digits hold
-// q46 = round(v 2^(kCrtDigitBits - e)); the CRT integer is q = round(q46 / 2^(kCrtDigitBits - B)) (ties to even), a
-// valid B-bit quantisation of the same amplitude with the same row exponent.  One CTA per row; nat planes only.
+// 6 nat digit planes: 6 instead of s bytes per component; the receiver derives the residues).  The digits are those
+// of the CRT integer q = round(v 2^(B - e)) itself (k_slice_crt), so the residues are the sender's.  nat planes only.
 // (The kernel runs NEXT TO the persistent Gram kernel, which keeps ~28 K registers and 198 KB of shared memory per SM:
 // four components per thread keep it below 48 registers so that several CTAs fit beside it.)
 __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
-                                                          int64_t kbytes, int n_mod, double drop, int8_t* __restrict__ out,
+                                                          int64_t kbytes, int n_mod, int8_t* __restrict__ out,
                                                           int64_t rows_o, int64_t row0_o) {
     const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
     const int8_t* src = digits + (size_t)(row0_d + blockIdx.y) * kbytes;
     int8_t* dst = out + (size_t)(row0_o + blockIdx.y) * kbytes;
     const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (k0 >= kbytes) return;
-    // the digit integer from two 24-bit halves (int32 arithmetic), then rounded to B bits (ties to even)
+    // the integer from two 24-bit halves (int32 arithmetic; exact in a double)
     int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
@@ -827,7 +826,7 @@ __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restri
     double q[4], qm[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        q[b] = magic_rint(fma((double)hi[b], 16777216.0, (double)lo[b]) * drop);
+        q[b] = fma((double)hi[b], 16777216.0, (double)lo[b]);
         qm[b] = q[b] + kRoundMagic;
     }
     for (int mi = 0; mi < n_mod; ++mi) {
@@ -877,6 +876,131 @@ __device__ __forceinline__ double crt_fraction(const int* __restrict__ w, size_t
     return f;
 }
 
+// Final kernel of the usual case (one K chunk per unit): W8[tile][modulus][part][row][col] holds int8 residues.  A
+// thread reconstructs FOUR consecutive columns of one row: one 32-bit load per (modulus, part), all 2 s loads issued
+// before the first use (the int32 form below keeps one load in flight per thread and is latency-bound).  The integer
+// arithmetic is exact, so a diagonal tile is symmetric as computed.
+__global__ void __launch_bounds__(256, 3) k_gram_crt_final8(const int8_t* __restrict__ W8, const __grid_constant__ I8Args A) {
+    __shared__ double sm[32][33];   // [row][col]
+    __shared__ double s_red[2][8];
+    extern __shared__ double2 s_tab[];   // [n_mod][kCrtTabStride]
+    const int n_mod = A.sched.n_classes;
+    for (int t = threadIdx.x; t < n_mod * kCrtTabStride; t += blockDim.x) {
+        const int mi = t / kCrtTabStride, r = t - mi * kCrtTabStride - 128;
+        s_tab[t] = crt_term(r, c_crt_moduli[mi], A.crt_c[mi]);
+    }
+    __syncthreads();
+    int ji = 0;
+    while (ji + 1 < A.n_jobs && (int)blockIdx.x >= A.jobs[ji].tile0 + A.jobs[ji].n_tiles) ++ji;
+    const I8Job& J = A.jobs[ji];
+    int bm, bn;
+    decode_tile(J, (int)blockIdx.x - J.tile0, bm, bn);
+    const int MN = A.mn, nsb = MN / 32;
+    const size_t part = (size_t)MN * MN, mod_stride = 2 * part;
+    const int8_t* wt = W8 + (size_t)blockIdx.x * n_mod * mod_stride;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int lrow = threadIdx.x >> 3, lcol = (threadIdx.x & 7) * 4;   // compute phase: 4 columns of one row
+    const uint32_t flags = J.flags;
+    const bool sym = flags & B200SQ_GRAM_SYMMETRIC;
+    const int64_t nx = J.nx, ny = J.ny, ldk = J.ldk;
+    double* __restrict__ K = J.K;
+    double* __restrict__ Km = sym ? nullptr : J.K_mirror;
+    const int* __restrict__ ex = J.ex + J.row0_a;
+    const int* __restrict__ ey = J.ey + J.row0_b;
+    const double* __restrict__ ayx = J.align_yx;
+    const double* __restrict__ ayy = J.align_yy;
+    double a_ky = 0.0, a_kk = 0.0;
+    for (int sb = blockIdx.y; sb < nsb * nsb; sb += gridDim.y) {   // a tile is shared by gridDim.y CTAs
+        const int sr = sb / nsb, sc = sb - sr * nsb;
+        if ((int64_t)bm * MN + sr * 32 >= nx || (int64_t)bn * MN + sc * 32 >= ny) continue;  // CTA-uniform
+        {
+            const int row = sr * 32 + lrow, col = sc * 32 + lcol;
+            const int64_t i = (int64_t)bm * MN + row;
+            const uint32_t* w0 = reinterpret_cast<const uint32_t*>(wt + (size_t)row * MN + col);
+            uint32_t wre[kCrtMaxModuli], wim[kCrtMaxModuli];
+#pragma unroll
+            for (int mi = 0; mi < kCrtMaxModuli; ++mi)
+                if (mi < n_mod) {
+                    wre[mi] = __ldcs(w0 + (size_t)mi * (mod_stride / 4));
+                    wim[mi] = __ldcs(w0 + (size_t)mi * (mod_stride / 4) + part / 4);
+                }
+            const int e_i = i < nx ? ex[i] : 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t j = (int64_t)bn * MN + col + c;
+                double k = 0.0;
+                if (i < nx && j < ny) {
+                    double rh = 0.0, rl = 0.0, ih = 0.0, il = 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < kCrtMaxModuli; ++mi)
+                        if (mi < n_mod) {
+                            const double2 tr = s_tab[mi * kCrtTabStride + (int)(int8_t)(wre[mi] >> (8 * c)) + 128];
+                            const double2 ti = s_tab[mi * kCrtTabStride + (int)(int8_t)(wim[mi] >> (8 * c)) + 128];
+                            double t = rh + tr.x, bb = t - rh;
+                            rl += ((rh - (t - bb)) + (tr.x - bb)) + tr.y;
+                            rh = t;
+                            t = ih + ti.x;
+                            bb = t - ih;
+                            il += ((ih - (t - bb)) + (ti.x - bb)) + ti.y;
+                            ih = t;
+                        }
+                    double fr = (rh - rint(rh)) + rl, fi = (ih - rint(ih)) + il;
+                    if (fr > 0.5) fr -= 1.0;
+                    if (fr < -0.5) fr += 1.0;
+                    if (fi > 0.5) fi -= 1.0;
+                    if (fi < -0.5) fi += 1.0;
+                    const double re = fr * A.crt_scale, im = fi * A.crt_scale;
+                    k = ldexp(re * re + im * im, 2 * (e_i + ey[j]));
+                    if (sym && bm == bn && i == j) {
+                        if (flags & B200SQ_GRAM_DIAG_ONE) k = 1.0;
+                        else if (flags & B200SQ_GRAM_DIAG_ZERO) k = 0.0;
+                    }
+                    if (ayx) {
+                        const double wgt = sym ? (bm != bn ? 2.0 : 1.0) : J.align_weight;
+                        a_ky = fma(wgt * k, ayx[i] * ayy[j], a_ky);
+                        a_kk = fma(wgt * k, k, a_kk);
+                    }
+                }
+                sm[lrow][lcol + c] = k;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            {   // direct: K[i][j], consecutive threads -> consecutive j
+                const int row = sr * 32 + ty + 8 * qd, col = sc * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) K[i * ldk + j] = sm[ty + 8 * qd][tx];
+            }
+            if (sym && bm != bn) {  // mirror: K[j][i], consecutive threads -> consecutive i
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) K[j * ldk + i] = sm[tx][ty + 8 * qd];
+            } else if (Km) {        // transpose of a rectangular block for the owner of its columns
+                const int col = sc * 32 + ty + 8 * qd, row = sr * 32 + tx;
+                const int64_t i = (int64_t)bm * MN + row, j = (int64_t)bn * MN + col;
+                if (i < nx && j < ny) Km[j * J.ldm + i] = sm[tx][ty + 8 * qd];
+            }
+        }
+        __syncthreads();
+    }
+    if (Km) __threadfence_system();
+    if (ayx) {
+        for (int o = 16; o > 0; o >>= 1) {
+            a_ky += __shfl_xor_sync(0xffffffffu, a_ky, o);
+            a_kk += __shfl_xor_sync(0xffffffffu, a_kk, o);
+        }
+        if (tx == 0) { s_red[0][ty] = a_ky; s_red[1][ty] = a_kk; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+            atomicAdd(J.align_out + threadIdx.x, t);
+        }
+    }
+}
+
+// Final kernel when K is cut into chunks: W[tile][modulus][part][col][row] holds int32 sums of chunk residues.
 __global__ void __launch_bounds__(256) k_gram_crt_final(const int* __restrict__ W, const __grid_constant__ I8Args A) {
     __shared__ double sm[32][33];
     __shared__ double s_red[2][8];
@@ -1071,9 +1195,8 @@ static CrtPlan crt_plan(int64_t dim) {
     long double P = 1.0L;
     for (int s = 1; s <= kCrtMaxModuli; ++s) {
         P *= (long double)h_crt_moduli[s - 1];
-        // every component of q is off by at most 5/8 (rounding, twice when the digits are rounded first):
-        // |q|_2 <= 2^(B - e) |x|_2 + 0.625 sqrt(K')
-        const long double r_eff = sqrtl(P / 2.0L) - 0.625L * sqrtl((long double)kp) - 1.0L;
+        // every component of q is off by at most 1/2 (rounding): |q|_2 <= 2^(B - e) |x|_2 + sqrt(K') / 2
+        const long double r_eff = sqrtl(P / 2.0L) - 0.5L * sqrtl((long double)kp) - 1.0L;
         if (r_eff < 2.0L) continue;
         const int bits = std::min((int)floorl(log2l(r_eff)), kCrtMaxBits);
         if (bits >= need || (s == kCrtMaxModuli && bits >= 30)) {
@@ -1110,8 +1233,7 @@ int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, i
     if (pl.n_mod <= 0) return (int)cudaErrorInvalidValue;
     const int64_t kbytes = 2 * dim;
     const dim3 grid((unsigned)((kbytes / 4 + 255) / 256), (unsigned)n);
-    k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, pl.n_mod, ldexp(1.0, -(kCrtDigitBits - pl.bits)),
-                                              out, rows_o, row0_o);
+    k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, pl.n_mod, out, rows_o, row0_o);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -1330,7 +1452,7 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
         J.map_b = m;
         ++a.n_jobs;
     }
-    const size_t wbytes = crt ? (size_t)a.n_tiles * n_mod * 2 * a.mn * a.mn * sizeof(int)
+    const size_t wbytes = crt ? (size_t)a.n_tiles * n_mod * 2 * a.mn * a.mn * (a.n_chunks == 1 ? sizeof(int8_t) : sizeof(int))
                               : (size_t)a.n_tiles * 2 * a.mn * a.mn * sizeof(double);
     if ((e = cudaMallocAsync(&W, wbytes, stream)) != cudaSuccess) { cleanup(); return (int)e; }
     a.W = W;
@@ -1370,8 +1492,17 @@ int launch_gram_jobs(const int8_t* px, const int* ex, int64_t rows_x, int64_t di
             return (int)e;
         }
         const int split = a.mn == 256 ? 4 : 2;   // CTAs per tile: enough of them to fill the machine
-        k_gram_crt_final<<<dim3((unsigned)a.n_tiles, (unsigned)split), 256, tab_bytes, stream>>>(
-            reinterpret_cast<const int*>(W), a);
+        if (a.n_chunks == 1) {
+            if ((e = cudaFuncSetAttribute(k_gram_crt_final8, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes)) != cudaSuccess) {
+                cleanup();
+                return (int)e;
+            }
+            k_gram_crt_final8<<<dim3((unsigned)a.n_tiles, (unsigned)split), 256, tab_bytes, stream>>>(
+                reinterpret_cast<const int8_t*>(W), a);
+        } else {
+            k_gram_crt_final<<<dim3((unsigned)a.n_tiles, (unsigned)split), 256, tab_bytes, stream>>>(
+                reinterpret_cast<const int*>(W), a);
+        }
     }
     else k_gram_i8_final<<<a.n_tiles, 256, 0, stream>>>(W, a);
     count_launch();

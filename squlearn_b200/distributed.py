@@ -23,7 +23,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 
-def _mark(name):  # phase hook for tools/dist_breakdown.py (no-op in production)
+def _mark(name, stream=None):  # phase hook for tools/dist_breakdown.py / dist_timeline.py (no-op in production)
     pass
 
 
@@ -284,6 +284,7 @@ class ShardedFidelityKernel:
         else:
             eng.slice_states(psi_local, planes, expo, 0)
         del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+        _mark("sliced")
 
         if mode == "ipc":
             peer["epoch"] += 1
@@ -304,6 +305,7 @@ class ShardedFidelityKernel:
                 eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
             peer["pushed"] = torch.cuda.Event()
             peer["pushed"].record(st)
+            _mark("pushed", st)
             epoch_t.record_stream(st)
             flags_ptr = arena.data_ptr() + peer["offs"]["flags"]
             n = rows.shape[1]
@@ -374,6 +376,7 @@ class ShardedFidelityKernel:
                           "mirror": j.get("mirror")})
         if glist:
             eng.gram_jobs(a_planes, a_expo, glist)
+        _mark("gram")
         if mode == "ipc" and store_mirror:
             # tell every owner that its mirrored blocks are stored; wait for the ranks that store into my rows
             for q in sorted({j["owner"] for j in mine}):
@@ -410,6 +413,7 @@ class ShardedFidelityKernel:
                     eng.digits_to_crt(j["planes_y"], j["rows_y"], j["y0"], w, dim, conv, w, 0)
                     eng.copy_async(cflags.data_ptr() + 4 * j["owner"], epoch_t.data_ptr(), 4, cs)
                 j["ready"] = (cflags.data_ptr() + 4 * j["owner"], j["ready"][1])
+                _mark("converted", cs)
             else:
                 eng.digits_to_crt(j["planes_y"], j["rows_y"], j["y0"], w, dim, conv, w, 0)
             j["planes_y"], j["expo_y"], j["rows_y"], j["y0"] = conv, expo_ptr, w, 0

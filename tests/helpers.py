@@ -127,7 +127,7 @@ def i8_gram(planes_x, expo_x, planes_y, expo_y):
 # 2^(B - e) |row|_2 <= R_eff ~ sqrt(P / 2) (Cauchy-Schwarz keeps every inner product below P / 2), one exact integer
 # product per modulus, Chinese remainder reconstruction with the kernel's double-double accumulation of k_m / p_m.
 CRT_MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193]
-CRT_DIGIT_BITS = 46
+CRT_MAX_BITS = 45
 CRT_TOL = 1e-10
 
 
@@ -141,11 +141,11 @@ def crt_plan(dim):
     big = 1
     for s_ in range(1, len(CRT_MODULI) + 1):
         big *= CRT_MODULI[s_ - 1]
-        r_eff = (Decimal(big) / 2).sqrt() - Decimal("0.625") * Decimal(kp).sqrt() - 1
+        r_eff = (Decimal(big) / 2).sqrt() - Decimal("0.5") * Decimal(kp).sqrt() - 1
         if r_eff < 2:
             continue
         log2r = float(r_eff.ln() / Decimal(2).ln())
-        bits = min(int(np.floor(log2r)), CRT_DIGIT_BITS - 1)
+        bits = min(int(np.floor(log2r)), CRT_MAX_BITS)
         if bits >= need or (s_ == len(CRT_MODULI) and bits >= 30):
             return s_, bits, bits - log2r
     raise AssertionError("no CRT plan")
@@ -166,19 +166,14 @@ def crt_expo(psi, dim):
     return np.where(n2 > 0, np.ceil(0.5 * np.log2(np.where(n2 > 0, n2, 1.0)) + e_bias + 1e-9), 0).astype(np.int32)
 
 
-def crt_slice(psi, via_digits=False):
-    """(planes [2 s, N, 2 D] int8, expo [N] int32) like k_slice_crt; ``via_digits``: the integers a receiver derives
-    from the exchange digits (round to CRT_DIGIT_BITS first, then to B bits, ties to even)."""
+def crt_slice(psi):
+    """(planes [2 s, N, 2 D] int8, expo [N] int32) like k_slice_crt."""
     psi = np.asarray(psi, dtype=np.complex128)
     n_rows, dim = psi.shape
     s_, bits, _ = crt_plan(dim)
     nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
     expo = crt_expo(psi, dim)
-    if via_digits:
-        qd = np.rint(np.ldexp(nat, (CRT_DIGIT_BITS - expo)[:, None]))
-        q = np.rint(qd * 2.0 ** -(CRT_DIGIT_BITS - bits)).astype(np.int64)
-    else:
-        q = np.rint(np.ldexp(nat, (bits - expo)[:, None])).astype(np.int64)
+    q = np.rint(np.ldexp(nat, (bits - expo)[:, None])).astype(np.int64)
     rot = np.empty_like(q)
     rot[:, 0::2], rot[:, 1::2] = -q[:, 1::2], q[:, 0::2]
     planes = np.zeros((2 * s_, n_rows, 2 * dim), dtype=np.int8)
@@ -190,12 +185,12 @@ def crt_slice(psi, via_digits=False):
 
 def crt_digits(psi):
     """(digits [6, N, 2 D] int8, expo [N] int32): the nat digit planes k_slice_crt writes for the multi-GPU exchange,
-    balanced base-256 digits of round(v * 2^(CRT_DIGIT_BITS - e)) with the CRT row exponent."""
+    balanced base-256 digits of the CRT integers q = round(v * 2^(B - e)) themselves."""
     psi = np.asarray(psi, dtype=np.complex128)
     n_rows, dim = psi.shape
     nat = np.stack([psi.real, psi.imag], axis=2).reshape(n_rows, 2 * dim)
     expo = crt_expo(psi, dim)
-    q = np.rint(np.ldexp(nat, (CRT_DIGIT_BITS - expo)[:, None])).astype(np.int64)
+    q = np.rint(np.ldexp(nat, (crt_plan(dim)[1] - expo)[:, None])).astype(np.int64)
     planes = np.zeros((I8_SLICES, n_rows, 2 * dim), dtype=np.int8)
     for s_ in range(I8_SLICES - 1, 0, -1):
         d = ((q + 128) & 255) - 128

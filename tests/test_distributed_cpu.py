@@ -280,10 +280,19 @@ def test_crt_scheme_error_on_circuit_states():
     want = np.abs(sv.conj() @ sv.T) ** 2
     assert np.max(np.abs(got - want)) < 5e-12
     assert np.array_equal(got, got.T)
-    # rows of any scale (the exponent follows the row norm) and the integers a receiver derives from the exchange digits
+    # rows of any scale: the exponent follows the row norm
     sv2 = sv * np.array([3.7, 1e-3, 0.49, 17.0] * 11)[:sv.shape[0], None]
-    for via in (False, True):
-        pl2, ex2 = crt_slice(sv2, via_digits=via)
-        got2 = crt_gram(pl2, ex2, pl2, ex2)
-        want2 = np.abs(sv2.conj() @ sv2.T) ** 2
-        assert np.max(np.abs(got2 - want2) / np.maximum(want2.max(axis=0)[None, :] ** 0.5 * want2.max(axis=1)[:, None] ** 0.5, 1e-300)) < 1e-11
+    pl2, ex2 = crt_slice(sv2)
+    got2 = crt_gram(pl2, ex2, pl2, ex2)
+    want2 = np.abs(sv2.conj() @ sv2.T) ** 2
+    n2 = np.sum(np.abs(sv2) ** 2, axis=1)
+    assert np.max(np.abs(got2 - want2) / (n2[:, None] * n2[None, :])) < 1e-11
+    # the exchange digits are the digits of the same integers
+    from tests.helpers import crt_digits
+
+    dg, ex3 = crt_digits(sv2)
+    q = sum(dg[s_].astype(np.int64) << (8 * (5 - s_)) for s_ in range(6))
+    assert np.array_equal(ex3, ex2)
+    for mi, p_ in enumerate(__import__("tests.helpers", fromlist=["CRT_MODULI"]).CRT_MODULI[:pl2.shape[0] // 2]):
+        r = np.mod(q, p_)
+        assert np.array_equal(np.where(r > (p_ - 1) // 2, r - p_, r).astype(np.int8), pl2[mi])

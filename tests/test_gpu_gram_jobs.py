@@ -181,7 +181,7 @@ def test_crt_planes_from_digits_agree_between_sender_and_receiver(eng):
     eng.slice_states(t, cplanes, cexpo, 0, "crt", digits=digits)
     want_digits, want_expo = crt_digits(a)
     assert np.array_equal(cexpo.cpu().numpy(), want_expo) and np.array_equal(digits.cpu().numpy(), want_digits)
-    assert np.array_equal(cplanes.cpu().numpy(), crt_slice(a, via_digits=True)[0])
+    assert np.array_equal(cplanes.cpu().numpy(), crt_slice(a)[0])
     s_ = cplanes.shape[0] // 2
     conv = torch.empty((s_, n, 2 * dim), dtype=torch.int8, device="cuda")
     eng.digits_to_crt(digits, n, 0, n, dim, conv, n, 0)
