@@ -801,43 +801,55 @@ __global__ void __launch_bounds__(256) k_slice_crt(const double2* __restrict__ p
 // Digit planes -> residue planes, for column blocks that arrive as digit planes (the multi-GPU exchange sends the
 // 6 nat digit planes: 6 instead of s bytes per component; the receiver derives the residues).  The digits are those
 // of the CRT integer q = round(v 2^(B - e)) itself (k_slice_crt), so the residues are the sender's.  nat planes only.
-// (The kernel runs NEXT TO the persistent Gram kernel, which keeps ~28 K registers and 198 KB of shared memory per SM:
-// four components per thread keep it below 48 registers so that several CTAs fit beside it.)
+// The kernel runs NEXT TO the persistent Gram kernel, which keeps ~30 K registers and 198 KB of shared memory per SM:
+// at most 64 registers per thread let two CTAs fit beside it, and every thread fetches kConvCols independent words
+// of each digit plane (24 loads in flight) before it starts to compute, because with so few resident warps the
+// kernel is bound by the number of bytes in flight, not by arithmetic (measured on 8 GPUs: the conversions, not the
+// NVLink pushes, were the critical path of the exchange).
+constexpr int kConvCols = 4;
 __global__ void __launch_bounds__(256, 4) k_digits_to_crt(const int8_t* __restrict__ digits, int64_t rows_d, int64_t row0_d,
                                                           int64_t kbytes, int n_mod, int8_t* __restrict__ out,
                                                           int64_t rows_o, int64_t row0_o) {
     const size_t stride_d = (size_t)rows_d * kbytes, stride_o = (size_t)rows_o * kbytes;
     const int8_t* src = digits + (size_t)(row0_d + blockIdx.y) * kbytes;
     int8_t* dst = out + (size_t)(row0_o + blockIdx.y) * kbytes;
-    const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (k0 >= kbytes) return;
-    // the integer from two 24-bit halves (int32 arithmetic; exact in a double)
-    int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    const int64_t kb0 = ((int64_t)blockIdx.x * kConvCols * blockDim.x + threadIdx.x) * 4;   // word u: kb0 + u * 4 * blockDim.x
+    uint32_t wd[kConvCols][kSlices];
 #pragma unroll
-    for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
-        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(src + (size_t)sl * stride_d + k0));
+    for (int u = 0; u < kConvCols; ++u) {
+        const int64_t k0 = kb0 + (int64_t)u * 4 * blockDim.x;
+#pragma unroll
+        for (int sl = 0; sl < kSlices; ++sl)
+            wd[u][sl] = k0 < kbytes ? __ldcs(reinterpret_cast<const uint32_t*>(src + (size_t)sl * stride_d + k0)) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kConvCols; ++u) {
+        const int64_t k0 = kb0 + (int64_t)u * 4 * blockDim.x;
+        if (k0 >= kbytes) break;
+        // the integer from two 24-bit halves (int32 arithmetic; exact in a double)
+        double q[4], qm[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int d = (int)(int8_t)((w >> (8 * b)) & 255u);
-            if (sl < 3) hi[b] = hi[b] * 256 + d;
-            else lo[b] = lo[b] * 256 + d;
-        }
-    }
-    double q[4], qm[4];
+            int hi = 0, lo = 0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        q[b] = fma((double)hi[b], 16777216.0, (double)lo[b]);
-        qm[b] = q[b] + kRoundMagic;
-    }
-    for (int mi = 0; mi < n_mod; ++mi) {
-        const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
-        uint32_t wn = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int r = crt_residue(q[b], qm[b], pm, inv);
-            wn |= ((uint32_t)r & 255u) << (8 * b);
+            for (int sl = 0; sl < kSlices; ++sl) {   // most significant digit first
+                const int d = (int)(int8_t)((wd[u][sl] >> (8 * b)) & 255u);
+                if (sl < 3) hi = hi * 256 + d;
+                else lo = lo * 256 + d;
+            }
+            q[b] = fma((double)hi, 16777216.0, (double)lo);
+            qm[b] = q[b] + kRoundMagic;
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)mi * stride_o + k0) = wn;
+        for (int mi = 0; mi < n_mod; ++mi) {
+            const double pm = (double)c_crt_moduli[mi], inv = c_crt_inv[mi];
+            uint32_t wn = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int r = crt_residue(q[b], qm[b], pm, inv);
+                wn |= ((uint32_t)r & 255u) << (8 * b);
+            }
+            *reinterpret_cast<uint32_t*>(dst + (size_t)mi * stride_o + k0) = wn;
+        }
     }
 }
 
@@ -1232,7 +1244,7 @@ int launch_digits_to_crt(const int8_t* digits, int64_t rows_d, int64_t row0_d, i
     const CrtPlan pl = crt_plan(dim);
     if (pl.n_mod <= 0) return (int)cudaErrorInvalidValue;
     const int64_t kbytes = 2 * dim;
-    const dim3 grid((unsigned)((kbytes / 4 + 255) / 256), (unsigned)n);
+    const dim3 grid((unsigned)((kbytes / 4 + 256 * kConvCols - 1) / (256 * kConvCols)), (unsigned)n);
     k_digits_to_crt<<<grid, 256, 0, stream>>>(digits, rows_d, row0_d, kbytes, pl.n_mod, out, rows_o, row0_o);
     count_launch();
     return (int)cudaGetLastError();

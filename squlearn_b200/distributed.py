@@ -98,8 +98,9 @@ def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
 
 
 def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_local: int = 0, n: int = 0,
-                 align: int = 1024):
-    """Receive arena of a rank: one slot [6 nat planes | row exponents] per off-diagonal job, in arrival order,
+                 align: int = 1024, n_planes: int = 6):
+    """Receive arena of a rank: one slot [n_planes nat planes | row exponents] per off-diagonal job (6 digit planes,
+    or the s residue planes when residues travel), in arrival order,
     then the arrival flags, the "mirrored blocks stored" flags and the rank's row block K[r0:r1, :] itself (peers
     store the transposes of their blocks straight into it).  Returns ([{"owner", "cols", "rows", "off",
     "expo_off"}], {"flags", "done", "rows", "total"} byte offsets); every rank computes the layout of every other
@@ -109,7 +110,7 @@ def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_lo
     mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
     for j in mine:
         w = j["cols"][1] - j["cols"][0]
-        nb = 6 * w * 2 * dim
+        nb = n_planes * w * 2 * dim
         slots.append({"owner": j["owner"], "cols": j["cols"], "rows": w, "off": off, "expo_off": off + nb})
         off = (off + nb + 4 * w + align - 1) // align * align
     flags_off = off
@@ -167,18 +168,18 @@ class ShardedFidelityKernel:
             raise ValueError("B200SQ_DIST_EXCHANGE must be auto, ipc, p2p or allgather")
         return mode
 
-    def _peer_setup(self, eng, parts, jobs, dim):
+    def _peer_setup(self, eng, parts, jobs, dim, n_planes=6):
         """Arena, flags, the shared row block and the peer mappings of the ipc exchange (cached while the shapes
-        stay the same)."""
+        stay the same).  ``n_planes``: nat planes per exchanged block (6 digit planes or the s residue planes)."""
         import torch
 
         dist = self._dist
-        key = (tuple(parts), dim)
+        key = (tuple(parts), dim, n_planes)
         if self._peer is not None and self._peer["key"] == key:
             return self._peer
         self._peer_close()
         n = parts[-1][1]
-        lay = lambda q: arena_layout(jobs[q], q, self.world, dim, parts[q][1] - parts[q][0], n)
+        lay = lambda q: arena_layout(jobs[q], q, self.world, dim, parts[q][1] - parts[q][0], n, n_planes=n_planes)
         slots, offs = lay(self.rank)
         arena = eng.alloc_bytes(offs["total"])
         arena[offs["flags"]:offs["rows"]].zero_()
@@ -262,14 +263,26 @@ class ShardedFidelityKernel:
         # with digits_to_crt, on a side stream, as the block lands.
         scheme = eng.gram_precision(parts[-1][1], parts[-1][1], dim, self.precision)
         crt = scheme == "crt" and hasattr(eng, "digits_to_crt")
+        # CRT + ipc on few ranks: the s nat RESIDUE planes travel instead of the 6 digit planes.  That is s / 6 times
+        # the bytes but no conversion at the receiver; with two ranks the pushes hide completely behind the diagonal
+        # block while a conversion would run next to (and be starved by) the busy Gram kernel.  From three ranks on
+        # the exchange is the critical path and the digits travel (B200SQ_DIST_CRT_EXCHANGE = auto | digits | residues).
+        xch = os.environ.get("B200SQ_DIST_CRT_EXCHANGE", "auto").lower()
+        if xch not in ("auto", "digits", "residues"):
+            raise ValueError("B200SQ_DIST_CRT_EXCHANGE must be auto, digits or residues")
+        residues = crt and mode == "ipc" and (xch == "residues" or (xch == "auto" and self.world <= 2))
+        n_xch = eng.plane_count(dim, "crt") if residues else 6
         if crt:   # residue planes for the local rows + their 6 nat digit planes for the exchange, from ONE read
-            buf_local, planes, expo = self._nat_block(eng, "local_nat", n_local, dim)
             _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
+            if residues:
+                buf_local, planes, expo = None, a_planes, a_expo
+            else:
+                buf_local, planes, expo = self._nat_block(eng, "local_nat", n_local, dim)
         else:
             buf_local, planes, expo = self._plane_block(eng, "local", n_local, dim)
             a_planes, a_expo = planes, expo      # row operand of the Gram jobs
         if mode == "ipc":
-            peer = self._peer_setup(eng, parts, jobs, dim)
+            peer = self._peer_setup(eng, parts, jobs, dim, n_xch)
             if peer["pushed"] is not None:   # my previous pushes read the local planes
                 torch.cuda.current_stream(eng.device).wait_event(peer["pushed"])
             rows = peer["rows"]              # peers store their mirrored blocks into this (shared) row block
@@ -279,7 +292,7 @@ class ShardedFidelityKernel:
         psi_local = self.kernel.states(x[r0:r1]).contiguous()
         _mark("states")
         if crt:
-            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt", digits=planes)
+            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt", digits=None if residues else planes)
             expo = a_expo
         else:
             eng.slice_states(psi_local, planes, expo, 0)
@@ -296,10 +309,10 @@ class ShardedFidelityKernel:
             kb = 2 * dim
             for p in peer["pushes"]:     # nearest consumer first
                 w = p["b"] - p["a"]
-                if w == n_local:         # the whole block: its 6 nat planes are contiguous
-                    eng.copy_async(p["dst"], planes.data_ptr(), nat_bytes, st)
+                if w == n_local:         # the whole block: its nat planes are contiguous
+                    eng.copy_async(p["dst"], planes.data_ptr(), n_xch * n_local * kb, st)
                 else:                    # a row range (antipodal split): one copy per plane
-                    for s_ in range(6):
+                    for s_ in range(n_xch):
                         eng.copy_async(p["dst"] + s_ * w * kb, planes[s_, p["a"]].data_ptr(), w * kb, st)
                 eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
                 eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
@@ -364,7 +377,7 @@ class ShardedFidelityKernel:
         if n_local:
             glist.append({"x0": 0, "nx": n_local, "planes_y": a_planes, "expo_y": a_expo, "rows_y": n_local, "y0": 0,
                           "ny": n_local, "out": rows[:, r0:r1], "symmetric": True, "diagonal": self.diagonal})
-        if crt and mine:
+        if crt and mine and not residues:
             self._convert_blocks(eng, mine, dim, mode, peer if mode == "ipc" else None,
                                  epoch_t if mode == "ipc" else None)
         for j in mine:
