@@ -296,6 +296,10 @@ B200SQ_API int b200sq_ipc_export(const void* dev_ptr, void* handle_out_64, int64
 B200SQ_API int b200sq_ipc_open(const void* handle_64, void** base_out);
 B200SQ_API int b200sq_ipc_close(void* base);
 B200SQ_API int b200sq_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+/* n_planes copies of `bytes` bytes each, plane p from src + p * src_pitch to dst + p * dst_pitch: a row range of
+ * every plane of a plane set in one call (one copy-engine copy per plane).                                */
+B200SQ_API int b200sq_copy_planes_async(void* dst_dev, size_t dst_pitch, const void* src_dev, size_t src_pitch,
+                                        size_t bytes, int n_planes, void* stream);
 
 /* Gaussian outer kernel of the projected quantum kernel: K[i][j] = exp(-gamma |F_x[i]-F_y[j]|^2)
  * (src/squlearn/kernel/lowlevel_kernel/projected_quantum_kernel.py:945-973).

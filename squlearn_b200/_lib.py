@@ -74,7 +74,7 @@ EXPORTS = [
     "b200sq_gram_rowmax", "b200sq_gram_slice_rowmax", "b200sq_simulate_expvals2", "b200sq_gram_crt_moduli", "b200sq_gram_crt_bits",
     "b200sq_gram_slice_crt", "b200sq_gram_slice_crt_digits", "b200sq_gram_digits_to_crt", "b200sq_simulate_expvals", "b200sq_expvals",
     "b200sq_gram", "b200sq_gram_planes_bytes", "b200sq_gram_slice", "b200sq_gram_from_planes", "b200sq_gram_jobs", "b200sq_wait_flags", "b200sq_gram_ready_timeouts", "b200sq_ipc_export", "b200sq_ipc_open", "b200sq_ipc_close",
-    "b200sq_copy_async", "b200sq_rbf",
+    "b200sq_copy_async", "b200sq_copy_planes_async", "b200sq_rbf",
     "b200sq_launch_count",
 ]
 
@@ -164,6 +164,8 @@ def load():
     lib.b200sq_ipc_close.argtypes = [vp]
     lib.b200sq_copy_async.restype = c.c_int
     lib.b200sq_copy_async.argtypes = [vp, vp, c.c_size_t, vp]
+    lib.b200sq_copy_planes_async.restype = c.c_int
+    lib.b200sq_copy_planes_async.argtypes = [vp, c.c_size_t, vp, c.c_size_t, c.c_size_t, c.c_int, vp]
     lib.b200sq_rbf.restype = c.c_int
     lib.b200sq_rbf.argtypes = [vp, i64, vp, i64, c.c_int, dbl, vp, i64, vp]
     if lib.b200sq_abi_version() != 3:

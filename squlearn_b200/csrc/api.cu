@@ -643,6 +643,21 @@ int b200sq_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* st
     return 0;
 }
 
+int b200sq_copy_planes_async(void* dst_dev, size_t dst_pitch, const void* src_dev, size_t src_pitch, size_t bytes,
+                             int n_planes, void* stream_) {
+    if (bytes == 0 || n_planes <= 0) return 0;
+    if (!dst_dev || !src_dev) return fail(2, "NULL argument");
+    for (int p = 0; p < n_planes; ++p) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst_dev + (size_t)p * dst_pitch, (const char*)src_dev + (size_t)p * src_pitch,
+                                        bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return cuda_fail(e, "cudaMemcpyAsync (device to device, plane)");
+        }
+    }
+    return 0;
+}
+
 int b200sq_rbf(const double* fx_dev, int64_t Nx, const double* fy_dev, int64_t Ny, int nf, double gamma,
                double* K_dev, int64_t ldk, void* stream_) {
     if (!fx_dev || !fy_dev || !K_dev) return fail(2, "NULL argument");

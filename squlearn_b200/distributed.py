@@ -120,6 +120,34 @@ def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_lo
     return slots, {"flags": flags_off, "done": done_off, "rows": rows_off, "total": total}
 
 
+def push_schedule(pushes: List[dict], bounds: List[Tuple[int, int]], fill: int = 1) -> List[List[tuple]]:
+    """Order of the copy-engine pushes when the local rows become available sub-block by sub-block.
+
+    ``pushes`` (priority order: nearest consumer first) each cover local rows [a, b); ``bounds`` are the sub-blocks in
+    the order they are sliced.  A chunk = (push index, lo, hi, last): rows [lo, hi) of that push, ``last`` when it
+    completes the push (its exponents and arrival flag follow).  Stage s lists the chunks issued right after
+    sub-block s has been sliced: the ``1 + fill`` most urgent chunks whose rows exist by then, everything that is left
+    after the last sub-block.  Every row of every push is issued exactly once, a push's chunks in row order."""
+    chunks = []   # (priority, sub, push, lo, hi)
+    for pi, p in enumerate(pushes):
+        for sub, (a, b) in enumerate(bounds):
+            lo, hi = max(a, p["a"]), min(b, p["b"])
+            if hi > lo:
+                chunks.append((pi, sub, lo, hi))
+    left = {pi: sum(1 for c in chunks if c[0] == pi) for pi in range(len(pushes))}
+    done, stages = set(), []
+    for s in range(len(bounds)):
+        ready = [c for c in chunks if c[1] <= s and c not in done]   # sorted by (push priority, sub-block)
+        take = ready if s == len(bounds) - 1 else ready[:1 + fill]
+        stage = []
+        for c in take:
+            done.add(c)
+            left[c[0]] -= 1
+            stage.append((c[0], c[2], c[3], left[c[0]] == 0))
+        stages.append(stage)
+    return stages
+
+
 class ShardedFidelityKernel:
     """Fidelity Gram matrix of ``x`` across all ranks of a process group.
 
@@ -263,14 +291,15 @@ class ShardedFidelityKernel:
         # with digits_to_crt, on a side stream, as the block lands.
         scheme = eng.gram_precision(parts[-1][1], parts[-1][1], dim, self.precision)
         crt = scheme == "crt" and hasattr(eng, "digits_to_crt")
-        # CRT + ipc on few ranks: the s nat RESIDUE planes travel instead of the 6 digit planes.  That is s / 6 times
-        # the bytes but no conversion at the receiver; with two ranks the pushes hide completely behind the diagonal
-        # block while a conversion would run next to (and be starved by) the busy Gram kernel.  From three ranks on
-        # the exchange is the critical path and the digits travel (B200SQ_DIST_CRT_EXCHANGE = auto | digits | residues).
+        # CRT + ipc: by default the s nat RESIDUE planes travel instead of the 6 digit planes.  That is s / 6 times the
+        # bytes but no conversion at the receiver: measured on 2, 4 and 8 GPUs (profiles/r2_timeline_*), a conversion
+        # that runs next to the persistent Gram kernel is starved by it (3 - 10 times its stand-alone time) and was the
+        # critical path of every step, while the pushes ride on otherwise idle copy engines
+        # (B200SQ_DIST_CRT_EXCHANGE = auto | digits | residues; auto = residues).
         xch = os.environ.get("B200SQ_DIST_CRT_EXCHANGE", "auto").lower()
         if xch not in ("auto", "digits", "residues"):
             raise ValueError("B200SQ_DIST_CRT_EXCHANGE must be auto, digits or residues")
-        residues = crt and mode == "ipc" and (xch == "residues" or (xch == "auto" and self.world <= 2))
+        residues = crt and mode == "ipc" and xch != "digits"
         n_xch = eng.plane_count(dim, "crt") if residues else 6
         if crt:   # residue planes for the local rows + their 6 nat digit planes for the exchange, from ONE read
             _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
@@ -289,33 +318,64 @@ class ShardedFidelityKernel:
         else:
             rows = torch.zeros((n_local, parts[-1][1]), dtype=torch.float64, device=eng.device
                                if hasattr(eng, "device") else "cpu")
-        psi_local = self.kernel.states(x[r0:r1]).contiguous()
-        _mark("states")
-        if crt:
-            eng.slice_states(psi_local, a_planes, a_expo, 0, "crt", digits=None if residues else planes)
-            expo = a_expo
-        else:
-            eng.slice_states(psi_local, planes, expo, 0)
-        del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
-        _mark("sliced")
-
+        # Residue exchange on three or more ranks: the local rows are simulated, sliced and pushed in SUB-BLOCKS, so
+        # that the copy engines start while the later sub-blocks are still being computed (from three ranks on the
+        # NVLink pushes, not the arithmetic, are the critical path of a step).
+        n_sub = 1
+        if residues:
+            env_sub = os.environ.get("B200SQ_DIST_SUBBLOCKS", "")
+            n_sub = int(env_sub) if env_sub else (4 if self.world >= 3 else 1)
+            n_sub = max(1, min(n_sub, n_local // 64 if n_local >= 64 else 1))
         if mode == "ipc":
             peer["epoch"] += 1
             epoch = peer["epoch"]
             arena, st = peer["arena"], peer["stream"]
             epoch_t = torch.full((1,), epoch, dtype=torch.int32, device=eng.device)
-            peer["sliced"].record(torch.cuda.current_stream(eng.device))
-            st.wait_event(peer["sliced"])
             kb = 2 * dim
-            for p in peer["pushes"]:     # nearest consumer first
-                w = p["b"] - p["a"]
-                if w == n_local:         # the whole block: its nat planes are contiguous
-                    eng.copy_async(p["dst"], planes.data_ptr(), n_xch * n_local * kb, st)
-                else:                    # a row range (antipodal split): one copy per plane
-                    for s_ in range(n_xch):
-                        eng.copy_async(p["dst"] + s_ * w * kb, planes[s_, p["a"]].data_ptr(), w * kb, st)
-                eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
-                eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
+        if n_sub > 1:
+            bounds = [ab for ab in row_partition(n_local, n_sub) if ab[1] > ab[0]]
+            stages = push_schedule(peer["pushes"], bounds, fill=1)
+            main = torch.cuda.current_stream(eng.device)
+            for (a, b), stage in zip(bounds, stages):
+                psi_sub = self.kernel.states(x[r0 + a:r0 + b]).contiguous()
+                eng.slice_states(psi_sub, a_planes, a_expo, a, "crt")
+                del psi_sub
+                ev = torch.cuda.Event()
+                ev.record(main)
+                st.wait_event(ev)
+                for pi, lo, hi, last in stage:
+                    p = peer["pushes"][pi]
+                    w = p["b"] - p["a"]
+                    eng.copy_planes_async(p["dst"] + (lo - p["a"]) * kb, w * kb, planes[0, lo].data_ptr(), n_local * kb,
+                                          (hi - lo) * kb, n_xch, st)
+                    if last:
+                        eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
+                        eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
+            _mark("states")
+            _mark("sliced")
+        else:
+            psi_local = self.kernel.states(x[r0:r1]).contiguous()
+            _mark("states")
+            if crt:
+                eng.slice_states(psi_local, a_planes, a_expo, 0, "crt", digits=None if residues else planes)
+                expo = a_expo
+            else:
+                eng.slice_states(psi_local, planes, expo, 0)
+            del psi_local  # only the planes are needed from here on (16 GiB per rank at n = 20)
+            _mark("sliced")
+
+        if mode == "ipc":
+            if n_sub == 1:
+                peer["sliced"].record(torch.cuda.current_stream(eng.device))
+                st.wait_event(peer["sliced"])
+                for p in peer["pushes"]:     # nearest consumer first
+                    w = p["b"] - p["a"]
+                    if w == n_local:         # the whole block: its nat planes are contiguous
+                        eng.copy_async(p["dst"], planes.data_ptr(), n_xch * n_local * kb, st)
+                    else:                    # a row range (antipodal split): one copy per plane
+                        eng.copy_planes_async(p["dst"], w * kb, planes[0, p["a"]].data_ptr(), n_local * kb, w * kb, n_xch, st)
+                    eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
+                    eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
             peer["pushed"] = torch.cuda.Event()
             peer["pushed"].record(st)
             _mark("pushed", st)

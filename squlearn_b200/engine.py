@@ -499,6 +499,14 @@ class Engine:
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b200sq_copy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), int(nbytes), st))
 
+    def copy_planes_async(self, dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, nbytes: int, n_planes: int,
+                          stream=None):
+        """``n_planes`` copy-engine copies of ``nbytes`` each (plane p: src + p * src_pitch -> dst + p * dst_pitch)."""
+        st = self._stream() if stream is None else ctypes.c_void_p(stream.cuda_stream)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b200sq_copy_planes_async(ctypes.c_void_p(dst_ptr), int(dst_pitch), ctypes.c_void_p(src_ptr),
+                                                          int(src_pitch), int(nbytes), int(n_planes), st))
+
     @staticmethod
     def gram_precision(nx: int, ny: int, dim: int, precision: Optional[str] = None) -> str:
         """Resolve the Gram arithmetic: "fp64" (DMMA), "int8" (digit-slice tcgen05 path) or "crt" (residue-number

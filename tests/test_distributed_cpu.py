@@ -296,3 +296,35 @@ def test_crt_scheme_error_on_circuit_states():
     for mi, p_ in enumerate(__import__("tests.helpers", fromlist=["CRT_MODULI"]).CRT_MODULI[:pl2.shape[0] // 2]):
         r = np.mod(q, p_)
         assert np.array_equal(np.where(r > (p_ - 1) // 2, r - p_, r).astype(np.int8), pl2[mi])
+
+
+def test_push_schedule_covers_every_row_once_and_in_order():
+    """Sub-block pipelining of the residue exchange: every push's rows go out exactly once, in row order, never
+    before the sub-block that holds them has been sliced, and the arrival flag follows the last chunk."""
+    import random
+
+    from squlearn_b200.distributed import push_schedule, row_partition
+
+    rnd = random.Random(7)
+    for _ in range(300):
+        n, ns = rnd.randint(64, 700), rnd.randint(1, 6)
+        pushes = []
+        for _k in range(rnd.randint(1, 5)):
+            a = rnd.randint(0, n - 1)
+            pushes.append({"a": a, "b": rnd.randint(a + 1, n)})
+        bounds = [ab for ab in row_partition(n, ns) if ab[1] > ab[0]]
+        stages = push_schedule(pushes, bounds, fill=rnd.randint(0, 3))
+        assert len(stages) == len(bounds)
+        cov, finished = {pi: [] for pi in range(len(pushes))}, set()
+        for s_, stage in enumerate(stages):
+            for pi, lo, hi, last in stage:
+                assert hi <= bounds[s_][1] and pi not in finished
+                cov[pi].append((lo, hi))
+                if last:
+                    finished.add(pi)
+        for pi, p in enumerate(pushes):
+            assert cov[pi] == sorted(cov[pi]) and cov[pi][0][0] == p["a"] and cov[pi][-1][1] == p["b"]
+            assert all(b == c for (_a, b), (c, _d) in zip(cov[pi], cov[pi][1:])) and pi in finished
+    # the nearest consumer's block completes right after the last sub-block, not after all earlier pushes
+    st = push_schedule([{"a": 0, "b": 512}] * 4, row_partition(512, 4), fill=1)
+    assert st[3][0] == (0, 384, 512, True) and [len(x) for x in st] == [2, 2, 2, 10]

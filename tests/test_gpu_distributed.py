@@ -51,6 +51,18 @@ def _worker(rank, world, port, out_dir, big):
                         save(f"k_{mode}_{rep}", np.array(k))   # copy: the shared host buffer is reused
                 del sh
             os.environ.pop("B200SQ_DIST_EXCHANGE", None)
+            # CRT arithmetic over the ipc exchange: residue planes pushed whole, pushed in sub-blocks while the later
+            # sub-blocks are still being simulated, and digit planes converted by the receiver
+            for tag, env in (("res", {}), ("sub", {"B200SQ_DIST_SUBBLOCKS": "2"}), ("dig", {"B200SQ_DIST_CRT_EXCHANGE": "digits"})):
+                os.environ.update(env)
+                sh = ShardedFidelityKernel(fk, precision="crt")
+                for rep, n_points in enumerate((301, 301, 304)):
+                    k = sh.evaluate(_data(10 + rep, n_points, 3))
+                    if rank == 0:
+                        save(f"k_crt{tag}_{rep}", np.array(k))
+                del sh
+                for key in env:
+                    os.environ.pop(key, None)
             # parameter shift sharded by shifted variant (BASELINE configs[3] shape, fewer samples)
             enc = sq.ChebyshevRx(8, 4, closed=False)
             circ = sq.B200Circuit(enc.get_program(2), sq.SummedPaulis(8))
@@ -114,6 +126,14 @@ def test_sharded_gram_nccl(tmp_path):
             assert np.max(np.abs(got8 - want)) < 1e-10, (mode, rep)
             assert np.array_equal(got8, got8.T), (mode, rep)
             assert np.all(np.diag(got8) == 1.0)
+    for rep, n_points in enumerate((301, 301, 304)):
+        want = oracle.fidelity_kernel(gates, 9, _data(10 + rep, n_points, 3), None, p, pairloop=False)
+        ks = [np.load(tmp_path / f"k_crt{tag}_{rep}.npy") for tag in ("res", "sub", "dig")]
+        for k in ks:
+            assert k.shape == want.shape and np.max(np.abs(k - want)) < 1e-10, rep
+            assert np.array_equal(k, k.T) and np.all(np.diag(k) == 1.0)
+        # the exchange format does not change a single bit: every rank works with the same integers
+        assert np.array_equal(ks[0], ks[1]) and np.array_equal(ks[0], ks[2])
     g, g1 = np.load(tmp_path / "grad_sharded.npy"), np.load(tmp_path / "grad_single.npy")
     assert g.shape == g1.shape == (96, 1, 64)
     assert np.max(np.abs(g - g1)) < 1e-12
