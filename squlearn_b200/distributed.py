@@ -23,6 +23,12 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 
+# Sub-block pipelining of the residue exchange from three ranks on (see ShardedFidelityKernel._rows_planes); chosen
+# from the 4- and 8-GPU timelines under profiles/.
+_DEFAULT_SUBBLOCKS = 4
+_DEFAULT_PIPELINE = "full"
+
+
 def _mark(name, stream=None):  # phase hook for tools/dist_breakdown.py / dist_timeline.py (no-op in production)
     pass
 
@@ -321,11 +327,14 @@ class ShardedFidelityKernel:
         # Residue exchange on three or more ranks: the local rows are simulated, sliced and pushed in SUB-BLOCKS, so
         # that the copy engines start while the later sub-blocks are still being computed (from three ranks on the
         # NVLink pushes, not the arithmetic, are the critical path of a step).
-        n_sub = 1
+        n_sub, sub_sim = 1, True
         if residues:
             env_sub = os.environ.get("B200SQ_DIST_SUBBLOCKS", "")
-            n_sub = int(env_sub) if env_sub else (4 if self.world >= 3 else 1)
+            n_sub = int(env_sub) if env_sub else (_DEFAULT_SUBBLOCKS if self.world >= 3 else 1)
             n_sub = max(1, min(n_sub, n_local // 64 if n_local >= 64 else 1))
+            # "full": simulate, slice and push sub-block by sub-block; "slice": simulate all local rows in one batch
+            # (small batches lose efficiency in the gate passes), slice and push in sub-blocks
+            sub_sim = os.environ.get("B200SQ_DIST_PIPELINE", _DEFAULT_PIPELINE).lower() != "slice"
         if mode == "ipc":
             peer["epoch"] += 1
             epoch = peer["epoch"]
@@ -336,10 +345,17 @@ class ShardedFidelityKernel:
             bounds = [ab for ab in row_partition(n_local, n_sub) if ab[1] > ab[0]]
             stages = push_schedule(peer["pushes"], bounds, fill=1)
             main = torch.cuda.current_stream(eng.device)
+            if not sub_sim:
+                psi_local = self.kernel.states(x[r0:r1]).contiguous()
+                stats = eng.row_stats_of(psi_local)
             for (a, b), stage in zip(bounds, stages):
-                psi_sub = self.kernel.states(x[r0 + a:r0 + b]).contiguous()
-                eng.slice_states(psi_sub, a_planes, a_expo, a, "crt")
-                del psi_sub
+                if sub_sim:
+                    psi_sub = self.kernel.states(x[r0 + a:r0 + b]).contiguous()
+                    eng.slice_states(psi_sub, a_planes, a_expo, a, "crt")
+                    del psi_sub
+                else:
+                    eng.slice_states(psi_local[a:b], a_planes, a_expo, a, "crt",
+                                     stats=stats[a:b] if stats is not None else None)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 st.wait_event(ev)
@@ -351,6 +367,7 @@ class ShardedFidelityKernel:
                     if last:
                         eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
                         eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
+            psi_local = None
             _mark("states")
             _mark("sliced")
         else:

@@ -45,6 +45,8 @@ class CompiledProgram:
 
     def set_params(self, params: Optional[np.ndarray]):
         """New circuit parameters: only the angle coefficients change, the plan is kept."""
+        if params is not None and self.params is not None and np.array_equal(np.asarray(params, dtype=np.float64), self.params):
+            return   # unchanged (every sub-block of a sharded Gram, every step of a benchmark loop)
         c0, c1 = self.program.coefficient_arrays(params)
         n = max(len(c0), 1)
         a0 = (ctypes.c_double * n)(*c0)
@@ -225,6 +227,10 @@ class Engine:
             out._b200sq_row_max = (row_max[0], out._version)
         return out
 
+    def row_stats_of(self, psi):
+        """Row statistics ([N, 4] int32 view of b200sq_row_stats) simulate() attached to ``psi``, or None."""
+        return self._row_max_of(psi) if psi.is_contiguous() else None
+
     @staticmethod
     def _row_max_of(psi):
         """The row statistics simulate() attached to this very tensor, if it has not been written to since."""
@@ -344,12 +350,16 @@ class Engine:
         with torch.cuda.device(self.device):
             return torch.empty((int(nbytes),), dtype=torch.int8, device=self.device)
 
-    def slice_states(self, psi, planes, expo, row0: int = 0, scheme: Optional[str] = None, digits=None):
+    def slice_states(self, psi, planes, expo, row0: int = 0, scheme: Optional[str] = None, digits=None, stats=None):
         """Write the planes of the states ``psi`` into rows [row0, row0 + len(psi)) of ``planes`` (digit slices, or
         CRT residues when ``scheme == "crt"`` / the plane count says so).  ``digits`` (CRT only): a [6][N][2 dim]
-        int8 tensor that receives the nat digit planes of the same states (the multi-GPU exchange format)."""
+        int8 tensor that receives the nat digit planes of the same states (the multi-GPU exchange format).
+        ``stats``: the row statistics of exactly these states (rows of what ``row_stats_of`` returned for the tensor
+        ``psi`` is a row range of); default: the statistics simulate() attached to ``psi`` itself."""
         torch = self._torch
-        rm = self._row_max_of(psi) if psi.is_contiguous() else None
+        rm = stats if stats is not None else (self._row_max_of(psi) if psi.is_contiguous() else None)
+        if rm is not None and (rm.shape[0] != psi.shape[0] or not rm.is_contiguous()):
+            raise ValueError("row statistics do not match the states")
         psi = psi.contiguous()
         if psi.dtype != torch.complex128 or psi.dim() != 2:
             raise ValueError("states must be a (N, 2^n) complex128 array")

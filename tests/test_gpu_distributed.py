@@ -53,7 +53,8 @@ def _worker(rank, world, port, out_dir, big):
             os.environ.pop("B200SQ_DIST_EXCHANGE", None)
             # CRT arithmetic over the ipc exchange: residue planes pushed whole, pushed in sub-blocks while the later
             # sub-blocks are still being simulated, and digit planes converted by the receiver
-            for tag, env in (("res", {}), ("sub", {"B200SQ_DIST_SUBBLOCKS": "2"}), ("dig", {"B200SQ_DIST_CRT_EXCHANGE": "digits"})):
+            for tag, env in (("res", {}), ("sub", {"B200SQ_DIST_SUBBLOCKS": "2"}),
+                             ("slc", {"B200SQ_DIST_SUBBLOCKS": "2", "B200SQ_DIST_PIPELINE": "slice"}), ("dig", {"B200SQ_DIST_CRT_EXCHANGE": "digits"})):
                 os.environ.update(env)
                 sh = ShardedFidelityKernel(fk, precision="crt")
                 for rep, n_points in enumerate((301, 301, 304)):
@@ -128,12 +129,12 @@ def test_sharded_gram_nccl(tmp_path):
             assert np.all(np.diag(got8) == 1.0)
     for rep, n_points in enumerate((301, 301, 304)):
         want = oracle.fidelity_kernel(gates, 9, _data(10 + rep, n_points, 3), None, p, pairloop=False)
-        ks = [np.load(tmp_path / f"k_crt{tag}_{rep}.npy") for tag in ("res", "sub", "dig")]
+        ks = [np.load(tmp_path / f"k_crt{tag}_{rep}.npy") for tag in ("res", "sub", "slc", "dig")]
         for k in ks:
             assert k.shape == want.shape and np.max(np.abs(k - want)) < 1e-10, rep
             assert np.array_equal(k, k.T) and np.all(np.diag(k) == 1.0)
         # the exchange format does not change a single bit: every rank works with the same integers
-        assert np.array_equal(ks[0], ks[1]) and np.array_equal(ks[0], ks[2])
+        assert all(np.array_equal(ks[0], k) for k in ks[1:])
     g, g1 = np.load(tmp_path / "grad_sharded.npy"), np.load(tmp_path / "grad_single.npy")
     assert g.shape == g1.shape == (96, 1, 64)
     assert np.max(np.abs(g - g1)) < 1e-12
