@@ -23,9 +23,11 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 
-# Sub-block pipelining of the residue exchange from three ranks on (see ShardedFidelityKernel._rows_planes); chosen
-# from the 4- and 8-GPU timelines under profiles/.
-_DEFAULT_SUBBLOCKS = 4
+# Sub-block pipelining of the residue exchange (see ShardedFidelityKernel._rows_planes) is OFF by default: measured
+# on 4 and 8 GPUs (profiles/r2_timeline_n{4,8}_variants.log) the per-copy overhead of the many small pushes and the
+# less efficient small simulation batches cost more (8 GPUs: 6.3 - 6.7 ms) than the earlier start saves (5.7 ms with
+# one push per block).
+_DEFAULT_SUBBLOCKS = 1
 _DEFAULT_PIPELINE = "full"
 
 
@@ -96,11 +98,16 @@ def ring_distance(rank: int, owner: int, world: int) -> int:
 
 
 def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
-    """The off-diagonal jobs of ``rank`` in the order their column planes arrive: nearest owner first (every
-    rank pushes its planes to rank-1, rank-2, ... in that order, so the block a rank needs first lands first)."""
+    """The off-diagonal jobs of ``rank`` in the order their column planes arrive: the narrowest block first (the
+    half of an antipodal block lands in half the time, so the Gram kernel has work right after its diagonal block),
+    then nearest owner first (every rank pushes its planes in the same order: see ``_job_order``)."""
     mine = [j for j in jobs[rank] if not j["diag"]]
-    mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
+    mine.sort(key=lambda j: _job_order(j, rank, world))
     return mine
+
+
+def _job_order(j: dict, rank: int, world: int):
+    return (j["cols"][1] - j["cols"][0], ring_distance(rank, j["owner"], world), j["rows"])
 
 
 def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_local: int = 0, n: int = 0,
@@ -113,7 +120,7 @@ def arena_layout(jobs_of_rank: List[dict], rank: int, world: int, dim: int, n_lo
     rank from the job table alone (a sender needs the receiver's offsets)."""
     slots, off = [], 0
     mine = [j for j in jobs_of_rank if not j["diag"]]
-    mine.sort(key=lambda j: (ring_distance(rank, j["owner"], world), j["rows"]))
+    mine.sort(key=lambda j: _job_order(j, rank, world))
     for j in mine:
         w = j["cols"][1] - j["cols"][0]
         nb = n_planes * w * 2 * dim
@@ -245,7 +252,7 @@ class ShardedFidelityKernel:
                                "dst_flag": base + q_offs["flags"] + 4 * self.rank})
                 if q not in writers:
                     writers.append(q)
-        pushes.sort(key=lambda p: (p["dist"], p["q"]))
+        pushes.sort(key=lambda p: (p["b"] - p["a"], p["dist"], p["q"]))   # the consumers' order (_job_order)
         owners = {}    # owner of the columns of one of my jobs -> (its rows pointer, its "done" flag for me)
         for sl in slots:
             q = sl["owner"]
@@ -324,13 +331,12 @@ class ShardedFidelityKernel:
         else:
             rows = torch.zeros((n_local, parts[-1][1]), dtype=torch.float64, device=eng.device
                                if hasattr(eng, "device") else "cpu")
-        # Residue exchange on three or more ranks: the local rows are simulated, sliced and pushed in SUB-BLOCKS, so
-        # that the copy engines start while the later sub-blocks are still being computed (from three ranks on the
-        # NVLink pushes, not the arithmetic, are the critical path of a step).
+        # Optional (B200SQ_DIST_SUBBLOCKS > 1): the local rows are simulated, sliced and pushed in SUB-BLOCKS, so that
+        # the copy engines start while the later sub-blocks are still being computed (see _DEFAULT_SUBBLOCKS).
         n_sub, sub_sim = 1, True
         if residues:
             env_sub = os.environ.get("B200SQ_DIST_SUBBLOCKS", "")
-            n_sub = int(env_sub) if env_sub else (_DEFAULT_SUBBLOCKS if self.world >= 3 else 1)
+            n_sub = int(env_sub) if env_sub else _DEFAULT_SUBBLOCKS
             n_sub = max(1, min(n_sub, n_local // 64 if n_local >= 64 else 1))
             # "full": simulate, slice and push sub-block by sub-block; "slice": simulate all local rows in one batch
             # (small batches lose efficiency in the gate passes), slice and push in sub-blocks
