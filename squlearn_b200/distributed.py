@@ -28,6 +28,8 @@ import numpy as np
 # less efficient small simulation batches cost more (8 GPUs: 6.3 - 6.7 ms) than the earlier start saves (5.7 ms with
 # one push per block).
 _DEFAULT_SUBBLOCKS = 1
+_DEFAULT_PUSH_STREAMS = "1"
+_DEFAULT_ORDER = "narrow"   # order of the exchanged blocks: "narrow" (narrowest block first) or "ring" (nearest owner first)
 _DEFAULT_PIPELINE = "full"
 
 
@@ -107,6 +109,8 @@ def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
 
 
 def _job_order(j: dict, rank: int, world: int):
+    if os.environ.get("B200SQ_DIST_ORDER", _DEFAULT_ORDER).lower() == "ring":   # nearest owner first (A/B measurements)
+        return (0, ring_distance(rank, j["owner"], world), j["rows"])
     return (j["cols"][1] - j["cols"][0], ring_distance(rank, j["owner"], world), j["rows"])
 
 
@@ -215,7 +219,7 @@ class ShardedFidelityKernel:
         import torch
 
         dist = self._dist
-        key = (tuple(parts), dim, n_planes)
+        key = (tuple(parts), dim, n_planes, os.environ.get("B200SQ_DIST_ORDER", _DEFAULT_ORDER).lower())
         if self._peer is not None and self._peer["key"] == key:
             return self._peer
         self._peer_close()
@@ -252,7 +256,8 @@ class ShardedFidelityKernel:
                                "dst_flag": base + q_offs["flags"] + 4 * self.rank})
                 if q not in writers:
                     writers.append(q)
-        pushes.sort(key=lambda p: (p["b"] - p["a"], p["dist"], p["q"]))   # the consumers' order (_job_order)
+        narrow = os.environ.get("B200SQ_DIST_ORDER", _DEFAULT_ORDER).lower() != "ring"
+        pushes.sort(key=lambda p: (p["b"] - p["a"] if narrow else 0, p["dist"], p["q"]))   # the consumers' order (_job_order)
         owners = {}    # owner of the columns of one of my jobs -> (its rows pointer, its "done" flag for me)
         for sl in slots:
             q = sl["owner"]
@@ -264,7 +269,8 @@ class ShardedFidelityKernel:
         rows = arena[offs["rows"]:offs["rows"] + 8 * n_local * n].view(torch.float64).view(n_local, n)
         self._peer = {"key": key, "arena": arena, "slots": slots, "offs": offs, "pushes": pushes, "writers": writers,
                       "owners": owners, "rows": rows, "bases": bases, "epoch": 0,
-                      "stream": torch.cuda.Stream(device=eng.device), "sliced": torch.cuda.Event(), "pushed": None,
+                      "stream": torch.cuda.Stream(device=eng.device), "stream2": torch.cuda.Stream(device=eng.device),
+                      "sliced": torch.cuda.Event(), "pushed": None,
                       "eng": eng}
         return self._peer
 
@@ -325,8 +331,8 @@ class ShardedFidelityKernel:
             a_planes, a_expo = planes, expo      # row operand of the Gram jobs
         if mode == "ipc":
             peer = self._peer_setup(eng, parts, jobs, dim, n_xch)
-            if peer["pushed"] is not None:   # my previous pushes read the local planes
-                torch.cuda.current_stream(eng.device).wait_event(peer["pushed"])
+            for ev in peer["pushed"] or ():   # my previous pushes read the local planes
+                torch.cuda.current_stream(eng.device).wait_event(ev)
             rows = peer["rows"]              # peers store their mirrored blocks into this (shared) row block
         else:
             rows = torch.zeros((n_local, parts[-1][1]), dtype=torch.float64, device=eng.device
@@ -391,7 +397,12 @@ class ShardedFidelityKernel:
             if n_sub == 1:
                 peer["sliced"].record(torch.cuda.current_stream(eng.device))
                 st.wait_event(peer["sliced"])
-                for p in peer["pushes"]:     # nearest consumer first
+                # B200SQ_DIST_PUSH_STREAMS=2: alternate blocks go out on a second stream (two copy engines at a time)
+                two = os.environ.get("B200SQ_DIST_PUSH_STREAMS", _DEFAULT_PUSH_STREAMS) == "2"
+                if two:
+                    peer["stream2"].wait_event(peer["sliced"])
+                for pk, p in enumerate(peer["pushes"]):     # the consumers' order
+                    st = peer["stream2"] if (two and pk % 2 == 1) else peer["stream"]
                     w = p["b"] - p["a"]
                     if w == n_local:         # the whole block: its nat planes are contiguous
                         eng.copy_async(p["dst"], planes.data_ptr(), n_xch * n_local * kb, st)
@@ -399,10 +410,14 @@ class ShardedFidelityKernel:
                         eng.copy_planes_async(p["dst"], w * kb, planes[0, p["a"]].data_ptr(), n_local * kb, w * kb, n_xch, st)
                     eng.copy_async(p["dst_expo"], expo[p["a"]:].data_ptr(), 4 * w, st)
                     eng.copy_async(p["dst_flag"], epoch_t.data_ptr(), 4, st)
-            peer["pushed"] = torch.cuda.Event()
-            peer["pushed"].record(st)
-            _mark("pushed", st)
-            epoch_t.record_stream(st)
+            peer["pushed"] = []
+            for st in (peer["stream"], peer["stream2"]):
+                ev = torch.cuda.Event()
+                ev.record(st)
+                peer["pushed"].append(ev)
+                epoch_t.record_stream(st)
+            _mark("pushed", peer["stream"])
+            _mark("pushed2", peer["stream2"])
             flags_ptr = arena.data_ptr() + peer["offs"]["flags"]
             n = rows.shape[1]
             store_mirror = os.environ.get("B200SQ_DIST_MIRROR", "store").lower() != "nccl"

@@ -2,7 +2,7 @@
 every phase mark records a CUDA event on the stream that carries the phase (main, push or conversion stream) plus
 the host clock; after the step the event times (relative to the step's first event) and the host issue times are
 printed for every rank.  usage: torchrun ... tools/dist_timeline.py   (QUBITS / POINTS from the environment;
-VARIANTS="1:full,4:full,4:slice" runs several settings of B200SQ_DIST_SUBBLOCKS:B200SQ_DIST_PIPELINE[:exchange]
+VARIANTS="1:full,4:full,4:slice" runs several settings of B200SQ_DIST_SUBBLOCKS:B200SQ_DIST_PIPELINE[:exchange[:order[:push streams]]]
 in one process group)"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,6 +30,8 @@ for variant in os.environ.get("VARIANTS", "").split(",") if os.environ.get("VARI
         os.environ["B200SQ_DIST_SUBBLOCKS"] = f[0]
         os.environ["B200SQ_DIST_PIPELINE"] = f[1] if len(f) > 1 else "full"
         os.environ["B200SQ_DIST_CRT_EXCHANGE"] = f[2] if len(f) > 2 else "auto"
+        os.environ["B200SQ_DIST_ORDER"] = f[3] if len(f) > 3 else "narrow"
+        os.environ["B200SQ_DIST_PUSH_STREAMS"] = f[4] if len(f) > 4 else "1"
     sh = D.ShardedFidelityKernel(fk)
     out, totals = None, []
     for it in range(6):
@@ -46,13 +48,20 @@ for variant in os.environ.get("VARIANTS", "").split(",") if os.environ.get("VARI
         out = {"rank": rank, "host_total_ms": totals[-1],
                "marks": [(nm, round((t - t0) * 1e3, 2), round(e0.elapsed_time(ev), 2)) for nm, t, ev in marks]}
     out["totals_ms"] = totals
+    # parity of this variant's result: 64 local rows x 128 columns spread over all ranks vs the FP64 DMMA Gram
+    r0 = D.row_partition(N, world)[rank][0]
+    idx = np.arange(5, N, N // 128)[:128]
+    k64 = ex.engine.gram(fk.states(X[r0:r0 + 64]), fk.states(X[idx]), precision="fp64")
+    out["max_err_vs_fp64"] = float((rows[:64][:, torch.as_tensor(idx, device=dev)] - k64).abs().max())
+    assert out["max_err_vs_fp64"] < 1e-10, out["max_err_vs_fp64"]
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
         print(f"# variant '{variant}' world {world}: (phase, host issue time ms, GPU completion time ms) of the last of 6 steps")
         for g in gathered[:2] + gathered[-1:]:
             print(json.dumps(g))
-        print("# step totals (ms) per rank:", [g["totals_ms"][2:] for g in gathered][:3], flush=True)
+        print("# step totals (ms) per rank:", [g["totals_ms"][2:] for g in gathered][:3],
+              "max |K - K_fp64| over ranks: %.2e" % max(g["max_err_vs_fp64"] for g in gathered), flush=True)
     del sh
     torch.cuda.synchronize(dev)
     dist.barrier()
