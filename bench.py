@@ -295,17 +295,30 @@ def run_gpu_arm(args):
     x_dev = torch.from_numpy(X).to(dev)
     k_buf = torch.empty((n_points, n_points), dtype=torch.float64, device=dev) if not multi else None
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    gate_ms, gram_ms = [], []
+    gate_ms, gram_ms, slice_ms = [], [], []
+    scheme = eng.gram_precision(n_points, n_points, dim)
+    # INT8 paths: the step goes through the plane interface of the C ABI (b200sq_gram_slice_* + b200sq_gram_from_planes:
+    # exactly the kernels b200sq_gram launches, with the planes allocated once), so that the slicing kernel and the
+    # tcgen05 kernel are timed separately with CUDA events inside the timed region
+    planes = expo = None
+    if not multi and scheme in ("int8", "crt"):
+        _, planes, expo = eng.alloc_plane_block(n_points, dim, scheme)
 
     def step_single(record=False):
-        e0, e1, e2 = ev(), ev(), ev()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         psi = eng.simulate(cprog, x_dev)
         e1.record()
-        eng.gram(psi, None, diagonal="one", out=k_buf)
-        e2.record()
+        if planes is not None:
+            eng.slice_states(psi, planes, expo, 0, scheme)
+            e2.record()
+            eng.gram_from_planes(planes, expo, 0, n_points, diagonal="one", out=k_buf, scheme=scheme)
+        else:
+            e2.record()
+            eng.gram(psi, None, diagonal="one", out=k_buf)
+        e3.record()
         if record:
-            return (e0, e1, e2)
+            return (e0, e1, e2, e3)
         return None
 
     def step_multi(record=False):
@@ -350,7 +363,8 @@ def run_gpu_arm(args):
     for r in recs:
         if r is not None:
             gate_ms.append(r[0].elapsed_time(r[1]))
-            gram_ms.append(r[1].elapsed_time(r[2]))
+            slice_ms.append(r[1].elapsed_time(r[2]))
+            gram_ms.append(r[2].elapsed_time(r[3]))
 
     # ---- end to end through the public API (host x -> host K)
     e2e_steps = max(2, min(args.steps, 5))
@@ -400,7 +414,6 @@ def run_gpu_arm(args):
         del psi_chk
 
     line = None
-    scheme = eng.gram_precision(n_points, n_points, dim)
     dtype_str = {"int8": "f64 (complex128 states; Gram via exact int8 slices of a 47-bit fixed-point split, FP64 recombination)",
                  "crt": "f64 (complex128 states; Gram via exact int8 residue products of a 44-bit fixed-point split "
                         "relative to the row norm, CRT reconstruction in double-double)"}.get(scheme, "f64 (complex128)")
@@ -447,14 +460,15 @@ def run_gpu_arm(args):
                 fp64_equiv = 8.0 * dim * (n_points * (n_points + 1) / 2) / (g_ms * 1e-3) / 1e12
                 line["roofline"] = {
                     "kernel": "k_gram_i8<2> (tcgen05.mma kind::i8 on CTA pairs, TMA operands, TMEM s32 accumulators) "
-                              + ("+ k_slice_i8 + k_gram_i8_final" if scheme == "int8" else
-                                 "+ k_slice_crt + k_gram_crt_final (CRT reconstruction)"), "bound": "tensor",
+                              + ("+ k_gram_i8_final" if scheme == "int8" else
+                                 "+ k_gram_crt_final8 (CRT reconstruction, 2 % of the duration)"), "bound": "tensor",
                     "achieved": achieved, "peak": i8_peak, "unit": "TFLOP/s", "frac": achieved / i8_peak,
                     "traffic": traffic.get("k_gram_i8"), "ms_per_launch": g_ms,
                     "algorithmic": f"split-integer FP64 emulation ({'digit slices' if scheme == 'int8' else 'residues modulo ' + str(pairs) + ' coprime moduli'}): {pairs} int8 plane pairs x 2 (Re, Im) x 2*2^n "
                                    f"multiply-adds per entry x {entries_computed} entries computed ({tiles} "
-                                   f"lower-triangle 256x256 tiles); the duration is the whole b200sq_gram call "
-                                   f"(digit slicing, memset, tcgen05 kernel, |.|^2 kernel)",
+                                   f"lower-triangle 256x256 tiles); the duration is b200sq_gram_from_planes "
+                                   f"(tcgen05 kernel + reconstruction / |.|^2 kernel) between CUDA events of the timed steps; "
+                                   f"the slicing kernel is timed separately (roofline_slice)",
                     "peak_source": ("profiles/r2_i8_peak_probe.json: dense tcgen05.mma.cta_group::2.kind::i8 M=N=256 K=32 on "
                                     "all 74 SM pairs, SMEM-resident pseudo-random operands (tools/i8_peak_probe.cu), "
                                     "SUSTAINED over 4 s under the power cap; MEASURED_PEAKS.json has no INT8 figure")
@@ -466,6 +480,18 @@ def run_gpu_arm(args):
                                             f"distinct entries; measured FP64 DGEMM peak here {fp64_peak:.1f} TFLOP/s",
                     "frac_of_fp64_tensor_peak": fp64_equiv / fp64_peak,
                     "share_of_step": g_ms / ms_per_step,
+                }
+                s_ms = float(np.mean(slice_ms))
+                hbm_gbs = float(peaks.get("hbm_gbs", 6650.0))
+                slice_bytes = (16.0 + 4.0 * (pairs if scheme == "crt" else 6)) * n_points * dim
+                line["roofline_slice"] = {
+                    "kernel": "k_slice_crt" if scheme == "crt" else "k_slice_i8", "bound": "hbm",
+                    "achieved": slice_bytes / (s_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                    "frac": slice_bytes / (s_ms * 1e-3) / 1e9 / hbm_gbs, "traffic": traffic.get("k_slice"),
+                    "ms_per_launch": s_ms, "share_of_step": s_ms / ms_per_step,
+                    "algorithmic": "16 bytes read per amplitude (the row statistics come from the last gate pass: one "
+                                   "read) + 2 operand halves x planes x 2 int8 written per amplitude",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs",
                 }
             else:
                 mode_4m = os.environ.get("B200SQ_GRAM_MODE", "3m").lower() == "4m"

@@ -29,7 +29,10 @@ import numpy as np
 # one push per block).
 _DEFAULT_SUBBLOCKS = 1
 _DEFAULT_PUSH_STREAMS = "1"
-_DEFAULT_ORDER = "narrow"   # order of the exchanged blocks: "narrow" (narrowest block first) or "ring" (nearest owner first)
+# Order of the exchanged blocks: "ring" (nearest owner first) or "narrow" (narrowest block first); a second push stream
+# (B200SQ_DIST_PUSH_STREAMS=2) sends alternate blocks concurrently.  Measured on 4 / 8 GPUs
+# (profiles/r2_timeline_n{4,8}_order.log): ring + one stream 8.9 / 5.75 ms, narrow 10.9 / 7.4 ms, two streams 10.7 / 7.3 ms.
+_DEFAULT_ORDER = "ring"
 _DEFAULT_PIPELINE = "full"
 
 
@@ -100,9 +103,9 @@ def ring_distance(rank: int, owner: int, world: int) -> int:
 
 
 def remote_jobs(jobs: List[List[dict]], rank: int, world: int) -> List[dict]:
-    """The off-diagonal jobs of ``rank`` in the order their column planes arrive: the narrowest block first (the
-    half of an antipodal block lands in half the time, so the Gram kernel has work right after its diagonal block),
-    then nearest owner first (every rank pushes its planes in the same order: see ``_job_order``)."""
+    """The off-diagonal jobs of ``rank`` in the order their column planes arrive: nearest owner first (every rank
+    pushes its planes to rank-1, rank-2, ... in that order, so the block a rank needs first lands first; see
+    ``_job_order`` for the measured alternative)."""
     mine = [j for j in jobs[rank] if not j["diag"]]
     mine.sort(key=lambda j: _job_order(j, rank, world))
     return mine

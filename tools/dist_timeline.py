@@ -30,7 +30,7 @@ for variant in os.environ.get("VARIANTS", "").split(",") if os.environ.get("VARI
         os.environ["B200SQ_DIST_SUBBLOCKS"] = f[0]
         os.environ["B200SQ_DIST_PIPELINE"] = f[1] if len(f) > 1 else "full"
         os.environ["B200SQ_DIST_CRT_EXCHANGE"] = f[2] if len(f) > 2 else "auto"
-        os.environ["B200SQ_DIST_ORDER"] = f[3] if len(f) > 3 else "narrow"
+        os.environ["B200SQ_DIST_ORDER"] = f[3] if len(f) > 3 else "ring"
         os.environ["B200SQ_DIST_PUSH_STREAMS"] = f[4] if len(f) > 4 else "1"
     sh = D.ShardedFidelityKernel(fk)
     out, totals = None, []
