@@ -50,7 +50,7 @@ def config_dict(args, n_gpus):
         "workload": f"FidelityKernel Gram, ChebyshevPQC({args.qubits} qubits, 2 layers), "
                     f"N={args.points}, d=4 (BASELINE configs[{4 if args.qubits >= 20 else 2}])",
         "n_qubits": args.qubits, "n_points": args.points, "n_gates": 6 * args.qubits,
-        "sharding": "single GPU" if n_gpus == 1 else f"row blocks over {n_gpus} ranks; symmetric half-ring of Gram blocks; the 6 int8 nat digit planes of the needed row blocks are pushed peer-to-peer by the copy engines over NVLink (CUDA IPC) and multiplied as they land by one job-table Gram launch per rank (NCCL for the mirror exchange and barriers)",
+        "sharding": "single GPU" if n_gpus == 1 else f"row blocks over {n_gpus} ranks; symmetric half-ring of Gram blocks; the int8 nat planes of the needed row blocks (CRT arithmetic: the residue planes; digit form: the 6 digit planes) are pushed peer-to-peer by the copy engines over NVLink (CUDA IPC) and multiplied as they land by one job-table Gram launch per rank, whose epilogue stores the mirrored blocks into the owners' row blocks (NCCL only for barriers)",
         "l2_policy": "inputs larger than L2 (statevector batch 16*N*2^n bytes >> 126 MB)",
     }
 
