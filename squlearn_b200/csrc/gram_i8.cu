@@ -70,7 +70,9 @@ constexpr int kStageBytes = 3 * kTileBytes;      // A, Bnat, Brot
 constexpr int kStages = 4;
 constexpr int kChunkK = 16384;                   // bytes of K per int32 accumulation chunk
 constexpr int kMaxClasses = 16, kMaxPairs = 8;
-constexpr int kCrtMaxBits = 45;                   // upper limit of B: |q| < 2^46 fits the 6 balanced base-256 exchange digits
+constexpr int kCrtMaxBits = 46;                   // upper limit of B
+constexpr double kCrtMaxLog2R = 46.9;             // upper limit of the scaled row norm: |q| <= 2^46.9 fits the 6 balanced
+                                                  // base-256 exchange digits (top digit <= 120) and is exact in a double
 constexpr int kCrtMaxModuli = 16;
 // pairwise coprime moduli (256; 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime): symmetric
 // residues fit int8 (256: -128 stands for +-128), and 127^2 * 2^17 < 2^31 keeps a whole 128 KiB K chunk exact in int32
@@ -1208,8 +1210,9 @@ static CrtPlan crt_plan(int64_t dim) {
     for (int s = 1; s <= kCrtMaxModuli; ++s) {
         P *= (long double)h_crt_moduli[s - 1];
         // every component of q is off by at most 1/2 (rounding): |q|_2 <= 2^(B - e) |x|_2 + sqrt(K') / 2
-        const long double r_eff = sqrtl(P / 2.0L) - 0.5L * sqrtl((long double)kp) - 1.0L;
+        long double r_eff = sqrtl(P / 2.0L) - 0.5L * sqrtl((long double)kp) - 1.0L;
         if (r_eff < 2.0L) continue;
+        r_eff = std::min(r_eff, powl(2.0L, (long double)kCrtMaxLog2R));
         const int bits = std::min((int)floorl(log2l(r_eff)), kCrtMaxBits);
         if (bits >= need || (s == kCrtMaxModuli && bits >= 30)) {
             pl.n_mod = s;

@@ -127,7 +127,8 @@ def i8_gram(planes_x, expo_x, planes_y, expo_y):
 # 2^(B - e) |row|_2 <= R_eff ~ sqrt(P / 2) (Cauchy-Schwarz keeps every inner product below P / 2), one exact integer
 # product per modulus, Chinese remainder reconstruction with the kernel's double-double accumulation of k_m / p_m.
 CRT_MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193]
-CRT_MAX_BITS = 45
+CRT_MAX_BITS = 46
+CRT_MAX_LOG2R = 46.9
 CRT_TOL = 1e-10
 
 
@@ -144,7 +145,7 @@ def crt_plan(dim):
         r_eff = (Decimal(big) / 2).sqrt() - Decimal("0.5") * Decimal(kp).sqrt() - 1
         if r_eff < 2:
             continue
-        log2r = float(r_eff.ln() / Decimal(2).ln())
+        log2r = min(float(r_eff.ln() / Decimal(2).ln()), CRT_MAX_LOG2R)
         bits = min(int(np.floor(log2r)), CRT_MAX_BITS)
         if bits >= need or (s_ == len(CRT_MODULI) and bits >= 30):
             return s_, bits, bits - log2r

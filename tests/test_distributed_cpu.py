@@ -265,7 +265,7 @@ def test_crt_scheme_error_on_circuit_states():
     from tests.helpers import crt_plan
 
     assert [crt_num_moduli(1 << n) for n in (6, 12, 16, 20)] == [10, 11, 11, 12]
-    assert [crt_plan(1 << n)[1] for n in (6, 12, 16, 20)] == [39, 43, 43, 45]
+    assert [crt_plan(1 << n)[1] for n in (6, 12, 16, 20)] == [39, 43, 43, 46]
     for n_ in (6, 12, 16, 18, 20):
         assert 2.0 * np.sqrt(2.0 ** (n_ + 1)) * 2.0 ** -crt_plan(1 << n_)[1] <= 1e-10
     n = 10
