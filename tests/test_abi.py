@@ -97,3 +97,25 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert not re.search(r"^\s*(from|import)\s+tests\b", src, re.M), f
+
+
+def test_crt_plan_of_the_library_equals_the_restatement():
+    """The host-side CRT plan (number of moduli and bits per state dimension, gram_i8.cu: crt_plan) equals the NumPy
+    restatement the CPU error tests use (tests/helpers.py), for every dimension the INT8 Gram supports; the worst-case
+    bound 2 sqrt(K') 2^-B of a unit-norm entry stays below 1e-10 wherever the moduli suffice."""
+    from tests.helpers import crt_plan
+
+    lib = _lib.load()
+    for n in range(6, 23):
+        s_, bits, _ = crt_plan(1 << n)
+        assert lib.b200sq_gram_crt_moduli(1 << n) == s_, n
+        assert lib.b200sq_gram_crt_bits(1 << n) == bits, n
+        assert 2.0 * np.sqrt(2.0 ** (n + 1)) * 2.0 ** -bits <= 1e-10, n
+    assert lib.b200sq_gram_crt_moduli(32) == 0          # below the smallest supported dimension
+    assert (lib.b200sq_gram_crt_moduli(1 << 16), lib.b200sq_gram_crt_bits(1 << 16)) == (11, 43)   # BASELINE configs[2]
+
+
+def test_row_stats_struct_layout():
+    text = open(os.path.join(ROOT, "include", "b200sq.h")).read()
+    body = re.search(r"typedef struct b200sq_row_stats \{(.*?)\} b200sq_row_stats;", text, re.S).group(1)
+    assert [w for w in re.findall(r"(\w+);", body)] == ["norm2", "max_hi", "reserved"]
