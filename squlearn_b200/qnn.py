@@ -39,7 +39,7 @@ _DIRECT = {"f", "fcc", "dfdp", "dfccdp", "dfdop", "dfccdop", "dfdx", "dfccdx",
            # "dfdpdx" -> (..., P, d) (the reference reorders its nested jacobians the same way,
            # lowlevel_qnn_pennylane.py:331-338)
            "dfdxdx", "dfdpdp", "dfdpdx", "dfdxdp", "dfccdxdx", "dfccdpdp",
-           "dfdopdx", "dfdopdp", "dfdpdop", "dfdopdop", "dfdopdxdx"}
+           "dfdopdx", "dfdopdp", "dfdpdop", "dfdopdop", "dfdopdxdx", "dfccdopdx", "dfccdopdop"}
 _SECOND = {"dfdxdx": ("x", "x"), "dfdpdp": ("param", "param"), "dfdpdx": ("param", "x"), "dfdxdp": ("x", "param"),
            "dfccdxdx": ("x", "x"), "dfccdpdp": ("param", "param")}
 _POST = {
@@ -50,7 +50,7 @@ _POST = {
     "laplace": ("dfdxdx",), "laplace_dop": ("dfdopdxdx",),
 }
 # third order in the circuit angles (and the Fisher matrix): not offered
-_NOT_YET = {"laplace_dp", "dfdxdxdp", "dfdxdpdx", "dfdpdxdx", "dfccdopdx", "dfccdopdop", "fischer"}
+_NOT_YET = {"laplace_dp", "dfdxdxdp", "dfdxdpdx", "dfdpdxdx", "fischer"}
 
 
 class LowLevelQNN:
@@ -148,6 +148,35 @@ class LowLevelQNN:
                 fm = ex.b200_execute(b200_evaluate, self._circuit, squared=True, param=p, x=x_inp,
                                      param_obs=pobs - e)
                 out[:, :, j] = 0.5 * (fp - fm)
+            return out
+        if key == "dfccdopdx":
+            # d/dx of d<O^2>/d op_j (evaluation_classes.py:177-185): <O^2> is quadratic in param_obs, so the symmetric
+            # difference of its x-gradient over param_obs is exact -> (N, n_obs, P_op, d)
+            out = np.zeros((x_inp.shape[0], self.num_operator, len(pobs), self._num_features))
+            for j in range(len(pobs)):
+                e = np.zeros(len(pobs))
+                e[j] = 1.0
+                gp = ex.b200_execute(b200_gradient, self._circuit, squared=True, wrt="x", param=p, x=x_inp,
+                                     param_obs=pobs + e)
+                gm = ex.b200_execute(b200_gradient, self._circuit, squared=True, wrt="x", param=p, x=x_inp,
+                                     param_obs=pobs - e)
+                out[:, :, j, :] = 0.5 * (gp - gm)
+            return out
+        if key == "dfccdopdop":
+            # Hessian of the quadratic <O^2> in param_obs (evaluation_classes.py:190-193): second differences with
+            # unit steps are exact -> (N, n_obs, P_op, P_op)
+            npo = len(pobs)
+            f = lambda q: ex.b200_execute(b200_evaluate, self._circuit, squared=True, param=p, x=x_inp, param_obs=q)
+            f0 = f(pobs)
+            unit = np.eye(npo)
+            plus = [f(pobs + unit[j]) for j in range(npo)]
+            minus = [f(pobs - unit[j]) for j in range(npo)]
+            out = np.zeros((x_inp.shape[0], self.num_operator, npo, npo))
+            for j in range(npo):
+                out[:, :, j, j] = plus[j] - 2.0 * f0 + minus[j]
+                for k in range(j):
+                    # f(+j+k) - f(+j) - f(+k) + f(0) is the mixed term of a quadratic exactly
+                    out[:, :, j, k] = out[:, :, k, j] = f(pobs + unit[j] + unit[k]) - plus[j] - plus[k] + f0
             return out
         raise ValueError("Unknown input string:", key)
 

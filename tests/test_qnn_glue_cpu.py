@@ -77,3 +77,32 @@ def test_dfdx_shapes_multi_output_and_linear_encoding():
     assert single.shape == (2, d) and np.allclose(single, r["dfdx"][0])
     with pytest.raises(NotImplementedError):
         qnn.evaluate(X, p, [], "dfdxdxdp")
+
+
+def test_squared_operator_second_derivatives_in_the_operator_parameters():
+    """"dfccdopdop" and "dfccdopdx" (evaluation_classes.py:177-193): <O^2> is a quadratic form in the observable
+    parameters, so its Hessian is constant in them, symmetric, and reproduces <O^2> and "dfccdop" exactly; the mixed
+    derivative is checked against central differences of "dfccdop" in x."""
+    n, d, N = 3, 2, 4
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-0.8, 0.8, (N, d))
+    enc = sq.ChebyshevPQC(n, 1)
+    p = rng.uniform(-1, 1, enc.num_parameters)
+    pop = rng.uniform(-1, 1, n + 1)
+    qnn = sq.LowLevelQNN(enc, sq.SummedPaulis(n), EmuExecutor(), d, caching=False)
+    r = qnn.evaluate(X, p, pop, "fcc", "dfccdop", "dfccdopdop", "dfccdopdx")
+    hess = r["dfccdopdop"]
+    assert hess.shape == (N, n + 1, n + 1) and np.allclose(hess, np.swapaxes(hess, -1, -2))
+    # quadratic form: <O^2>(c) = 1/2 c^T H c and grad = H c
+    assert np.max(np.abs(0.5 * np.einsum("j,njk,k->n", pop, hess, pop) - r["fcc"])) < 1e-11
+    assert np.max(np.abs(np.einsum("njk,k->nj", hess, pop) - r["dfccdop"])) < 1e-11
+    pop2 = rng.uniform(-1, 1, n + 1)
+    assert np.max(np.abs(qnn.evaluate(X, p, pop2, "dfccdopdop")["dfccdopdop"] - hess)) < 1e-11
+    mixed = r["dfccdopdx"]
+    assert mixed.shape == (N, n + 1, d)
+    h = 1e-6
+    for j in range(d):
+        e = np.zeros(d)
+        e[j] = h
+        fd = (qnn.evaluate(X + e, p, pop, "dfccdop")["dfccdop"] - qnn.evaluate(X - e, p, pop, "dfccdop")["dfccdop"]) / (2 * h)
+        assert np.max(np.abs(mixed[:, :, j] - fd)) < 1e-7
