@@ -92,8 +92,9 @@ typedef struct b200sq_program b200sq_program;
                                    /* DESIGN.md); needs dim >= 64, otherwise the FP64 path runs   */
 
 #define B200SQ_GRAM_CRT 64u        /* with B200SQ_GRAM_INT8: the residue-number ("Ozaki II") form of the scheme:  */
-                                   /* 41-bit fixed point per row, one int8 product per modulus (13 for 2^16        */
-                                   /* amplitudes) and a CRT reconstruction instead of 22 digit-pair products       */
+                                   /* fixed point relative to the row 2-norm (44 bits at 2^16 amplitudes), one     */
+                                   /* int8 product per modulus (11 there) and a CRT reconstruction instead of 22   */
+                                   /* digit-pair products; worst-case |dK| <= 2 sqrt(2 dim) 2^-B (b200sq_gram_crt_bits) */
 
 #if !defined(__CUDACC_RTC__) /* host entry points: invisible to the run-time compiled device code */
 
@@ -228,15 +229,15 @@ B200SQ_API int b200sq_gram_slice_crt(const void* psi_dev, int64_t N, int64_t dim
                                      int64_t plane_rows, int64_t row0, int32_t* expo_dev,
                                      const b200sq_row_stats* row_stats_dev, void* stream);
 
-/* b200sq_gram_slice_crt that also writes the 6 nat DIGIT planes ([6][digit_rows][2 * dim]: what the multi-GPU
- * exchange sends) from the same read of the states; the residues are then those b200sq_gram_digits_to_crt derives
- * from these digits, so sender and receivers hold identical integers for a state.                        */
+/* b200sq_gram_slice_crt that also writes the 6 nat DIGIT planes ([6][digit_rows][2 * dim]: the compact exchange
+ * format, 6 instead of s bytes per component) from the same read of the states: the balanced base-256 digits of the
+ * CRT integers themselves, so the residues b200sq_gram_digits_to_crt derives from them are the sender's.     */
 B200SQ_API int b200sq_gram_slice_crt_digits(const void* psi_dev, int64_t N, int64_t dim, void* planes_dev,
                                             int64_t plane_rows, int64_t row0, int32_t* expo_dev,
                                             const b200sq_row_stats* row_stats_dev, void* digit_planes_dev, int64_t digit_rows,
                                             int64_t digit_row0, void* stream);
 
-/* Residue planes of a COLUMN block from its 6 nat digit planes (what the multi-GPU exchange delivers: 6 instead of
+/* Residue planes of a COLUMN block from its 6 nat digit planes (what a digit exchange delivers: 6 instead of
  * s bytes per component): rows [row0_d, row0_d + N) of digit planes [>= 6][plane_rows_d][2 * dim] ->
  * rows [row0_o, row0_o + N) of residue planes [s][plane_rows_o][2 * dim] (nat residues only; the row exponents of
  * the digit planes stay valid).                                                                          */

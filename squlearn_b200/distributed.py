@@ -178,8 +178,9 @@ class ShardedFidelityKernel:
 
     INT8 (digit-plane) path, exchange modes (``B200SQ_DIST_EXCHANGE``):
 
-    * ``ipc`` (default on CUDA): every rank PUSHES the 6 nat planes of its row block into the receive arenas of
-      the ranks that need them with copy-engine copies over NVLink (CUDA IPC mappings; no SM is spent on the
+    * ``ipc`` (default on CUDA): every rank PUSHES the nat planes of its row block (CRT arithmetic: the s residue
+      planes; digit form: the 6 digit planes) into the receive arenas of the ranks that need them with copy-engine
+      copies over NVLink (CUDA IPC mappings; no SM is spent on the
       exchange) and then writes an epoch flag; the receiver's single job-table Gram launch multiplies each
       block as soon as its flag is visible (``b200sq_gram_jobs``), so the exchange hides behind the diagonal
       block and the earlier blocks.
@@ -307,10 +308,8 @@ class ShardedFidelityKernel:
         nat_bytes = 6 * n_local * 2 * dim
         mode = self._exchange_mode(eng, equal, n_local, nat_bytes + 4 * n_local)
 
-        # Arithmetic of the blocks: digit slices ("int8") or residues ("crt": fewer tensor-core products).  Either
-        # way the 6 nat DIGIT planes travel (6 bytes per component; 13 residue planes would more than double the
-        # exchange): with "crt" every rank turns its own states into residue planes directly and each received block
-        # with digits_to_crt, on a side stream, as the block lands.
+        # Arithmetic of the blocks: digit slices ("int8": the 6 nat digit planes travel) or residues ("crt": fewer
+        # tensor-core products; every rank turns its own states into residue planes directly).
         scheme = eng.gram_precision(parts[-1][1], parts[-1][1], dim, self.precision)
         crt = scheme == "crt" and hasattr(eng, "digits_to_crt")
         # CRT + ipc: by default the s nat RESIDUE planes travel instead of the 6 digit planes.  That is s / 6 times the
@@ -323,7 +322,7 @@ class ShardedFidelityKernel:
             raise ValueError("B200SQ_DIST_CRT_EXCHANGE must be auto, digits or residues")
         residues = crt and mode == "ipc" and xch != "digits"
         n_xch = eng.plane_count(dim, "crt") if residues else 6
-        if crt:   # residue planes for the local rows + their 6 nat digit planes for the exchange, from ONE read
+        if crt:   # residue planes for the local rows (+ with the digit exchange their 6 nat digit planes, from ONE read)
             _, a_planes, a_expo = self._plane_block(eng, "local_crt", n_local, dim, "crt")
             if residues:
                 buf_local, planes, expo = None, a_planes, a_expo
