@@ -137,7 +137,13 @@ class KernelMatrixBase:
 
 
 class FidelityKernel(KernelMatrixBase):
-    """K_ij = |<psi(x_i)|psi(y_j)>|^2 evaluated on the B200 engine."""
+    """K_ij = |<psi(x_i)|psi(y_j)>|^2 evaluated on the B200 engine
+    (kernel/lowlevel_kernel/fidelity_kernel.py:353-415 -> fidelity_kernel_statevector.py:284-387).
+
+    Arithmetic of the Gram: small problems run FP64 DMMA; from 2^12 amplitudes and 1024 x 512 entries on the engine's
+    ``precision="auto"`` policy uses the exact split-integer emulation on the INT8 tensor cores (worst-case
+    |dK| <= 2 sqrt(2 * 2^n) 2^-B < 1e-10, measured ~1e-13: DESIGN.md 4.2).  ``B200SQ_GRAM_PRECISION=fp64`` keeps FP64
+    DMMA everywhere."""
 
     def __init__(self, encoding_circuit, executor: Executor,
                  evaluate_duplicates: str = "off_diagonal", mit_depol_noise: Union[str, None] = None,
